@@ -1,0 +1,218 @@
+/*
+ * mmemo.h — C ABI of libmmemo.so, the B200 (sm_100a) hot path of
+ * youngzhou97qz/Multimodal-emotion-processing.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; its drop-in boundary is the set
+ * of nn.Module forwards listed in SURVEY.md §8(b).  Each entry point below replaces the eager
+ * ATen op sequence of one reference code span (cited per function, paths relative to the reference
+ * root).  The Python host (multimodal-emotion-processing_b200/ops.py) binds these with ctypes and
+ * registers them as torch custom ops; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the comment says "host"; buffers are owned by the
+ *     caller; nothing here allocates, synchronises or keeps global state; all work is enqueued on
+ *     `stream` (a cudaStream_t passed as void*).
+ *   - return 0 on success, <0 on error (MMEMO_ERR_*).  No CPU fallback exists.
+ *   - suffix _f32 / _bf16 = dtype of ACTIVATIONS and GEMM weights (T).  Small parameter vectors
+ *     (bias, LayerNorm gamma/beta, gates a/b/c, position tables) and ALL parameter gradients are
+ *     float32 in both modes; accumulation is always float32.
+ *   - "ld*" = leading dimension (row stride, in elements) of a row-major matrix.
+ *   - outputs marked "+=" are accumulated into (caller zero-initialises).
+ */
+#ifndef MMEMO_H_
+#define MMEMO_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMEMO_OK 0
+#define MMEMO_ERR_ARG (-1)   /* null / inconsistent argument                         */
+#define MMEMO_ERR_SHAPE (-2) /* shape outside what the kernels support (see DESIGN)  */
+#define MMEMO_ERR_CUDA (-3)  /* a CUDA runtime / driver call failed                  */
+
+typedef void* mmemo_stream_t; /* cudaStream_t */
+
+/* library / device info */
+int mmemo_version(void);
+const char* mmemo_last_error(void); /* host string describing the last MMEMO_ERR_CUDA */
+/* 1 if (M,N,K,mode) is served by the tcgen05/TMA tensor-core GEMM, 0 if by the SIMT GEMM */
+int mmemo_gemm_uses_tensor_cores(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                                 int64_t ldc, int mode);
+
+/* ---------------------------------------------------------------------------------------------
+ * Linear / Conv1d(k=1) layers.  Replaces nn.Linear / nn.Conv1d(kernel_size=1) calls:
+ *   others/realformer.py:140-143,188,204,163-168,263,277   cmu-mosei/run.py:213-214,257,261,319
+ *   Ren-MME/run.py:165-166,209,213,271   rencecps/run.py:139-140   robot_demo.py:302-311,353,369,441
+ * fwd : y[M,N] (+)= act( x[M,K] . w[N,K]^T + bias[N] + pos[m % pos_period, N] )
+ *       x may be float32 even in the _bf16 build (x_is_f32=1: raw input features).
+ *       pos: learned position table (others/realformer.py:145-152,225-227) fused as a periodic bias.
+ * bwd_x: dx[M,K] (+)= ( dy[M,N] . w[N,K] ) * (relu_src[M,K] > 0)
+ * bwd_w: dw[N,K] (+)= dy[M,N]^T . x[M,K]  (float32 out);  dbias[N] += colsum(dy) if non-null.
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_linear_fwd_f32(const void* x, int x_is_f32, int64_t ldx, const void* w, int64_t ldw,
+                         const float* bias, const float* pos, int64_t pos_period, void* y,
+                         int64_t ldy, int64_t M, int64_t N, int64_t K, int relu, int accumulate,
+                         mmemo_stream_t stream);
+int mmemo_linear_fwd_bf16(const void* x, int x_is_f32, int64_t ldx, const void* w, int64_t ldw,
+                          const float* bias, const float* pos, int64_t pos_period, void* y,
+                          int64_t ldy, int64_t M, int64_t N, int64_t K, int relu, int accumulate,
+                          mmemo_stream_t stream);
+int mmemo_linear_bwd_x_f32(const void* dy, int64_t lddy, const void* w, int64_t ldw, void* dx,
+                           int64_t lddx, const void* relu_src, int64_t ldrelu, int64_t M, int64_t N,
+                           int64_t K, int accumulate, mmemo_stream_t stream);
+int mmemo_linear_bwd_x_bf16(const void* dy, int64_t lddy, const void* w, int64_t ldw, void* dx,
+                            int64_t lddx, const void* relu_src, int64_t ldrelu, int64_t M,
+                            int64_t N, int64_t K, int accumulate, mmemo_stream_t stream);
+int mmemo_linear_bwd_w_f32(const void* dy, int64_t lddy, const void* x, int x_is_f32, int64_t ldx,
+                           float* dw, int64_t lddw, float* dbias, int64_t M, int64_t N, int64_t K,
+                           int accumulate, mmemo_stream_t stream);
+int mmemo_linear_bwd_w_bf16(const void* dy, int64_t lddy, const void* x, int x_is_f32, int64_t ldx,
+                            float* dw, int64_t lddw, float* dbias, int64_t M, int64_t N, int64_t K,
+                            int accumulate, mmemo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused residual-attention core (kernel a / a').  Replaces
+ *   others/realformer.py:189-203  cmu-mosei/run.py:242-256  Ren-MME/run.py:194-208
+ *   robot_demo.py:354-368
+ * q (B,Lq,H*hd) row stride ldq; k, v (B,Lk,H*hd); head h lives in columns [h*hd,(h+1)*hd).
+ * mask: float 0/1, element (b,i,j) at mask[b*mask_bs + i*mask_rs + j]  ((B,Lk): mask_rs = 0).
+ * S = q_h k_h^T / sqrt(hd) + c*S_prev - 1e8*(1-mask)   (fp32 op order of the reference)
+ * s_out (B,H,Lq,Lk) receives S (post-mask, pre-softmax; what the reference returns); may be null
+ * when no later layer / backward needs it.  o (B,Lq,H*hd) = merge_heads(softmax(S) v_h).
+ * lse (B,H,Lq,2) float32 = (row max, row sum of exp(S - max)) saved for backward; kept as a pair
+ * because a fully masked row has max = -1e8, where max + log(sum) is absorbed by fp32 rounding.
+ * bwd: dS = P*(dP - rowsum(dO*O)) + dS_next; dq = dS k / sqrt(hd); dk = dS^T q / sqrt(hd);
+ *      dv = P^T dO; dc += sum(dS*S_prev); ds_prev = c*dS.   s == null -> scores are recomputed
+ *      (only legal when s_prev == null).  dq_ws: float32 (B,Lq,H*hd) scratch, needed for the _bf16
+ *      build when Lk > 128 (may be null otherwise).
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_resattn_fwd_f32(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                          int64_t ldv, const float* mask, int64_t mask_bs, int64_t mask_rs,
+                          const void* s_prev, const float* c, void* s_out, void* o, int64_t ldo,
+                          float* lse, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t hd,
+                          mmemo_stream_t stream);
+int mmemo_resattn_fwd_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                           int64_t ldv, const float* mask, int64_t mask_bs, int64_t mask_rs,
+                           const void* s_prev, const float* c, void* s_out, void* o, int64_t ldo,
+                           float* lse, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t hd,
+                           mmemo_stream_t stream);
+int mmemo_resattn_bwd_f32(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k,
+                          int64_t ldk, const void* v, int64_t ldv, const float* mask,
+                          int64_t mask_bs, int64_t mask_rs, const void* s, const void* s_prev,
+                          const float* c, const void* ds_next, const void* o, int64_t ldo,
+                          const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk,
+                          void* dv, int64_t lddv, void* ds_prev, float* dc, float* dq_ws, int64_t B,
+                          int64_t H, int64_t Lq, int64_t Lk, int64_t hd, mmemo_stream_t stream);
+int mmemo_resattn_bwd_bf16(const void* d_o, int64_t lddo, const void* q, int64_t ldq,
+                           const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           const float* mask, int64_t mask_bs, int64_t mask_rs, const void* s,
+                           const void* s_prev, const float* c, const void* ds_next, const void* o,
+                           int64_t ldo, const float* lse, void* dq, int64_t lddq, void* dk,
+                           int64_t lddk, void* dv, int64_t lddv, void* ds_prev, float* dc,
+                           float* dq_ws, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t hd,
+                           mmemo_stream_t stream);
+/* 1 if the tcgen05/TMA attention kernels serve this shape in the _bf16 build */
+int mmemo_resattn_uses_tensor_cores(int64_t Lq, int64_t Lk, int64_t hd, int64_t ld);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gated residual + LayerNorm (+ReLU).  y = act( LN( res + gate * x ) * gamma + beta ), eps 1e-5.
+ * Replaces others/realformer.py:207-208,263  cmu-mosei/run.py:261  Ren-MME/run.py:166,213
+ * robot_demo.py:372-373.  res == null -> LN(gate*x); gate == null -> 1.  mean/rstd (M) saved.
+ * bwd: dres (nullable) and dx written; dgate, dgamma, dbeta are "+=" float32.
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_add_ln_fwd_f32(const void* res, int64_t ldres, const void* x, int64_t ldx,
+                         const float* gate, const float* gamma, const float* beta, void* y,
+                         int64_t ldy, float* mean, float* rstd, int64_t M, int64_t d, float eps,
+                         int relu, mmemo_stream_t stream);
+int mmemo_add_ln_fwd_bf16(const void* res, int64_t ldres, const void* x, int64_t ldx,
+                          const float* gate, const float* gamma, const float* beta, void* y,
+                          int64_t ldy, float* mean, float* rstd, int64_t M, int64_t d, float eps,
+                          int relu, mmemo_stream_t stream);
+int mmemo_add_ln_bwd_f32(const void* dy, int64_t lddy, const void* res, int64_t ldres,
+                         const void* x, int64_t ldx, const float* gate, const float* gamma,
+                         const void* y, int64_t ldy, const float* mean, const float* rstd,
+                         void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgate,
+                         float* dgamma, float* dbeta, int64_t M, int64_t d, int relu,
+                         mmemo_stream_t stream);
+int mmemo_add_ln_bwd_bf16(const void* dy, int64_t lddy, const void* res, int64_t ldres,
+                          const void* x, int64_t ldx, const float* gate, const float* gamma,
+                          const void* y, int64_t ldy, const float* mean, const float* rstd,
+                          void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgate,
+                          float* dgamma, float* dbeta, int64_t M, int64_t d, int relu,
+                          mmemo_stream_t stream);
+
+/* out[m % period, n] += x[m, n]  (float32 out).  Bias gradients (period 1) and position-table
+ * gradients (period L; backward of others/realformer.py:225-227). */
+int mmemo_rowsum_f32(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
+                     mmemo_stream_t stream);
+int mmemo_rowsum_bf16(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
+                      mmemo_stream_t stream);
+/* dtype conversion of n contiguous elements (bf16 shadow copies of float32 master weights) */
+int mmemo_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mmemo_stream_t stream);
+int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_t stream);
+/* y = x * keep/(1-p), keep ~ Bernoulli(1-p) from a counter-based RNG keyed by (seed, element).
+ * Forward and backward are the same call (nn.Dropout at others/realformer.py:139,159,167,222). */
+int mmemo_dropout_f32(const void* x, void* y, int64_t n, float p, uint64_t seed,
+                      mmemo_stream_t stream);
+int mmemo_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed,
+                       mmemo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fusion pooling: concat on features, concat on positions (l, a, v), mean || max over ALL
+ * positions (mask-unaware).  Replaces others/realformer.py:258-262  cmu-mosei/run.py:314-318
+ * Ren-MME/run.py:266-270  robot_demo.py:435-439 without materialising the concatenation.
+ * seg_ptrs: HOST array [n_groups*n_slots]; seg[g*n_slots+s] is a (B, group_len[g], d) tensor of T
+ * that fills feature slot s for the positions of group g.  out (B, 2*n_slots*d) float32 =
+ * [mean | max]; argmax (B, n_slots*d) int32 = flat position of the first maximum.
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_pool_fwd_f32(const void* const* seg_ptrs, const int64_t* group_len, int n_groups,
+                       int n_slots, int64_t B, int64_t d, float* out, int32_t* argmax,
+                       mmemo_stream_t stream);
+int mmemo_pool_fwd_bf16(const void* const* seg_ptrs, const int64_t* group_len, int n_groups,
+                        int n_slots, int64_t B, int64_t d, float* out, int32_t* argmax,
+                        mmemo_stream_t stream);
+int mmemo_pool_bwd_f32(const float* dout, const int32_t* argmax, void* const* dseg_ptrs,
+                       const int64_t* group_len, int n_groups, int n_slots, int64_t B, int64_t d,
+                       mmemo_stream_t stream);
+int mmemo_pool_bwd_bf16(const float* dout, const int32_t* argmax, void* const* dseg_ptrs,
+                        const int64_t* group_len, int n_groups, int n_slots, int64_t B, int64_t d,
+                        mmemo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heads and losses (float32 only; O(B*C) work).
+ * state_transfer: others/realformer.py:274-286.  feats (B,P,2C) = [o | g]; out (B,P,C).
+ * bilinear_head : cmu-mosei/run.py:332-339  Ren-MME/run.py:285-292  rencecps/run.py:141-148
+ *                 z[b,k] = sum_{j,m} this[b,j] last[b,m] T[j,m,k]; out = W [this || LN(z)] + bias.
+ * circle_loss   : others/realformer.py:289-298 (per-row loss, literal +-1e12 masking).
+ * rdrop_kl      : Ren-MME/run.py:332-334 (scalar; rows 2i / 2i+1; target not detached).
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_state_transfer_fwd(const float* feats, const float* trans, float* out, int64_t B,
+                             int64_t P, int64_t C, mmemo_stream_t stream);
+int mmemo_state_transfer_bwd(const float* dout, const float* feats, const float* trans,
+                             const float* out, float* dfeats, float* dtrans, int64_t B, int64_t P,
+                             int64_t C, mmemo_stream_t stream);
+int mmemo_bilinear_head_fwd(const float* this_feat, const float* last_feat, const float* trans,
+                            const float* gamma, const float* beta, const float* w,
+                            const float* bias, float* out, float* z, int64_t B, int64_t C,
+                            float eps, mmemo_stream_t stream);
+int mmemo_bilinear_head_bwd(const float* dout, const float* this_feat, const float* last_feat,
+                            const float* trans, const float* gamma, const float* beta,
+                            const float* w, const float* z, float* dthis, float* dlast,
+                            float* dtrans, float* dgamma, float* dbeta, float* dw, float* dbias,
+                            int64_t B, int64_t C, float eps, mmemo_stream_t stream);
+int mmemo_circle_loss_fwd(const float* logits, const float* labels, float* loss, int64_t R,
+                          int64_t C, mmemo_stream_t stream);
+int mmemo_circle_loss_bwd(const float* dloss, const float* logits, const float* labels,
+                          float* dlogits, int64_t R, int64_t C, mmemo_stream_t stream);
+int mmemo_rdrop_kl_fwd(const float* logits, float* out, int64_t B, int64_t C,
+                       mmemo_stream_t stream);
+int mmemo_rdrop_kl_bwd(const float* dout, const float* logits, float* dlogits, int64_t B, int64_t C,
+                       mmemo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMEMO_H_ */

@@ -7,3 +7,7 @@ library is loaded lazily by ``mmemo_b200._lib`` on the first kernel call and rai
 missing: there is no CPU fallback.
 """
 __version__ = "0.1.0"
+
+from .blocks import get_precision, precision, set_precision  # noqa: E402,F401
+from . import cmu_mosei, realformer, ren_mme, rencecps, robot_demo, synth  # noqa: E402,F401
+from .encoder import ResidualEncoder  # noqa: E402,F401

@@ -1,0 +1,192 @@
+"""Shared host-side building blocks of the drop-in modules (precision switch, the two
+``Attention_Block`` flavours, the 9-chain fusion trunk).  All compute goes through ``ops``.
+"""
+from __future__ import annotations
+
+import contextlib
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+_STATE = {"bf16": False}
+
+
+def set_precision(mode: str) -> None:
+    """'fp32' (parity mode, default) or 'bf16' (bf16 activations/GEMM operands, fp32 accumulate,
+    fp32 master parameters and gradients)."""
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _STATE["bf16"] = mode == "bf16"
+
+
+def get_precision() -> str:
+    return "bf16" if _STATE["bf16"] else "fp32"
+
+
+@contextlib.contextmanager
+def precision(mode: str):
+    old = get_precision()
+    set_precision(mode)
+    try:
+        yield
+    finally:
+        set_precision(old)
+
+
+def is_bf16() -> bool:
+    return _STATE["bf16"]
+
+
+def as_act(x: torch.Tensor) -> torch.Tensor:
+    """Cast an activation to the compute dtype of the current precision mode."""
+    want = torch.bfloat16 if _STATE["bf16"] else torch.float32
+    return x if x.dtype == want else x.to(want)
+
+
+def as_mask(m: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if m is None:
+        return None
+    m = m if m.dtype == torch.float32 else m.float()
+    return m if m.is_contiguous() else m.contiguous()
+
+
+def _split_check(dim: int, n_heads: int) -> None:
+    # reference: split_last asserts through view(); an indivisible dim raises there as well
+    if dim % n_heads != 0:
+        raise RuntimeError(f"dim {dim} is not divisible by n_heads {n_heads}")
+
+
+class FullAttentionBlock(nn.Module):
+    """RealFormer block with QKV projections, ReZero-gated post-LN and FFN.
+    Reference: others/realformer.py:154-209 (ffn multiplier from the global ``FFN``) and
+    robot_demo.py:324-374 (ffn is a ctor argument).  state_dict keys are the reference's."""
+
+    def __init__(self, dim: int, n_heads: int, ffn: int, drop: float = 0.0):
+        super().__init__()
+        _split_check(dim, n_heads)
+        self.w_qkv = nn.ModuleList([nn.Linear(dim, dim, bias=False) for _ in range(3)])
+        self.n_heads = n_heads
+        self.drop = nn.Dropout(drop)
+        self.proj = nn.Linear(dim, dim, bias=False)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.ffn = nn.Sequential(nn.Linear(dim, ffn * dim), nn.ReLU(), nn.Linear(ffn * dim, dim),
+                                 nn.Dropout(drop))
+        self.a = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
+        self.b = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
+        self.c = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
+        self.emit_scores = True  # set False when nothing consumes the returned scores
+
+    def _params(self) -> List[torch.Tensor]:
+        return [self.w_qkv[0].weight, self.w_qkv[1].weight, self.w_qkv[2].weight, self.proj.weight,
+                self.norm1.weight, self.norm1.bias, self.norm2.weight, self.norm2.bias,
+                self.ffn[0].weight, self.ffn[0].bias, self.ffn[2].weight, self.ffn[2].bias,
+                self.a, self.b, self.c]
+
+    def multi_head_attention(self, q, k, v, mask, scores=None):
+        """Projected attention + output projection; returns (drop(proj(att v)), scores)."""
+        bf = is_bf16()
+        q, k, v = as_act(q), as_act(k), as_act(v)
+        qp = ops.linear(q, self.w_qkv[0].weight, bf16=bf)
+        kp = ops.linear(k, self.w_qkv[1].weight, bf16=bf)
+        vp = ops.linear(v, self.w_qkv[2].weight, bf16=bf)
+        o, s, _ = ops.resattn_op(qp, kp, vp, as_mask(mask), scores, self.c, self.n_heads)
+        x = ops.linear(o, self.proj.weight, bf16=bf)
+        return ops.dropout(x, self.drop.p, self.training), s
+
+    def forward(self, q, k, v, mask, scores=None):
+        bf = is_bf16()
+        fused = (k is v) and not (self.training and self.drop.p > 0)
+        if fused:  # one autograd node for the whole block
+            same = q is k
+            q = as_act(q)
+            k = q if same else as_act(k)
+            out = ops.block_full_op(q, k, as_mask(mask), scores, self._params(), self.n_heads, bf,
+                                    self.emit_scores, q is k)
+            s = out[1]
+            return out[0], (s if s.numel() else None)
+        x, s = self.multi_head_attention(q, k, v, mask, scores)
+        q = as_act(q)
+        h1 = ops.add_ln(q, x, self.a, self.norm1.weight, self.norm1.bias)
+        f = ops.linear(h1, self.ffn[0].weight, self.ffn[0].bias, relu=True, bf16=bf)
+        f = ops.linear(f, self.ffn[2].weight, self.ffn[2].bias, bf16=bf)
+        f = ops.dropout(f, self.drop.p, self.training)
+        h2 = ops.add_ln(h1, f, self.b, self.norm2.weight, self.norm2.bias)
+        return h2, s
+
+
+class LiteAttentionBlock(nn.Module):
+    """Residual-attention block without QKV projections: ``LN(minus([q | proj(att)]))``.
+    Reference: cmu-mosei/run.py:217-262 (LayerNorm named ``norm1``) and Ren-MME/run.py:169-214
+    (``norm2``)."""
+
+    def __init__(self, dim: int, n_heads: int, ffn: int, drop: float = 0.0, norm_name: str = "norm1"):
+        super().__init__()
+        _split_check(dim, n_heads)
+        self.n_heads = n_heads
+        self.drop = nn.Dropout(drop)
+        self.proj = nn.Linear(dim, dim, bias=False)
+        self.minus = nn.Linear(dim * 2, dim, bias=False)
+        setattr(self, norm_name, nn.LayerNorm(dim))
+        self._norm_name = norm_name
+        self.c = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
+        self.emit_scores = True
+
+    @property
+    def _norm(self) -> nn.LayerNorm:
+        return getattr(self, self._norm_name)
+
+    def multi_head_attention(self, q, k, v, mask, scores=None):
+        bf = is_bf16()
+        q, k, v = as_act(q), as_act(k), as_act(v)
+        o, s, _ = ops.resattn_op(q, k, v, as_mask(mask), scores, self.c, self.n_heads)
+        x = ops.linear(o, self.proj.weight, bf16=bf)
+        return ops.dropout(x, self.drop.p, self.training), s
+
+    def forward(self, q, k, v, mask, scores=None):
+        bf = is_bf16()
+        n = self._norm
+        fused = (k is v) and not (self.training and self.drop.p > 0)
+        if fused:
+            same = q is k
+            q = as_act(q)
+            k = q if same else as_act(k)
+            out = ops.block_lite_op(q, k, as_mask(mask), scores,
+                                    [self.proj.weight, self.minus.weight, n.weight, n.bias, self.c],
+                                    self.n_heads, bf, self.emit_scores)
+            s = out[1]
+            return out[0], (s if s.numel() else None)
+        x, s = self.multi_head_attention(q, k, v, mask, scores)
+        y = ops.linear(torch.cat([as_act(q), x], dim=-1), self.minus.weight, bf16=bf)
+        y = ops.add_ln(None, y, None, n.weight, n.bias)
+        return ops.dropout(y, self.drop.p, self.training), s
+
+
+# (query modality, source modality) in the reference's fixed order:
+# others/realformer.py:232-257, cmu-mosei/run.py:278-313 — ll lv la vv vl va aa al av
+CHAINS = [("l", "l"), ("l", "v"), ("l", "a"), ("v", "v"), ("v", "l"), ("v", "a"),
+          ("a", "a"), ("a", "l"), ("a", "v")]
+
+
+def fusion_trunk(blocks: Sequence[nn.Module], n_layers: int, feats: Dict[str, torch.Tensor],
+                 masks: Dict[str, torch.Tensor], keep_all: bool) -> torch.Tensor:
+    """Run the nine chains and pool.  Block ``n_layers*chain + i`` is layer i of a chain; scores
+    restart at None per chain; the q-stream evolves while k = v = the un-evolved source modality.
+    Returns the float32 pooled features (B, 6*d*(n_layers if keep_all else 1))."""
+    outs: Dict[str, List[torch.Tensor]] = {"l": [], "v": [], "a": []}
+    for ci, (qm, sm) in enumerate(CHAINS):
+        q, s = feats[qm], None
+        src, m = feats[sm], masks[sm]
+        for i in range(n_layers):
+            blk = blocks[n_layers * ci + i]
+            blk.emit_scores = i + 1 < n_layers      # the last layer's scores feed nothing
+            q, s = blk(q, src, src, m, s)
+            if keep_all:
+                outs[qm].append(q)
+        if not keep_all:
+            outs[qm].append(q)
+    # feature concat per modality, position concat in the order (l, a, v), mean||max pooling
+    return ops.pool(outs["l"] + outs["a"] + outs["v"], 3)

@@ -1,0 +1,86 @@
+"""Drop-in modules for the reference script ``cmu-mosei/run.py`` (7 labels, lite blocks, two
+towers + 7x7x7 bilinear transition head)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .blocks import LiteAttentionBlock, as_mask, fusion_trunk, is_bf16
+
+# reference module constants (cmu-mosei/run.py:24-42) read inside the classes
+L_DIM, V_DIM, A_DIM = 300, 35, 74
+DROP = 0.0
+
+
+class Unify_Dimension(nn.Module):
+    """cmu-mosei/run.py:207-214.  Input widths come from module globals in the reference; they are
+    keyword arguments here with the same defaults."""
+
+    def __init__(self, dim, l_dim=None, v_dim=None, a_dim=None):
+        super().__init__()
+        self.linguistic = nn.Linear(L_DIM if l_dim is None else l_dim, dim, bias=False)
+        self.visual = nn.Linear(V_DIM if v_dim is None else v_dim, dim, bias=False)
+        self.acoustic = nn.Linear(A_DIM if a_dim is None else a_dim, dim, bias=False)
+
+    def forward(self, l, v, a):
+        bf = is_bf16()
+        return (ops.linear(l, self.linguistic.weight, bf16=bf),
+                ops.linear(v, self.visual.weight, bf16=bf),
+                ops.linear(a, self.acoustic.weight, bf16=bf))
+
+
+class Attention_Block(LiteAttentionBlock):
+    """cmu-mosei/run.py:217-262."""
+
+    def __init__(self, dim, n_heads, ffn):
+        super().__init__(dim, n_heads, ffn, DROP, norm_name="norm1")
+
+
+class Multi_ATTN(nn.Module):
+    """cmu-mosei/run.py:265-319."""
+    N_CLS = 7
+
+    def __init__(self, dim, l_len, v_len, a_len, n_heads, n_layers, ffn, l_dim=None, v_dim=None,
+                 a_dim=None):
+        super().__init__()
+        self.unify_dimension = Unify_Dimension(dim, l_dim, v_dim, a_dim)
+        self.n_layers = n_layers
+        self.multimodal_blocks = nn.ModuleList([Attention_Block(dim, n_heads, ffn)
+                                                for _ in range(9 * n_layers)])
+        self.classifier = nn.Linear(dim * 6 * n_layers, self.N_CLS, bias=False)
+
+    def forward(self, l, v, a, l_mask, v_mask, a_mask):
+        l, v, a = self.unify_dimension(l, v, a)
+        x = fusion_trunk(self.multimodal_blocks, self.n_layers, {"l": l, "v": v, "a": a},
+                         {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)},
+                         keep_all=True)
+        return ops.linear(x, self.classifier.weight)
+
+
+class Concat_Trans(nn.Module):
+    """cmu-mosei/run.py:321-339.  l (B,2,L,D): index 0 = previous sentence, 1 = current."""
+
+    def __init__(self, dim, l_len, v_len, a_len, n_heads, n_layers, ffn, l_dim=None, v_dim=None,
+                 a_dim=None):
+        super().__init__()
+        self.intensity = Multi_ATTN(dim, l_len, v_len, a_len, n_heads, n_layers, ffn, l_dim, v_dim,
+                                    a_dim)
+        self.stimulation = Multi_ATTN(dim, l_len, v_len, a_len, n_heads, n_layers, ffn, l_dim,
+                                      v_dim, a_dim)
+        self.trans = nn.Parameter(torch.rand(7, 7, 7), requires_grad=True)
+        self.norm1 = nn.LayerNorm(7)
+        self.out = nn.Linear(14, 7)
+
+    def forward(self, l, v, a, l_mask, v_mask, a_mask):
+        last_feat = self.intensity(l[:, 0], v[:, 0], a[:, 0], l_mask[:, 0], v_mask[:, 0],
+                                   a_mask[:, 0])
+        this_feat = self.stimulation(l[:, 1], v[:, 1], a[:, 1], l_mask[:, 1], v_mask[:, 1],
+                                     a_mask[:, 1])
+        return ops.bilinear_head(this_feat, last_feat, self.trans, self.norm1.weight,
+                                 self.norm1.bias, self.out.weight, self.out.bias)
+
+
+def multi_circle_loss(y_pred, y_true):
+    """cmu-mosei/run.py:342-351."""
+    return ops.circle_loss_op(y_pred, y_true)

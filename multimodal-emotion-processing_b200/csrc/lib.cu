@@ -1,0 +1,15 @@
+// Library-level entry points: version, last-error string.
+#include <stdio.h>
+
+#include "common.cuh"
+
+static thread_local char g_last_error[512] = "";
+
+void mmemo_set_error(const char* what, const char* file, int line) {
+  snprintf(g_last_error, sizeof(g_last_error), "%s (%s:%d)", what ? what : "?", file, line);
+}
+
+extern "C" {
+int mmemo_version(void) { return 100; }
+const char* mmemo_last_error(void) { return g_last_error; }
+}

@@ -1,0 +1,138 @@
+// Small bandwidth-bound helpers: periodic row-sum (bias / position-table gradients), dtype casts
+// (bf16 shadow weights) and counter-based dropout.
+#include "common.cuh"
+
+namespace {
+
+// out[(m % period), n] += x[m, n].  CTA = (32 columns, a strip of rows); lanes own columns so the
+// global reads are coalesced; rows with equal (m % period) are summed in registers first.
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowsum_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t M, int64_t N,
+              int64_t period, int64_t rows_per_cta) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t p = blockIdx.z;                       // residue class handled by this CTA
+  const int64_t r_beg = (int64_t)blockIdx.y * rows_per_cta;  // in units of periods
+  const int64_t n_per = (M - p + period - 1) / period;       // rows m = p + t*period, t < n_per
+  float acc = 0.f;
+  if (n < N) {
+    const int64_t t_end = min(n_per, r_beg + rows_per_cta);
+    for (int64_t t = r_beg + wy; t < t_end; t += 8) acc += to_f(x[(p + t * period) * ldx + n]);
+  }
+  red[wy][lane] = acc;
+  __syncthreads();
+  if (wy == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    atomicAdd(out + p * N + n, t);
+  }
+}
+
+__global__ void cast_f2b_kernel(const float* __restrict__ s, bf16* __restrict__ d, int64_t n) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(s + i);
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&a);
+    o.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(d + i) = o;
+  } else {
+    for (int64_t j = i; j < n; ++j) d[j] = __float2bfloat16_rn(s[j]);
+  }
+}
+__global__ void cast_b2f_kernel(const bf16* __restrict__ s, float* __restrict__ d, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __bfloat162float(s[i]);
+}
+
+// splitmix64-style hash of (seed, element index) -> uniform in [0,1)
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p,
+                               float scale, uint64_t seed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = from_f<T>(hash_uniform(seed, (uint64_t)i) >= p ? to_f(x[i]) * scale : 0.f);
+}
+
+template <typename T>
+int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
+           cudaStream_t st) {
+  if (M <= 0 || N <= 0) return MMEMO_OK;
+  MM_REQUIRE(x && out && period >= 1);
+  if (period > 65535) return MMEMO_ERR_SHAPE;
+  const int64_t n_per = cdiv(M, period);
+  // enough CTAs to fill the machine, at least 64 rows each
+  int64_t strips = cdiv(n_per, 64);
+  const int64_t base = cdiv(N, 32) * period;
+  if (strips * base > 148 * 16) strips = cdiv(148 * 16, base);
+  if (strips < 1) strips = 1;
+  if (strips > 65535) strips = 65535;
+  const int64_t rows_per_cta = cdiv(n_per, strips);
+  dim3 grid((unsigned)cdiv(N, 32), (unsigned)strips, (unsigned)period);
+  rowsum_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, period,
+                                         rows_per_cta);
+  MM_LAUNCH_OK();
+  return MMEMO_OK;
+}
+
+template <typename T>
+int dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, cudaStream_t st) {
+  if (n <= 0) return MMEMO_OK;
+  MM_REQUIRE(x && y && p >= 0.f && p < 1.f);
+  dropout_kernel<T><<<(unsigned)cdiv(n, 256), 256, 0, st>>>(
+      static_cast<const T*>(x), static_cast<T*>(y), n, p, 1.0f / (1.0f - p), seed);
+  MM_LAUNCH_OK();
+  return MMEMO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+int mmemo_rowsum_f32(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
+                     mmemo_stream_t s) {
+  return rowsum<float>(x, ldx, out, M, N, period, mm_stream(s));
+}
+int mmemo_rowsum_bf16(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
+                      mmemo_stream_t s) {
+  return rowsum<bf16>(x, ldx, out, M, N, period, mm_stream(s));
+}
+int mmemo_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mmemo_stream_t s) {
+  if (n <= 0) return MMEMO_OK;
+  MM_REQUIRE(src && dst);
+  cast_f2b_kernel<<<(unsigned)cdiv(cdiv(n, 4), 256), 256, 0, mm_stream(s)>>>(
+      src, static_cast<bf16*>(dst), n);
+  MM_LAUNCH_OK();
+  return MMEMO_OK;
+}
+int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_t s) {
+  if (n <= 0) return MMEMO_OK;
+  MM_REQUIRE(src && dst);
+  cast_b2f_kernel<<<(unsigned)cdiv(n, 256), 256, 0, mm_stream(s)>>>(
+      static_cast<const bf16*>(src), dst, n);
+  MM_LAUNCH_OK();
+  return MMEMO_OK;
+}
+int mmemo_dropout_f32(const void* x, void* y, int64_t n, float p, uint64_t seed, mmemo_stream_t s) {
+  return dropout<float>(x, y, n, p, seed, mm_stream(s));
+}
+int mmemo_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed,
+                       mmemo_stream_t s) {
+  return dropout<bf16>(x, y, n, p, seed, mm_stream(s));
+}
+}
+
+// internal: bias gradient (column sum) used by linear_bwd_w
+int mmemo_rowsum_dispatch(int bf16_mode, const void* x, int64_t ldx, float* out, int64_t M,
+                          int64_t N, cudaStream_t st) {
+  return bf16_mode ? rowsum<bf16>(x, ldx, out, M, N, 1, st) : rowsum<float>(x, ldx, out, M, N, 1, st);
+}

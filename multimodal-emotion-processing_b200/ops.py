@@ -1,0 +1,860 @@
+"""torch custom ops over the C ABI of libmmemo.so (include/mmemo.h).
+
+Every op allocates its outputs with torch (device memory + stream plumbing only), passes raw
+device pointers + the current CUDA stream to an ``extern "C"`` launcher, and registers an explicit
+backward (``torch.library.register_autograd``) that calls the matching ``*_bwd`` launchers, so the
+reference training loops (``loss.backward()``, ``clip_grad_norm_``, ``optimizer.step()``) work
+unchanged.  No op has a CPU implementation: calling one without a CUDA tensor or without the
+built library raises.
+
+Precision: activations are float32 (parity mode) or bfloat16 (``bf16=True``).  Parameters stay
+float32 ("master"); in bf16 mode GEMM weights are used through bf16 shadow copies refreshed when
+the parameter's version counter changes; all parameter gradients are returned in float32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+BF = torch.bfloat16
+F32 = torch.float32
+LN_EPS = 1e-5
+
+# number of libmmemo kernel launches issued through this module (bench.py's gpu_launches)
+launch_count = 0
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _call(name: str, *args) -> None:
+    global launch_count
+    launch_count += 1
+    _lib.check(getattr(_lib.load(), name)(*args), name)
+
+
+def _sfx(bf16: bool) -> str:
+    return "bf16" if bf16 else "f32"
+
+
+def _act_dtype(bf16: bool):
+    return BF if bf16 else F32
+
+
+def _need_cuda(*ts: Optional[Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mmemo_b200 ops run on CUDA tensors only (no CPU fallback)")
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 shadow copies of float32 master weights
+# ------------------------------------------------------------------------------------------------
+_shadow: dict = {}
+
+
+def clear_shadow_cache() -> None:
+    """Drop all bf16 weight shadows (call before CUDA-graph capture so the casts are captured)."""
+    _shadow.clear()
+
+
+def shadow_bf16(*ws: Tensor) -> Tensor:
+    """bf16 copy of one weight, or of several weights concatenated along dim 0 (e.g. [Wk; Wv])."""
+    key = tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in ws)
+    hit = _shadow.get(key)
+    if hit is not None:
+        return hit
+    # evict stale entries of the same storage(s)
+    ptrs = {k[0] for k in key}
+    for k in [k for k in _shadow if any(e[0] in ptrs for e in k) and len(k) == len(key)]:
+        del _shadow[k]
+    rows = sum(w.shape[0] for w in ws)
+    cols = ws[0].numel() // ws[0].shape[0]
+    out = torch.empty(rows, cols, dtype=BF, device=ws[0].device)
+    r = 0
+    for w in ws:
+        wd = w.detach()
+        if not wd.is_contiguous():
+            wd = wd.contiguous()
+        _call("mmemo_cast_f32_to_bf16", wd.data_ptr(), out[r:].data_ptr(), wd.numel(), _stream())
+        r += w.shape[0]
+    _shadow[key] = out
+    return out
+
+
+def _weight(bf16: bool, *ws: Tensor) -> Tensor:
+    if bf16:
+        return shadow_bf16(*ws)
+    if len(ws) == 1:
+        w = ws[0].detach()
+        w = w.reshape(w.shape[0], -1)
+        return w if w.is_contiguous() else w.contiguous()
+    return torch.cat([w.detach().reshape(w.shape[0], -1) for w in ws], 0)
+
+
+def _rows(x: Tensor) -> Tuple[Tensor, int, int]:
+    """View (..., K) as (M, K) with unit inner stride; returns (tensor, M, ld)."""
+    K = x.shape[-1]
+    if x.dim() == 2 and x.stride(1) == 1:
+        return x, x.shape[0], x.stride(0)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    return x, x.numel() // K, K
+
+
+# ------------------------------------------------------------------------------------------------
+# raw launch helpers (no autograd) -- shared by the fine-grained ops and the fused block ops
+# ------------------------------------------------------------------------------------------------
+def _linear_fwd(bf16, x, w, bias, pos, out, relu=False, accumulate=False, ldw=None, N=None, K=None):
+    x, M, ldx = _rows(x)
+    N = w.shape[0] if N is None else N
+    K = x.shape[-1] if K is None else K
+    ldw = w.stride(0) if ldw is None else ldw
+    _call(f"mmemo_linear_fwd_{_sfx(bf16)}", x.data_ptr(), int(x.dtype == F32), ldx, w.data_ptr(),
+          ldw, _p(bias), _p(pos), 0 if pos is None else pos.shape[0], out.data_ptr(),
+          out.stride(-2), M, N, K, int(relu), int(accumulate), _stream())
+
+
+def _linear_bwd_x(bf16, dy, w, dx, relu_src=None, accumulate=False, ldw=None, N=None, K=None):
+    dy, M, lddy = _rows(dy)
+    N = w.shape[0] if N is None else N
+    K = w.shape[1] if K is None else K
+    ldw = w.stride(0) if ldw is None else ldw
+    _call(f"mmemo_linear_bwd_x_{_sfx(bf16)}", dy.data_ptr(), lddy, w.data_ptr(), ldw,
+          dx.data_ptr(), dx.stride(-2), _p(relu_src),
+          0 if relu_src is None else relu_src.stride(-2), M, N, K, int(accumulate), _stream())
+
+
+def _linear_bwd_w(bf16, dy, x, dw, dbias=None, accumulate=False, N=None, K=None):
+    dy, M, lddy = _rows(dy)
+    x, _, ldx = _rows(x)
+    N = dy.shape[-1] if N is None else N
+    K = x.shape[-1] if K is None else K
+    _call(f"mmemo_linear_bwd_w_{_sfx(bf16)}", dy.data_ptr(), lddy, x.data_ptr(),
+          int(x.dtype == F32), ldx, dw.data_ptr(), dw.stride(0), _p(dbias), M, N, K,
+          int(accumulate), _stream())
+
+
+def _add_ln_fwd(bf16, res, x, gate, gamma, beta, relu=False):
+    x2, M, ldx = _rows(x)
+    d = x.shape[-1]
+    if res is not None:
+        res, _, ldres = _rows(res)
+    else:
+        ldres = 0
+    y = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    stat = torch.empty(2, M, dtype=F32, device=x.device)
+    _call(f"mmemo_add_ln_fwd_{_sfx(bf16)}", _p(res), ldres, x2.data_ptr(), ldx, _p(gate),
+          gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), d, stat[0].data_ptr(),
+          stat[1].data_ptr(), M, d, LN_EPS, int(relu), _stream())
+    return y, stat
+
+
+def _add_ln_bwd(bf16, dy, res, x, gate, gamma, y, stat, relu, want_dres, dres_out=None):
+    """Returns (dres, dx, dparams) with dparams = float32 [1 + 2d] = (dgate | dgamma | dbeta)."""
+    dy, M, lddy = _rows(dy)
+    x2, _, ldx = _rows(x)
+    d = x.shape[-1]
+    ldres = 0
+    if res is not None:
+        res, _, ldres = _rows(res)
+    dx = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+    dres = None
+    if want_dres:
+        dres = dres_out if dres_out is not None else torch.empty(x.shape, dtype=x.dtype,
+                                                                 device=x.device)
+    dpar = torch.zeros(1 + 2 * d, dtype=F32, device=x.device)
+    _call(f"mmemo_add_ln_bwd_{_sfx(bf16)}", dy.data_ptr(), lddy, _p(res), ldres, x2.data_ptr(),
+          ldx, _p(gate), gamma.data_ptr(), _p(y) if relu else None, d, stat[0].data_ptr(),
+          stat[1].data_ptr(), _p(dres), d, dx.data_ptr(), d, dpar.data_ptr(),
+          dpar[1:].data_ptr(), dpar[1 + d:].data_ptr(), M, d, int(relu), _stream())
+    return dres, dx, dpar
+
+
+def _rowsum(bf16_in: bool, x, out, period=1):
+    x, M, ldx = _rows(x)
+    _call(f"mmemo_rowsum_{_sfx(bf16_in)}", x.data_ptr(), ldx, out.data_ptr(), M, x.shape[-1],
+          period, _stream())
+
+
+def _bld(t: Tensor, L: int) -> int:
+    """Row stride of a (B, L, d) activation whose batch stride must be L*ld."""
+    assert t.dim() == 3 and t.stride(2) == 1 and (t.shape[0] == 1 or t.stride(0) == L * t.stride(1)), \
+        "activation must be (B, L, d) with unit inner stride and packed batch"
+    return t.stride(1)
+
+
+def _mask_strides(mask: Optional[Tensor], Lq: int, Lk: int) -> Tuple[int, int]:
+    if mask is None:
+        return 0, 0
+    if mask.dim() == 2:
+        return Lk, 0
+    return Lq * Lk, Lk
+
+
+def _attn_fwd(bf16, q, k, v, mask, s_prev, c, H, want_s):
+    B, Lq, d = q.shape
+    Lk = k.shape[1]
+    hd = d // H
+    dt = _act_dtype(bf16)
+    o = torch.empty(B, Lq, d, dtype=dt, device=q.device)
+    s = torch.empty(B, H, Lq, Lk, dtype=dt, device=q.device) if want_s else None
+    stat = torch.empty(B, H, Lq, 2, dtype=F32, device=q.device)
+    mbs, mrs = _mask_strides(mask, Lq, Lk)
+    _call(f"mmemo_resattn_fwd_{_sfx(bf16)}", q.data_ptr(), _bld(q, Lq), k.data_ptr(), _bld(k, Lk),
+          v.data_ptr(), _bld(v, Lk), _p(mask), mbs, mrs, _p(s_prev),
+          _p(c) if s_prev is not None else None, _p(s), o.data_ptr(), d, stat.data_ptr(), B, H, Lq,
+          Lk, hd, _stream())
+    return o, s, stat
+
+
+def _attn_bwd(bf16, do, q, k, v, mask, s, s_prev, c, ds_next, o, stat, H, dq, dk, dv, want_dsprev):
+    B, Lq, d = q.shape
+    Lk = k.shape[1]
+    hd = d // H
+    dt = _act_dtype(bf16)
+    ds_prev = None
+    dc = None
+    if s_prev is not None:
+        dc = torch.zeros(1, dtype=F32, device=q.device)
+        if want_dsprev:
+            ds_prev = torch.empty(B, H, Lq, Lk, dtype=dt, device=q.device)
+    ws = None
+    if bf16 and Lk > 128 and not _lib.load().mmemo_resattn_uses_tensor_cores(Lq, Lk, hd, d):
+        ws = torch.empty(B, Lq, d, dtype=F32, device=q.device)
+    mbs, mrs = _mask_strides(mask, Lq, Lk)
+    _call(f"mmemo_resattn_bwd_{_sfx(bf16)}", do.data_ptr(), _bld(do, Lq), q.data_ptr(),
+          _bld(q, Lq), k.data_ptr(), _bld(k, Lk), v.data_ptr(), _bld(v, Lk), _p(mask), mbs, mrs,
+          _p(s), _p(s_prev), _p(c) if s_prev is not None else None, _p(ds_next), o.data_ptr(),
+          _bld(o, Lq), stat.data_ptr(), dq.data_ptr(), _bld(dq, Lq), dk.data_ptr(), _bld(dk, Lk),
+          dv.data_ptr(), _bld(dv, Lk), _p(ds_prev), _p(dc), _p(ws), B, H, Lq, Lk, hd, _stream())
+    return ds_prev, dc
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::linear  (Linear / Conv1d(k=1) with optional bias, fused position table, fused ReLU)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::linear", mutates_args=())
+def linear_op(x: Tensor, w: Tensor, bias: Optional[Tensor], pos: Optional[Tensor], relu: bool,
+              bf16: bool) -> Tensor:
+    _need_cuda(x, w)
+    N = w.shape[0]
+    y = torch.empty(*x.shape[:-1], N, dtype=_act_dtype(bf16), device=x.device)
+    if pos is not None:
+        assert x.dim() == 3 and pos.shape[0] == x.shape[1], "position table length != seq length"
+    _linear_fwd(bf16, x, _weight(bf16, w), bias, pos, y.view(-1, N), relu=relu)
+    return y
+
+
+@linear_op.register_fake
+def _(x, w, bias, pos, relu, bf16):
+    return x.new_empty(*x.shape[:-1], w.shape[0], dtype=_act_dtype(bf16))
+
+
+@torch.library.custom_op("mmemo::linear_bwd", mutates_args=())
+def linear_bwd_op(dy: Tensor, x: Tensor, w: Tensor, y: Optional[Tensor], has_bias: bool,
+                  pos_len: int, need_dx: bool, bf16: bool) -> List[Tensor]:
+    N, K = w.shape[0], w.numel() // w.shape[0]
+    dev = x.device
+    dy = dy.contiguous()
+    if y is not None:  # fused ReLU: mask the incoming gradient once
+        dy = torch.where(y > 0, dy, torch.zeros((), dtype=dy.dtype, device=dev))
+    dw = torch.empty(N, K, dtype=F32, device=dev)
+    dbias = torch.zeros(N, dtype=F32, device=dev) if has_bias else torch.empty(0, device=dev)
+    _linear_bwd_w(bf16, dy.view(-1, N), x, dw, dbias if has_bias else None)
+    dpos = torch.empty(0, device=dev)
+    if pos_len > 0:
+        dpos = torch.zeros(pos_len, N, dtype=F32, device=dev)
+        _rowsum(bf16, dy.view(-1, N), dpos, period=pos_len)
+    dx = torch.empty(0, device=dev)
+    if need_dx:
+        dxa = torch.empty(x.shape, dtype=_act_dtype(bf16), device=dev)
+        _linear_bwd_x(bf16, dy.view(-1, N), _weight(bf16, w), dxa.view(-1, K))
+        dx = dxa if dxa.dtype == x.dtype else dxa.to(x.dtype)
+    return [dx, dw.view(w.shape), dbias, dpos]
+
+
+def _linear_setup(ctx, inputs, output):
+    x, w, bias, pos, relu, bf16 = inputs
+    ctx.save_for_backward(x, w, output if relu else None)
+    ctx.has_bias = bias is not None
+    ctx.pos_len = 0 if pos is None else pos.shape[0]
+    ctx.bf16 = bf16
+
+
+def _linear_backward(ctx, dy):
+    x, w, y = ctx.saved_tensors
+    dx, dw, dbias, dpos = linear_bwd_op(dy, x, w, y, ctx.has_bias, ctx.pos_len,
+                                        ctx.needs_input_grad[0], ctx.bf16)
+    return (dx if ctx.needs_input_grad[0] else None, dw, dbias if ctx.has_bias else None,
+            dpos if ctx.pos_len else None, None, None)
+
+
+linear_op.register_autograd(_linear_backward, setup_context=_linear_setup)
+
+
+def linear(x, w, bias=None, pos=None, relu=False, bf16=False):
+    if w.dim() == 3:  # Conv1d(kernel_size=1) weight (out, in, 1)
+        w = w.squeeze(-1)
+    return linear_op(x, w, bias, pos, relu, bf16)
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::add_ln   y = act(LN(res + gate*x))
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::add_ln", mutates_args=())
+def add_ln_op(res: Optional[Tensor], x: Tensor, gate: Optional[Tensor], gamma: Tensor,
+              beta: Tensor, relu: bool) -> Tuple[Tensor, Tensor]:
+    _need_cuda(x)
+    return _add_ln_fwd(x.dtype == BF, res, x, gate, gamma, beta, relu)
+
+
+@add_ln_op.register_fake
+def _(res, x, gate, gamma, beta, relu):
+    return torch.empty_like(x), x.new_empty(2, x.numel() // x.shape[-1], dtype=F32)
+
+
+@torch.library.custom_op("mmemo::add_ln_bwd", mutates_args=())
+def add_ln_bwd_op(dy: Tensor, res: Optional[Tensor], x: Tensor, gate: Optional[Tensor],
+                  gamma: Tensor, y: Tensor, stat: Tensor, relu: bool) -> List[Tensor]:
+    dres, dx, dpar = _add_ln_bwd(x.dtype == BF, dy.contiguous(), res, x, gate, gamma, y, stat, relu,
+                                 res is not None)
+    return [dres if dres is not None else torch.empty(0, device=x.device), dx, dpar]
+
+
+def _add_ln_setup(ctx, inputs, output):
+    res, x, gate, gamma, beta, relu = inputs
+    y, stat = output
+    ctx.save_for_backward(res, x, gate, gamma, y, stat)
+    ctx.relu = relu
+    ctx.set_materialize_grads(False)
+
+
+def _add_ln_backward(ctx, dy, _dstat):
+    res, x, gate, gamma, y, stat = ctx.saved_tensors
+    d = x.shape[-1]
+    dres, dx, dpar = add_ln_bwd_op(dy, res, x, gate, gamma, y, stat, ctx.relu)
+    return (dres if res is not None else None, dx, dpar[0:1] if gate is not None else None,
+            dpar[1:1 + d], dpar[1 + d:], None)
+
+
+add_ln_op.register_autograd(_add_ln_backward, setup_context=_add_ln_setup)
+
+
+def add_ln(res, x, gate, gamma, beta, relu=False):
+    return add_ln_op(res, x, gate, gamma, beta, relu)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::resattn  (the attention core on already-projected q/k/v; unit-testable piece of kernel a)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::resattn", mutates_args=())
+def resattn_op(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], s_prev: Optional[Tensor],
+               c: Optional[Tensor], n_heads: int) -> Tuple[Tensor, Tensor, Tensor]:
+    _need_cuda(q, k, v)
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    o, s, stat = _attn_fwd(q.dtype == BF, q, k, v, mask, s_prev, c, n_heads, True)
+    return o, s, stat
+
+
+@torch.library.custom_op("mmemo::resattn_bwd", mutates_args=())
+def resattn_bwd_op(do: Tensor, ds_next: Optional[Tensor], q: Tensor, k: Tensor, v: Tensor,
+                   mask: Optional[Tensor], s: Tensor, s_prev: Optional[Tensor],
+                   c: Optional[Tensor], o: Tensor, stat: Tensor, n_heads: int) -> List[Tensor]:
+    q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    ds_prev, dc = _attn_bwd(q.dtype == BF, do.contiguous(), q, k, v, mask, s, s_prev, c,
+                            None if ds_next is None else ds_next.contiguous(), o, stat, n_heads,
+                            dq, dk, dv, True)
+    return [dq, dk, dv, ds_prev if ds_prev is not None else torch.empty(0, device=q.device),
+            dc if dc is not None else torch.empty(0, device=q.device)]
+
+
+def _resattn_setup(ctx, inputs, output):
+    q, k, v, mask, s_prev, c, H = inputs
+    o, s, stat = output
+    ctx.save_for_backward(q, k, v, mask, s, s_prev, c, o, stat)
+    ctx.H = H
+    ctx.set_materialize_grads(False)
+
+
+def _resattn_backward(ctx, do, ds, _dstat):
+    q, k, v, mask, s, s_prev, c, o, stat = ctx.saved_tensors
+    if do is None:
+        do = torch.zeros_like(o)
+    dq, dk, dv, dsp, dc = resattn_bwd_op(do, ds, q, k, v, mask, s, s_prev, c, o, stat, ctx.H)
+    has_prev = s_prev is not None
+    return (dq, dk, dv, None, dsp if has_prev else None,
+            dc if (has_prev and c is not None) else None, None)
+
+
+resattn_op.register_autograd(_resattn_backward, setup_context=_resattn_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::block_full — the whole RealFormer block as ONE autograd node
+#   (others/realformer.py:182-209 == robot_demo.py:347-374)
+# params order: wq wk wv wo  n1w n1b n2w n2b  f1w f1b f2w f2b  a b c
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::block_full", mutates_args=())
+def block_full_op(q: Tensor, kv: Tensor, mask: Optional[Tensor], s_prev: Optional[Tensor],
+                  params: Sequence[Tensor], n_heads: int, bf16: bool, emit_s: bool,
+                  same_qkv: bool) -> List[Tensor]:
+    _need_cuda(q, kv)
+    wq, wk, wv, wo, n1w, n1b, n2w, n2b, f1w, f1b, f2w, f2b, ga, gb, gc = params
+    B, Lq, d = q.shape
+    Lk = kv.shape[1]
+    dt, dev = _act_dtype(bf16), q.device
+    q = q.contiguous()
+    kv = q if same_qkv else kv.contiguous()
+    # Q projection and fused [K|V] projection (one GEMM, N = 2d)
+    qp = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    kvp = torch.empty(B, Lk, 2 * d, dtype=dt, device=dev)
+    _linear_fwd(bf16, q, _weight(bf16, wq), None, None, qp.view(-1, d))
+    _linear_fwd(bf16, kv, _weight(bf16, wk, wv), None, None, kvp.view(-1, 2 * d))
+    kp, vp = kvp[..., :d], kvp[..., d:]
+    o, s, stat = _attn_fwd(bf16, qp, kp, vp, mask, s_prev, gc, n_heads, emit_s)
+    # output projection, gated residual + LN1
+    x = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    _linear_fwd(bf16, o, _weight(bf16, wo), None, None, x.view(-1, d))
+    h1, st1 = _add_ln_fwd(bf16, q, x, ga, n1w, n1b)
+    # FFN (ReLU fused in the first GEMM's epilogue), gated residual + LN2
+    dff = f1w.shape[0]
+    f1 = torch.empty(B, Lq, dff, dtype=dt, device=dev)
+    f2 = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    _linear_fwd(bf16, h1, _weight(bf16, f1w), f1b, None, f1.view(-1, dff), relu=True)
+    _linear_fwd(bf16, f1, _weight(bf16, f2w), f2b, None, f2.view(-1, d))
+    h2, st2 = _add_ln_fwd(bf16, h1, f2, gb, n2w, n2b)
+    e = torch.empty(0, device=dev)
+    return [h2, s if s is not None else e, qp, kvp, o, stat, x, h1, st1, f1, f2, st2]
+
+
+@torch.library.custom_op("mmemo::block_full_bwd", mutates_args=())
+def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Tensor,
+                      mask: Optional[Tensor], s_prev: Optional[Tensor], s: Optional[Tensor],
+                      saved: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
+                      same_qkv: bool, need_dsprev: bool) -> List[Tensor]:
+    wq, wk, wv, wo, n1w, n1b, n2w, n2b, f1w, f1b, f2w, f2b, ga, gb, gc = params
+    qp, kvp, o, stat, x, h1, st1, f1, f2, st2 = saved
+    B, Lq, d = q.shape
+    Lk = kv.shape[1]
+    dff = f1w.shape[0]
+    dt, dev = _act_dtype(bf16), q.device
+    q = q.contiguous()
+    kv = q if same_qkv else kv.contiguous()
+    dh2 = dh2.contiguous()
+    # LN2: h2 = LN(h1 + b*f2)
+    dh1, df2, dp2 = _add_ln_bwd(bf16, dh2, h1, f2, gb, n2w, None, st2, False, True)
+    # FFN backward; df1 = (df2 W2) * (f1 > 0) fused in the GEMM epilogue
+    df1 = torch.empty(B, Lq, dff, dtype=dt, device=dev)
+    _linear_bwd_x(bf16, df2, _weight(bf16, f2w), df1.view(-1, dff), relu_src=f1.view(-1, dff))
+    dw_f2 = torch.empty(d, dff, dtype=F32, device=dev)
+    db_f2 = torch.zeros(d, dtype=F32, device=dev)
+    _linear_bwd_w(bf16, df2.view(-1, d), f1.view(-1, dff), dw_f2, db_f2)
+    _linear_bwd_x(bf16, df1, _weight(bf16, f1w), dh1.view(-1, d), accumulate=True)
+    dw_f1 = torch.empty(dff, d, dtype=F32, device=dev)
+    db_f1 = torch.zeros(dff, dtype=F32, device=dev)
+    _linear_bwd_w(bf16, df1.view(-1, dff), h1.view(-1, d), dw_f1, db_f1)
+    # LN1: h1 = LN(q + a*x)
+    dq, dx, dp1 = _add_ln_bwd(bf16, dh1, q, x, ga, n1w, None, st1, False, True)
+    # output projection
+    do = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    _linear_bwd_x(bf16, dx, _weight(bf16, wo), do.view(-1, d))
+    dw_o = torch.empty(d, d, dtype=F32, device=dev)
+    _linear_bwd_w(bf16, dx.view(-1, d), o.view(-1, d), dw_o)
+    # attention core
+    dqp = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    dkvp = torch.empty(B, Lk, 2 * d, dtype=dt, device=dev)
+    ds_prev, dc = _attn_bwd(bf16, do, qp, kvp[..., :d], kvp[..., d:], mask, s, s_prev, gc, ds_next,
+                            o, stat, n_heads, dqp, dkvp[..., :d], dkvp[..., d:], need_dsprev)
+    # projections: dq += dqp Wq ; dkv = dkvp [Wk;Wv]
+    _linear_bwd_x(bf16, dqp, _weight(bf16, wq), dq.view(-1, d), accumulate=True)
+    dw_q = torch.empty(d, d, dtype=F32, device=dev)
+    _linear_bwd_w(bf16, dqp.view(-1, d), q.view(-1, d), dw_q)
+    dw_kv = torch.empty(2 * d, d, dtype=F32, device=dev)
+    _linear_bwd_w(bf16, dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)
+    if same_qkv:
+        _linear_bwd_x(bf16, dkvp, _weight(bf16, wk, wv), dq.view(-1, d), accumulate=True)
+        dkv = torch.empty(0, device=dev)
+    else:
+        dkv = torch.empty(B, Lk, d, dtype=dt, device=dev)
+        _linear_bwd_x(bf16, dkvp, _weight(bf16, wk, wv), dkv.view(-1, d))
+    return [dq, dkv, ds_prev if ds_prev is not None else torch.empty(0, device=dev),
+            dc if dc is not None else torch.empty(0, device=dev),
+            dw_q, dw_kv, dw_o, dp1, dp2, dw_f1, db_f1, dw_f2, db_f2]
+
+
+def _block_full_setup(ctx, inputs, output):
+    q, kv, mask, s_prev, params, H, bf16, emit_s, same_qkv = inputs
+    h2, s = output[0], output[1]
+    ctx.save_for_backward(q, kv, mask, s_prev, s if s.numel() else None, *output[2:], *params)
+    ctx.cfg = (H, bf16, same_qkv, len(output) - 2)
+    ctx.set_materialize_grads(False)
+
+
+def _block_full_backward(ctx, grads):
+    dh2, ds_next = grads[0], grads[1]
+    H, bf16, same_qkv, nsaved = ctx.cfg
+    t = ctx.saved_tensors
+    q, kv, mask, s_prev, s = t[:5]
+    saved, params = t[5:5 + nsaved], t[5 + nsaved:]
+    if dh2 is None:
+        dh2 = torch.zeros_like(q)
+    d = q.shape[-1]
+    need_dsprev = s_prev is not None and ctx.needs_input_grad[3]
+    (dq, dkv, ds_prev, dc, dw_q, dw_kv, dw_o, dp1, dp2, dw_f1, db_f1, dw_f2,
+     db_f2) = block_full_bwd_op(dh2, ds_next, q, kv, mask, s_prev, s, saved, params, H, bf16,
+                                same_qkv, need_dsprev)
+    has_prev = s_prev is not None
+    pgrads = [dw_q, dw_kv[:d], dw_kv[d:], dw_o, dp1[1:1 + d], dp1[1 + d:], dp2[1:1 + d],
+              dp2[1 + d:], dw_f1, db_f1, dw_f2, db_f2, dp1[0:1], dp2[0:1],
+              dc if has_prev else None]
+    return (dq, None if same_qkv else dkv, None, ds_prev if need_dsprev else None, pgrads,
+            None, None, None, None)
+
+
+block_full_op.register_autograd(_block_full_backward, setup_context=_block_full_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::block_lite — concat -> minus -> LN block  (cmu-mosei/run.py:236-262, Ren-MME/run.py:188-214)
+# params order: wo(proj) wm(minus, (d,2d)) nw nb c
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::block_lite", mutates_args=())
+def block_lite_op(q: Tensor, kv: Tensor, mask: Optional[Tensor], s_prev: Optional[Tensor],
+                  params: Sequence[Tensor], n_heads: int, bf16: bool, emit_s: bool) -> List[Tensor]:
+    _need_cuda(q, kv)
+    wo, wm, nw, nb, gc = params
+    B, Lq, d = q.shape
+    dt, dev = _act_dtype(bf16), q.device
+    q, kv = q.contiguous(), kv.contiguous()
+    o, s, stat = _attn_fwd(bf16, q, kv, kv, mask, s_prev, gc, n_heads, emit_s)
+    x = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    _linear_fwd(bf16, o, _weight(bf16, wo), None, None, x.view(-1, d))
+    # y = [q | x] Wm^T as two accumulating GEMMs over the halves of Wm (no concat copy)
+    wms = _weight(bf16, wm)
+    y = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    _linear_fwd(bf16, q, wms, None, None, y.view(-1, d), ldw=2 * d, N=d, K=d)
+    _linear_fwd(bf16, x, wms[:, d:], None, None, y.view(-1, d), accumulate=True, ldw=2 * d, N=d, K=d)
+    out, st = _add_ln_fwd(bf16, None, y, None, nw, nb)
+    e = torch.empty(0, device=dev)
+    return [out, s if s is not None else e, o, stat, x, y, st]
+
+
+@torch.library.custom_op("mmemo::block_lite_bwd", mutates_args=())
+def block_lite_bwd_op(dout: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Tensor,
+                      mask: Optional[Tensor], s_prev: Optional[Tensor], s: Optional[Tensor],
+                      saved: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
+                      need_dsprev: bool) -> List[Tensor]:
+    wo, wm, nw, nb, gc = params
+    o, stat, x, y, st = saved
+    B, Lq, d = q.shape
+    Lk = kv.shape[1]
+    dt, dev = _act_dtype(bf16), q.device
+    q, kv = q.contiguous(), kv.contiguous()
+    _, dy, dpn = _add_ln_bwd(bf16, dout.contiguous(), None, y, None, nw, None, st, False, False)
+    wms = _weight(bf16, wm)
+    # minus: dq = dy Wm[:, :d], dx = dy Wm[:, d:], dWm = dy^T [q | x]
+    dq = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    dx = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    _linear_bwd_x(bf16, dy, wms, dq.view(-1, d), ldw=2 * d, N=d, K=d)
+    _linear_bwd_x(bf16, dy, wms[:, d:], dx.view(-1, d), ldw=2 * d, N=d, K=d)
+    dwm = torch.empty(d, 2 * d, dtype=F32, device=dev)
+    _linear_bwd_w(bf16, dy.view(-1, d), q.view(-1, d), dwm)
+    _linear_bwd_w(bf16, dy.view(-1, d), x.view(-1, d), dwm[:, d:])
+    # proj
+    do = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    _linear_bwd_x(bf16, dx, _weight(bf16, wo), do.view(-1, d))
+    dwo = torch.empty(d, d, dtype=F32, device=dev)
+    _linear_bwd_w(bf16, dx.view(-1, d), o.view(-1, d), dwo)
+    # attention core (Q = q, K = V = kv): dk and dv both flow into kv
+    dqa = torch.empty(B, Lq, d, dtype=dt, device=dev)
+    dk = torch.empty(B, Lk, d, dtype=dt, device=dev)
+    dv = torch.empty(B, Lk, d, dtype=dt, device=dev)
+    ds_prev, dc = _attn_bwd(bf16, do, q, kv, kv, mask, s, s_prev, gc, ds_next, o, stat, n_heads,
+                            dqa, dk, dv, need_dsprev)
+    dq = dq + dqa
+    dkv = dk + dv
+    return [dq, dkv, ds_prev if ds_prev is not None else torch.empty(0, device=dev),
+            dc if dc is not None else torch.empty(0, device=dev), dwo, dwm, dpn]
+
+
+def _block_lite_setup(ctx, inputs, output):
+    q, kv, mask, s_prev, params, H, bf16, emit_s = inputs
+    s = output[1]
+    ctx.save_for_backward(q, kv, mask, s_prev, s if s.numel() else None, *output[2:], *params)
+    ctx.cfg = (H, bf16, len(output) - 2)
+    ctx.set_materialize_grads(False)
+
+
+def _block_lite_backward(ctx, grads):
+    dout, ds_next = grads[0], grads[1]
+    H, bf16, nsaved = ctx.cfg
+    t = ctx.saved_tensors
+    q, kv, mask, s_prev, s = t[:5]
+    saved, params = t[5:5 + nsaved], t[5 + nsaved:]
+    if dout is None:
+        dout = torch.zeros_like(q)
+    d = q.shape[-1]
+    need_dsprev = s_prev is not None and ctx.needs_input_grad[3]
+    dq, dkv, ds_prev, dc, dwo, dwm, dpn = block_lite_bwd_op(dout, ds_next, q, kv, mask, s_prev, s,
+                                                            saved, params, H, bf16, need_dsprev)
+    has_prev = s_prev is not None
+    pgrads = [dwo, dwm, dpn[1:1 + d], dpn[1 + d:], dc if has_prev else None]
+    return (dq, dkv, None, ds_prev if need_dsprev else None, pgrads, None, None, None)
+
+
+block_lite_op.register_autograd(_block_lite_backward, setup_context=_block_lite_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::pool  — concat + mean||max pooling over a segment table (float32 output)
+# segs: n_groups*n_slots tensors, group-major; group g tensors are (B, L_g, d)
+# ------------------------------------------------------------------------------------------------
+def _seg_table(segs: Sequence[Tensor], n_groups: int):
+    n_slots = len(segs) // n_groups
+    ptrs = (C.c_void_p * len(segs))(*[t.data_ptr() for t in segs])
+    lens = (C.c_int64 * n_groups)(*[segs[g * n_slots].shape[1] for g in range(n_groups)])
+    return ptrs, lens, n_slots
+
+
+@torch.library.custom_op("mmemo::pool", mutates_args=())
+def pool_op(segs: Sequence[Tensor], n_groups: int) -> Tuple[Tensor, Tensor]:
+    _need_cuda(*segs)
+    segs = [t.contiguous() for t in segs]
+    ptrs, lens, n_slots = _seg_table(segs, n_groups)
+    B, _, d = segs[0].shape
+    bf16 = segs[0].dtype == BF
+    out = torch.empty(B, 2 * n_slots * d, dtype=F32, device=segs[0].device)
+    amax = torch.empty(B, n_slots * d, dtype=torch.int32, device=segs[0].device)
+    _call(f"mmemo_pool_fwd_{_sfx(bf16)}", ptrs, lens, n_groups, n_slots, B, d, out.data_ptr(),
+          amax.data_ptr(), _stream())
+    return out, amax
+
+
+@torch.library.custom_op("mmemo::pool_bwd", mutates_args=())
+def pool_bwd_op(dout: Tensor, amax: Tensor, like: Sequence[Tensor], n_groups: int) -> List[Tensor]:
+    dsegs = [torch.empty(t.shape, dtype=t.dtype, device=t.device) for t in like]
+    ptrs, lens, n_slots = _seg_table(dsegs, n_groups)
+    B, _, d = dsegs[0].shape
+    _call(f"mmemo_pool_bwd_{_sfx(dsegs[0].dtype == BF)}", dout.contiguous().data_ptr(),
+          amax.data_ptr(), ptrs, lens, n_groups, n_slots, B, d, _stream())
+    return dsegs
+
+
+def _pool_setup(ctx, inputs, output):
+    segs, n_groups = inputs
+    ctx.save_for_backward(output[1], *segs)
+    ctx.n_groups = n_groups
+    ctx.set_materialize_grads(False)
+
+
+def _pool_backward(ctx, dout, _damax):
+    amax, *segs = ctx.saved_tensors
+    return pool_bwd_op(dout, amax, segs, ctx.n_groups), None
+
+
+pool_op.register_autograd(_pool_backward, setup_context=_pool_setup)
+
+
+def pool(segs: Sequence[Tensor], n_groups: int = 3) -> Tensor:
+    return pool_op(list(segs), n_groups)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# heads and losses (float32)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::state_transfer", mutates_args=())
+def state_transfer_op(feats: Tensor, trans: Tensor) -> Tensor:
+    _need_cuda(feats)
+    feats, trans = feats.float().contiguous(), trans.contiguous()
+    B, P, C2 = feats.shape
+    out = torch.empty(B, P, C2 // 2, dtype=F32, device=feats.device)
+    _call("mmemo_state_transfer_fwd", feats.data_ptr(), trans.data_ptr(), out.data_ptr(), B, P,
+          C2 // 2, _stream())
+    return out
+
+
+@torch.library.custom_op("mmemo::state_transfer_bwd", mutates_args=())
+def state_transfer_bwd_op(dout: Tensor, feats: Tensor, trans: Tensor, out: Tensor) -> List[Tensor]:
+    feats, trans = feats.float().contiguous(), trans.contiguous()
+    B, P, C2 = feats.shape
+    dfeats = torch.empty_like(feats)
+    dtrans = torch.zeros_like(trans)
+    _call("mmemo_state_transfer_bwd", dout.contiguous().data_ptr(), feats.data_ptr(),
+          trans.data_ptr(), out.data_ptr(), dfeats.data_ptr(), dtrans.data_ptr(), B, P, C2 // 2,
+          _stream())
+    return [dfeats, dtrans]
+
+
+def _st_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0], inputs[1], output)
+
+
+def _st_backward(ctx, dout):
+    feats, trans, out = ctx.saved_tensors
+    dfeats, dtrans = state_transfer_bwd_op(dout, feats, trans, out)
+    return dfeats.to(feats.dtype), dtrans
+
+
+state_transfer_op.register_autograd(_st_backward, setup_context=_st_setup)
+
+
+@torch.library.custom_op("mmemo::bilinear_head", mutates_args=())
+def bilinear_head_op(this_feat: Tensor, last_feat: Tensor, trans: Tensor, gamma: Tensor,
+                     beta: Tensor, w: Tensor, bias: Tensor) -> Tuple[Tensor, Tensor]:
+    _need_cuda(this_feat)
+    th, la = this_feat.float().contiguous(), last_feat.float().contiguous()
+    B, Cn = th.shape
+    out = torch.empty(B, Cn, dtype=F32, device=th.device)
+    z = torch.empty(B, Cn, dtype=F32, device=th.device)
+    _call("mmemo_bilinear_head_fwd", th.data_ptr(), la.data_ptr(), trans.contiguous().data_ptr(),
+          gamma.data_ptr(), beta.data_ptr(), w.contiguous().data_ptr(), bias.data_ptr(),
+          out.data_ptr(), z.data_ptr(), B, Cn, LN_EPS, _stream())
+    return out, z
+
+
+@torch.library.custom_op("mmemo::bilinear_head_bwd", mutates_args=())
+def bilinear_head_bwd_op(dout: Tensor, this_feat: Tensor, last_feat: Tensor, trans: Tensor,
+                         gamma: Tensor, beta: Tensor, w: Tensor, z: Tensor) -> List[Tensor]:
+    th, la = this_feat.float().contiguous(), last_feat.float().contiguous()
+    B, Cn = th.shape
+    dev = th.device
+    dth, dla = torch.empty_like(th), torch.empty_like(la)
+    dT = torch.zeros(Cn, Cn, Cn, dtype=F32, device=dev)
+    dg, db = torch.zeros(Cn, dtype=F32, device=dev), torch.zeros(Cn, dtype=F32, device=dev)
+    dw = torch.zeros(Cn, 2 * Cn, dtype=F32, device=dev)
+    dbias = torch.zeros(Cn, dtype=F32, device=dev)
+    _call("mmemo_bilinear_head_bwd", dout.contiguous().data_ptr(), th.data_ptr(), la.data_ptr(),
+          trans.contiguous().data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+          w.contiguous().data_ptr(), z.data_ptr(), dth.data_ptr(), dla.data_ptr(), dT.data_ptr(),
+          dg.data_ptr(), db.data_ptr(), dw.data_ptr(), dbias.data_ptr(), B, Cn, LN_EPS, _stream())
+    return [dth, dla, dT, dg, db, dw, dbias]
+
+
+def _bh_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs[:6], output[1])
+    ctx.set_materialize_grads(False)
+
+
+def _bh_backward(ctx, dout, _dz):
+    th, la, trans, gamma, beta, w, z = ctx.saved_tensors
+    dth, dla, dT, dg, db, dw, dbias = bilinear_head_bwd_op(dout, th, la, trans, gamma, beta, w, z)
+    return dth.to(th.dtype), dla.to(la.dtype), dT, dg, db, dw, dbias
+
+
+bilinear_head_op.register_autograd(_bh_backward, setup_context=_bh_setup)
+
+
+def bilinear_head(this_feat, last_feat, trans, gamma, beta, w, bias):
+    return bilinear_head_op(this_feat, last_feat, trans, gamma, beta, w, bias)[0]
+
+
+@torch.library.custom_op("mmemo::circle_loss", mutates_args=())
+def circle_loss_op(logits: Tensor, labels: Tensor) -> Tensor:
+    _need_cuda(logits)
+    C_ = logits.shape[-1]
+    lg = logits.float().contiguous()
+    lb = labels.to(F32).contiguous()
+    loss = torch.empty(logits.shape[:-1], dtype=F32, device=logits.device)
+    _call("mmemo_circle_loss_fwd", lg.data_ptr(), lb.data_ptr(), loss.data_ptr(),
+          lg.numel() // C_, C_, _stream())
+    return loss
+
+
+@torch.library.custom_op("mmemo::circle_loss_bwd", mutates_args=())
+def circle_loss_bwd_op(dloss: Tensor, logits: Tensor, labels: Tensor) -> Tensor:
+    C_ = logits.shape[-1]
+    lg = logits.float().contiguous()
+    lb = labels.to(F32).contiguous()
+    dl = torch.empty_like(lg)
+    _call("mmemo_circle_loss_bwd", dloss.to(F32).contiguous().data_ptr(), lg.data_ptr(),
+          lb.data_ptr(), dl.data_ptr(), lg.numel() // C_, C_, _stream())
+    return dl
+
+
+def _cl_setup(ctx, inputs, output):
+    ctx.save_for_backward(*inputs)
+
+
+def _cl_backward(ctx, dloss):
+    logits, labels = ctx.saved_tensors
+    return circle_loss_bwd_op(dloss, logits, labels).to(logits.dtype), None
+
+
+circle_loss_op.register_autograd(_cl_backward, setup_context=_cl_setup)
+
+
+@torch.library.custom_op("mmemo::rdrop_kl", mutates_args=())
+def rdrop_kl_op(logits: Tensor) -> Tensor:
+    _need_cuda(logits)
+    lg = logits.float().contiguous()
+    out = torch.empty((), dtype=F32, device=logits.device)
+    _call("mmemo_rdrop_kl_fwd", lg.data_ptr(), out.data_ptr(), lg.shape[0], lg.shape[1], _stream())
+    return out
+
+
+@torch.library.custom_op("mmemo::rdrop_kl_bwd", mutates_args=())
+def rdrop_kl_bwd_op(dout: Tensor, logits: Tensor) -> Tensor:
+    lg = logits.float().contiguous()
+    dl = torch.empty_like(lg)
+    _call("mmemo_rdrop_kl_bwd", dout.to(F32).contiguous().data_ptr(), lg.data_ptr(), dl.data_ptr(),
+          lg.shape[0], lg.shape[1], _stream())
+    return dl
+
+
+def _rk_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+
+
+def _rk_backward(ctx, dout):
+    (logits,) = ctx.saved_tensors
+    return rdrop_kl_bwd_op(dout, logits).to(logits.dtype)
+
+
+rdrop_kl_op.register_autograd(_rk_backward, setup_context=_rk_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# dropout (counter-based; forward and backward are the same kernel with the same seed)
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::dropout", mutates_args=())
+def dropout_op(x: Tensor, p: float, seed: int) -> Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _call(f"mmemo_dropout_{_sfx(x.dtype == BF)}", x.data_ptr(), y.data_ptr(), x.numel(), p,
+          seed & 0xFFFFFFFFFFFFFFFF, _stream())
+    return y
+
+
+def _do_setup(ctx, inputs, output):
+    ctx.p, ctx.seed = inputs[1], inputs[2]
+
+
+def _do_backward(ctx, dy):
+    return dropout_op(dy, ctx.p, ctx.seed), None, None
+
+
+dropout_op.register_autograd(_do_backward, setup_context=_do_setup)
+
+_dropout_counter = [0]
+
+
+def dropout(x: Tensor, p: float, training: bool) -> Tensor:
+    if not training or p <= 0.0:
+        return x
+    _dropout_counter[0] += 1
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _dropout_counter[0] * 0xD1B54A32D192ED03)
+    return dropout_op(x, float(p), seed & 0x7FFFFFFFFFFFFFFF)

@@ -1,0 +1,242 @@
+"""GPU parity tests of the drop-in modules.
+
+1. every model family vs the committed golden fixtures (= outputs of the REFERENCE's own classes,
+   tests/golden/make_golden.py): float32 mode <= 1e-4 relative on logits, loss, every parameter
+   gradient and input gradients; bf16 mode <= 2e-2 relative on logits;
+2. BASELINE.json's full-size configurations vs the CPU oracle on the same seeded inputs;
+3. size-independent properties at full size (batch-permutation equivariance, DP-shard
+   equivalence of gradients, window folding).
+"""
+import pytest
+import torch
+
+import mmemo_b200
+from mmemo_b200 import ops, synth
+from oracle import mmemo_oracle as O
+from tests import cases
+from tests.cases import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL32, TOLBF = 1e-4, 2e-2
+
+
+class Loss:
+    multi_circle_loss = staticmethod(lambda p, t: ops.circle_loss_op(p, t))
+    multi_loss = staticmethod(lambda p, t: ops.circle_loss_op(p, t).mean())
+    rdrop_kl = staticmethod(lambda p: ops.rdrop_kl_op(p))
+
+
+def to_dev(b):
+    if isinstance(b, dict):
+        return {k: to_dev(v) for k, v in b.items()}
+    if isinstance(b, (list, tuple)):
+        return [to_dev(v) for v in b]
+    return b.to(DEV) if torch.is_tensor(b) else b
+
+
+@pytest.fixture(autouse=True)
+def _defaults():
+    mmemo_b200.robot_demo.DROP = 0.0
+    mmemo_b200.ren_mme.DROP = 0.0
+    mmemo_b200.set_precision("fp32")
+    ops.clear_shadow_cache()
+    yield
+    mmemo_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_golden_fp32(name):
+    c = cases.CASES[name]
+    g = torch.load(cases.golden_path(name))
+    model = c.our_model(mmemo_b200).to(DEV).train()
+    model.load_state_dict(g["state"])
+    logits, loss, grads, igrads = cases.run_module_with_grads(model, c, to_dev(g["batch"]), Loss)
+    assert rel_err(logits, g["logits"]) < TOL32
+    assert abs(loss.item() - g["loss"].item()) < TOL32 * max(1.0, abs(g["loss"].item()))
+    assert set(grads) == set(g["grads"])
+    worst = max((rel_err(grads[k], v), k) for k, v in g["grads"].items())
+    assert worst[0] < TOL32, worst
+    for k, v in g["input_grads"].items():
+        assert rel_err(igrads[k], v) < TOL32, k
+
+
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_golden_bf16_logits(name):
+    c = cases.CASES[name]
+    g = torch.load(cases.golden_path(name))
+    model = c.our_model(mmemo_b200).to(DEV).train()
+    model.load_state_dict(g["state"])
+    with mmemo_b200.precision("bf16"), torch.no_grad():
+        logits = c.call(model, to_dev(g["batch"]))
+    assert rel_err(logits.float(), g["logits"]) < TOLBF
+
+
+def test_golden_eval_mode_no_grad(name="robot_multi_class"):
+    """robot_demo inference path: eval() + no_grad forward (robot_demo.py:610-614)."""
+    c = cases.CASES[name]
+    g = torch.load(cases.golden_path(name))
+    model = c.our_model(mmemo_b200).to(DEV).eval()
+    model.load_state_dict(g["state"])
+    with torch.no_grad():
+        logits = c.call(model, to_dev(g["batch"]))
+    assert rel_err(logits, g["logits"]) < TOL32
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size configurations vs the oracle
+# ------------------------------------------------------------------------------------------------
+def _model_and_state(ctor, seed=0):
+    torch.manual_seed(seed)
+    m = ctor().train()
+    sd = cases.seeded_state(m, seed=1)
+    m.load_state_dict(sd)
+    return m.to(DEV), sd
+
+
+def test_cfg1a_realformer_state_transfer_full_size():
+    """BASELINE config 1 (others/realformer.py defaults): B=32, P=6, seq 50, d=96, 6 heads, 2 layers,
+    with 'no_name' empty windows (all-zero masks, zero loss weight)."""
+    kw = dict(l_dim=300, v_dim=35, a_dim=74, dim=96, l_len=50, v_len=50, a_len=50, n_heads=6,
+              n_layers=2, ffn=2)
+    m, sd = _model_and_state(lambda: mmemo_b200.realformer.State_Transfer(**kw))
+    b = synth.realformer_batch(seed=1234, B=32, P=6, empty_windows=True)
+    c = cases.CASES["realformer_state_transfer"]
+    ref_logits, ref_loss, ref_grads, _ = cases.run_with_grads(
+        lambda s, bb: O.realformer_state_transfer(s, bb["l"], bb["v"], bb["a"], bb["l_mask"],
+                                                  bb["v_mask"], bb["a_mask"], 6, 2),
+        sd, b, c.loss, O, [])
+    logits, loss, grads, _ = cases.run_module_with_grads(
+        m, cases.Case(**{**c.__dict__, "grad_inputs": []}), to_dev(b), Loss)
+    live = b["wmask"].bool()
+    assert rel_err(logits.cpu()[live], ref_logits[live]) < TOL32
+    assert abs(loss.item() - ref_loss.item()) < TOL32 * abs(ref_loss.item())
+    worst = max((rel_err(grads[k], v), k) for k, v in ref_grads.items())
+    assert worst[0] < TOL32, worst
+
+
+def test_cfg2_encoder_chain_full_size_fp32_and_bf16():
+    """BASELINE config 2: 6 x Attention_Block(512, 8), B=64, L=128."""
+    dim, H, nl = 512, 8, 6
+    m, sd = _model_and_state(lambda: cases._RefChain(mmemo_b200.realformer.Attention_Block, dim, H,
+                                                     nl))
+    b = synth.encoder_batch(seed=1234, B=64, L=128, d=dim)
+    pres = [f"blocks.{i}." for i in range(nl)]
+    ref_out, ref_loss, ref_grads, ref_ig = cases.run_with_grads(
+        lambda s, bb: O.encoder_chain(s, pres, bb["x"], bb["mask"], H)[0], sd, b,
+        cases._sq_mean, O, ["x"])
+    c = cases.CASES["encoder_chain"]
+    out, loss, grads, ig = cases.run_module_with_grads(m, c, to_dev(b), Loss)
+    assert rel_err(out, ref_out) < TOL32
+    worst = max((rel_err(grads[k], v), k) for k, v in ref_grads.items())
+    assert worst[0] < TOL32, worst
+    assert rel_err(ig["x"], ref_ig["x"]) < TOL32
+    with mmemo_b200.precision("bf16"):
+        out_bf, loss_bf, grads_bf, _ = cases.run_module_with_grads(m, c, to_dev(b), Loss)
+    assert out_bf.dtype == torch.bfloat16
+    assert rel_err(out_bf.float(), ref_out) < TOLBF
+    # bf16 gradients are not a stated criterion; keep them sane (direction + scale)
+    for k in ("blocks.0.w_qkv.0.weight", "blocks.5.ffn.2.weight", "blocks.3.proj.weight"):
+        a, r = grads_bf[k].flatten().double().cpu(), ref_grads[k].flatten().double()
+        cos = torch.dot(a, r) / (a.norm() * r.norm())
+        assert cos > 0.98, (k, cos.item())
+
+
+def test_cfg1b_mosei_native_lengths_forward():
+    """cmu-mosei/run.py native lengths 20/100/200 (9 (Lq,Lk) combinations), 1 layer."""
+    kw = dict(dim=96, l_len=20, v_len=100, a_len=200, n_heads=6, n_layers=1, ffn=1)
+    m, sd = _model_and_state(lambda: mmemo_b200.cmu_mosei.Concat_Trans(**kw))
+    b = synth.mosei_batch(seed=1234, B=8)
+    with torch.no_grad():
+        ref = O.mosei_concat_trans(sd, b["l"], b["v"], b["a"], b["l_mask"], b["v_mask"], b["a_mask"],
+                                   6, 1)
+        out = cases._rf_call(m, to_dev(b))
+    assert rel_err(out, ref) < TOL32
+
+
+def test_cfg4_renmme_native_shapes_with_rdrop_loss():
+    """Ren-MME/run.py defaults at a reduced batch (16): seq 40/76/275, dims 768/640/205, d=128."""
+    m, sd = _model_and_state(lambda: mmemo_b200.ren_mme.Base_model())
+    b = synth.renmme_batch(seed=1234, B=16)
+    c = cases.CASES["renmme_base_model"]
+    ref_logits, ref_loss, ref_grads, _ = cases.run_with_grads(
+        lambda s, bb: O.renmme_base_model(s, *bb["inputs"]), sd, b, c.loss, O, [])
+    logits, loss, grads, _ = cases.run_module_with_grads(m, c, to_dev(b), Loss)
+    assert rel_err(logits, ref_logits) < TOL32
+    assert abs(loss.item() - ref_loss.item()) < TOL32 * abs(ref_loss.item())
+    worst = max((rel_err(grads[k], v), k) for k, v in ref_grads.items())
+    assert worst[0] < TOL32, worst
+    # R-Drop pairs carry identical inputs and dropout is off -> identical logits
+    assert torch.equal(logits[0::2], logits[1::2])
+
+
+def test_cfg5_robot_demo_native_shapes_batch1_and_32():
+    kw = dict(dim=192, l_len=25, v_len=100, a_len=100, n_heads=6, n_layers=2, ffn=2)
+    m, sd = _model_and_state(lambda: mmemo_b200.robot_demo.Multi_class(**kw))
+    m.eval()
+    for B in (1, 32):
+        b = synth.robot_batch(seed=77, B=B)
+        with torch.no_grad():
+            ref = O.robot_multi_class(sd, b["l"], b["v_256"], b["v_512"], b["v_1024"], b["a"],
+                                      b["l_mask"], b["v_mask"], b["a_mask"], 6, 2)
+            out = cases._robot_call(m, to_dev(b))
+        assert rel_err(out, ref) < TOL32
+
+
+def test_cfg3_rencecps_full_size():
+    m, sd = _model_and_state(lambda: mmemo_b200.rencecps.Concat_Linear(2304))
+    b = synth.rencecps_batch(seed=5, B=128)
+    c = cases.CASES["rencecps_concat_linear"]
+    ref_logits, ref_loss, ref_grads, _ = cases.run_with_grads(
+        lambda s, bb: O.rencecps_concat_linear(s, bb["feat"]), sd, b, c.loss, O, [])
+    logits, loss, grads, _ = cases.run_module_with_grads(
+        m, cases.Case(**{**c.__dict__, "grad_inputs": []}), to_dev(b), Loss)
+    assert rel_err(logits, ref_logits) < TOL32
+    worst = max((rel_err(grads[k], v), k) for k, v in ref_grads.items())
+    assert worst[0] < TOL32, worst
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_batch_permutation_equivariance_and_dp_shard_equivalence():
+    """Every op is per-sample: permuting the batch permutes the logits, and the mean of per-shard
+    gradients equals the full-batch gradient (DP is exact up to fp32 summation)."""
+    kw = dict(dim=96, l_len=50, v_len=50, a_len=50, n_heads=6, n_layers=2, ffn=1)
+    m, _ = _model_and_state(lambda: mmemo_b200.cmu_mosei.Concat_Trans(**kw))
+    b = to_dev(synth.mosei_batch(seed=3, B=16, L=(50, 50, 50)))
+    c = cases.CASES["mosei_concat_trans"]
+    nog = cases.Case(**{**c.__dict__, "grad_inputs": []})
+    logits, _, full, _ = cases.run_module_with_grads(m, nog, b, Loss)
+    perm = torch.randperm(16, generator=torch.Generator().manual_seed(0)).to(DEV)
+    pb = {k: v[perm] for k, v in b.items()}
+    with torch.no_grad():
+        assert torch.allclose(cases._rf_call(m, pb), logits[perm], atol=1e-5)
+    acc = {k: torch.zeros_like(v) for k, v in full.items()}
+    for sh in range(4):
+        sl = slice(4 * sh, 4 * sh + 4)
+        _, _, gsh, _ = cases.run_module_with_grads(m, nog, {k: v[sl] for k, v in b.items()}, Loss)
+        for k in acc:
+            acc[k] += gsh[k] / 4
+    worst = max((rel_err(acc[k], full[k]), k) for k in full)
+    assert worst[0] < 1e-5, worst
+
+
+def test_scores_returned_by_block_match_reference_semantics():
+    """Attention_Block returns post-mask pre-softmax scores, chained with c*S_prev
+    (others/realformer.py:191-204)."""
+    blk = mmemo_b200.realformer.Attention_Block(96, 6).to(DEV)
+    sd = cases.seeded_state(blk, seed=4)
+    blk.load_state_dict(sd)
+    gen = torch.Generator().manual_seed(8)
+    q, kv = torch.randn(4, 50, 96, generator=gen), torch.randn(4, 50, 96, generator=gen)
+    mask = synth.prefix_mask(gen, (4,), 50)
+    with torch.no_grad():
+        o1, s1 = blk(q.to(DEV), kv.to(DEV), kv.to(DEV), mask.to(DEV))
+        o2, s2 = blk(o1, kv.to(DEV), kv.to(DEV), mask.to(DEV), s1)
+        r1, t1 = O.block_full(sd, "", q, kv, kv, mask, 6, None)
+        r2, t2 = O.block_full(sd, "", r1, kv, kv, mask, 6, t1)
+    assert rel_err(o2, r2) < TOL32
+    assert rel_err(s2, t2) < 1e-6   # relative to 1.5e8: masked columns must carry c*(-1e8) - 1e8
+    valid = mask[:, None, None, :].expand_as(t2) > 0
+    assert rel_err(s2.cpu()[valid], t2[valid]) < TOL32

@@ -1,0 +1,110 @@
+"""CPU tests of the host logic with the kernel launches stubbed out.
+
+The C launchers cannot run here (no GPU), so ``ops._call`` is replaced by a recorder.  Outputs
+are uninitialised memory, but everything the Python side is responsible for is exercised: op
+schemas, autograd wiring of every custom op, output shapes/dtypes, which parameters receive a
+gradient (must equal the reference's set, e.g. first-layer ``c`` gets none — SURVEY §7), the
+sequence of launcher names, and state_dict compatibility with the reference fixtures.
+"""
+import pytest
+import torch
+
+import mmemo_b200
+from mmemo_b200 import ops
+from tests import cases
+
+
+class _FakeLib:
+    def mmemo_resattn_uses_tensor_cores(self, *a):
+        return 0
+
+
+@pytest.fixture()
+def stub(monkeypatch):
+    calls = []
+    monkeypatch.setattr(ops, "_call", lambda name, *a: calls.append(name))
+    monkeypatch.setattr(ops, "_need_cuda", lambda *a: None)
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(ops._lib, "load", lambda: _FakeLib())
+    mmemo_b200.robot_demo.DROP = 0.0
+    mmemo_b200.ren_mme.DROP = 0.0
+    ops.clear_shadow_cache()
+    yield calls
+    ops.clear_shadow_cache()
+
+
+class _Loss:
+    multi_circle_loss = staticmethod(lambda p, t: ops.circle_loss_op(p, t))
+    multi_loss = staticmethod(lambda p, t: ops.circle_loss_op(p, t).mean())
+    rdrop_kl = staticmethod(lambda p: ops.rdrop_kl_op(p))
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(cases.CASES))
+def test_module_wiring_matches_reference_grad_set(stub, name, mode):
+    c = cases.CASES[name]
+    g = torch.load(cases.golden_path(name))
+    model = c.our_model(mmemo_b200).train()
+    assert model.load_state_dict(g["state"]).missing_keys == []
+    with mmemo_b200.precision(mode):
+        logits, loss, grads, igrads = cases.run_module_with_grads(model, c, g["batch"], _Loss)
+    assert logits.shape == g["logits"].shape
+    assert set(grads) == set(g["grads"]), sorted(set(grads) ^ set(g["grads"]))
+    for k, v in grads.items():
+        assert v.shape == g["grads"][k].shape and v.dtype == torch.float32, k
+    for k, v in igrads.items():
+        assert v.shape == g["input_grads"][k].shape
+    assert any(n.startswith("mmemo_resattn_fwd") for n in stub) or name == "rencecps_concat_linear"
+    assert any(n.endswith("_bf16") for n in stub) == (mode == "bf16" and name != "rencecps_concat_linear")
+
+
+def test_state_dict_keys_equal_reference(stub):
+    for name, c in cases.CASES.items():
+        g = torch.load(cases.golden_path(name))
+        model = c.our_model(mmemo_b200)
+        assert list(model.state_dict().keys()) == list(g["state"].keys()), name
+        for k, v in model.state_dict().items():
+            assert v.shape == g["state"][k].shape, (name, k)
+
+
+def test_unfused_paths_when_k_is_not_v(stub):
+    blk = mmemo_b200.realformer.Attention_Block(16, 2)
+    q, k, v = torch.randn(2, 5, 16, requires_grad=True), torch.randn(2, 7, 16), torch.randn(2, 7, 16)
+    out, s = blk(q, k, v, torch.ones(2, 7))
+    assert out.shape == (2, 5, 16) and s.shape == (2, 2, 5, 7)
+    out.sum().backward()
+    assert q.grad.shape == q.shape and blk.w_qkv[2].weight.grad is not None
+    lite = mmemo_b200.cmu_mosei.Attention_Block(16, 2, 1)
+    out, s = lite(q, k, v, torch.ones(2, 7))
+    assert out.shape == (2, 5, 16)
+
+
+def test_trunk_skips_unused_score_writes(stub):
+    m = mmemo_b200.cmu_mosei.Multi_ATTN(16, 4, 5, 6, 2, 2, 1, l_dim=8, v_dim=6, a_dim=7)
+    m(torch.randn(2, 4, 8), torch.randn(2, 5, 6), torch.randn(2, 6, 7), torch.ones(2, 4),
+      torch.ones(2, 5), torch.ones(2, 6))
+    flags = [b.emit_scores for b in m.multimodal_blocks]
+    assert flags == [True, False] * 9
+
+
+def test_shadow_cache_tracks_parameter_version(stub):
+    w = torch.nn.Parameter(torch.randn(8, 4))
+    a = ops.shadow_bf16(w)
+    assert ops.shadow_bf16(w) is a
+    with torch.no_grad():
+        w.add_(1.0)
+    assert ops.shadow_bf16(w) is not a
+    assert len(ops._shadow) == 1
+
+
+def test_no_cpu_fallback():
+    """Without the stub, a CPU tensor must raise instead of silently computing on the host."""
+    with pytest.raises(RuntimeError):
+        ops.linear(torch.randn(2, 3), torch.randn(4, 3))
+
+
+def test_position_length_mismatch_raises(stub):
+    m = mmemo_b200.realformer.Multi_class(8, 6, 7, 16, 4, 5, 6, 2, 1, 2)
+    with pytest.raises(RuntimeError):
+        m(torch.randn(2, 9, 8), torch.randn(2, 5, 6), torch.randn(2, 6, 7), torch.ones(2, 9),
+          torch.ones(2, 5), torch.ones(2, 6))
