@@ -38,6 +38,10 @@ typedef void* mmemo_stream_t; /* cudaStream_t */
 /* library / device info */
 int mmemo_version(void);
 const char* mmemo_last_error(void); /* host string describing the last MMEMO_ERR_CUDA */
+/* Scratch for split-K partial tiles of the tcgen05 GEMM (weight-gradient shapes).  The library
+ * never allocates: the host registers one device buffer per process (one process per GPU); kernels
+ * that need more than `bytes` simply do not split.  Launches that use it must be stream-ordered. */
+int mmemo_set_workspace(void* ptr, int64_t bytes);
 /* 1 if (M,N,K,mode) is served by the tcgen05/TMA tensor-core GEMM, 0 if by the SIMT GEMM */
 int mmemo_gemm_uses_tensor_cores(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                  int64_t ldc, int mode);
@@ -86,7 +90,7 @@ int mmemo_linear_bwd_w_bf16(const void* dy, int64_t lddy, const void* x, int x_i
  * because a fully masked row has max = -1e8, where max + log(sum) is absorbed by fp32 rounding.
  * bwd: dS = P*(dP - rowsum(dO*O)) + dS_next; dq = dS k / sqrt(hd); dk = dS^T q / sqrt(hd);
  *      dv = P^T dO; dc += sum(dS*S_prev); ds_prev = c*dS.   s == null -> scores are recomputed
- *      (only legal when s_prev == null).  dq_ws: float32 (B,Lq,H*hd) scratch, needed for the _bf16
+ *      from q, k, mask (and s_prev, c).  dq_ws: float32 (B,Lq,H*hd) scratch, needed for the _bf16
  *      build when Lk > 128 (may be null otherwise).
  * ------------------------------------------------------------------------------------------- */
 int mmemo_resattn_fwd_f32(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,

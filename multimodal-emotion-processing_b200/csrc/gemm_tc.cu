@@ -1,5 +1,364 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 / TMA GEMM for sm_100a:  C[M,N] (+)= epi( A * B^T ), bf16 operands, fp32 accumulation in TMEM.
+//
+//   * operands staged by TMA (cp.async.bulk.tensor, SWIZZLE_128B) into a 3-stage shared-memory ring
+//   * one elected thread issues tcgen05.mma (UMMA 128 x 128 x 16, cta_group::1); accumulator = 128
+//     TMEM columns; completion is signalled to the ring / the epilogue with tcgen05.commit
+//   * both operand "majors" are handled through the UMMA descriptors, so y = x w^T (K-major A and B),
+//     dx = dy w (B MN-major) and dw = dy^T x (A and B MN-major) need no transposes in HBM
+//   * 4 epilogue warps read the accumulator with tcgen05.ld (thread = row) and apply
+//     bias / position table / ReLU / ReLU-mask / accumulate, then store bf16 or fp32 with 16-byte
+//     vector stores
+//   * split-K (gridDim.z) for the weight-gradient shapes (output = one weight matrix, K = B*L rows):
+//     partial tiles go to a caller-provided fp32 workspace, a second tiny kernel reduces them in a
+//     fixed order (deterministic) and applies the epilogue
+// 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// ~99 KB of shared memory and 128 TMEM columns per CTA -> two CTAs per SM, so one CTA's epilogue
+// overlaps the other's main loop.
 #include "common.cuh"
 #include "gemm.h"
-bool gemm_tc_supported(const GemmArgs&, int) { return false; }
-int gemm_tc(const GemmArgs&, int, cudaStream_t) { return MMEMO_ERR_SHAPE; }
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 3;
+constexpr uint32_t A_TILE = BM * BK * 2, B_TILE = BN * BK * 2;
+constexpr int NTHREADS = 192;
+constexpr uint32_t SMEM_BYTES = STAGES * (A_TILE + B_TILE) + 1024 /*align*/ + 256 /*barriers*/;
+
+struct TcArgs {
+  void* C;
+  int64_t ldc;
+  int M, N, K;
+  int c_bf16;
+  const float* bias;
+  const float* pos;
+  int pos_period;
+  const bf16* relu_src;
+  int64_t ldrelu;
+  int relu, accumulate;
+  int a_mn, b_mn;
+  uint32_t idesc;
+  int splits;
+  float* partial;  // [tile][split][BM*BN] when splits > 1
+};
+
+// epilogue on VEC consecutive columns of one row
+template <int VEC>
+__device__ __forceinline__ void apply_store(const TcArgs& a, int64_t m, int n, float* x) {
+  if (n >= a.N) return;
+  const bool full = (n + VEC <= a.N);
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) {
+    const int nn = n + j;
+    if (nn < a.N) {
+      if (a.bias) x[j] += __ldg(a.bias + nn);
+      if (a.pos) x[j] += __ldg(a.pos + (m % a.pos_period) * a.N + nn);
+      if (a.relu) x[j] = fmaxf(x[j], 0.f);
+      if (a.relu_src && !(to_f(a.relu_src[m * a.ldrelu + nn]) > 0.f)) x[j] = 0.f;
+    }
+  }
+  if (a.c_bf16) {
+    bf16* c = static_cast<bf16*>(a.C) + m * a.ldc + n;
+    if (full) {
+      if (a.accumulate) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) x[j] += to_f(c[j]);
+      }
+      uint32_t pk[VEC / 2];
+#pragma unroll
+      for (int j = 0; j < VEC / 2; ++j) {
+        __nv_bfloat162 t = __floats2bfloat162_rn(x[2 * j], x[2 * j + 1]);
+        pk[j] = *reinterpret_cast<uint32_t*>(&t);
+      }
+      if (VEC == 8) *reinterpret_cast<uint4*>(c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      else *reinterpret_cast<uint2*>(c) = make_uint2(pk[0], pk[1]);
+    } else {
+      for (int j = 0; j < VEC && n + j < a.N; ++j)
+        c[j] = from_f<bf16>(a.accumulate ? x[j] + to_f(c[j]) : x[j]);
+    }
+  } else {
+    float* c = static_cast<float*>(a.C) + m * a.ldc + n;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < VEC; j += 4) {
+        float4 v = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+        if (a.accumulate) {
+          const float4 o = *reinterpret_cast<const float4*>(c + j);
+          v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+        }
+        *reinterpret_cast<float4*>(c + j) = v;
+      }
+    } else {
+      for (int j = 0; j < VEC && n + j < a.N; ++j) c[j] = a.accumulate ? x[j] + c[j] : x[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base, sB = base + STAGES * A_TILE;
+  const uint32_t bars = sB + STAGES * B_TILE;          // full[STAGES] empty[STAGES] tmem_full
+  const uint32_t bar_full = bars, bar_empty = bars + 8 * STAGES, bar_acc = bars + 16 * STAGES;
+  const uint32_t tmem_slot = bar_acc + 8;
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // split-K range in units of BK
+  const int kb_total = (a.K + BK - 1) / BK;
+  const int kb_per = (kb_total + a.splits - 1) / a.splits;
+  const int kb_beg = blockIdx.z * kb_per;
+  const int kb_end = min(kb_total, kb_beg + kb_per);
+  const int n_kb = max(kb_end - kb_beg, 0);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(bar_full + 8 * s, 1);
+      tc::mbar_init(bar_empty + 8 * s, 1);
+    }
+    tc::mbar_init(bar_acc, 1);
+    tc::fence_barrier_init();
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, BN);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int it = 0; it < n_kb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc::mbar_wait(bar_empty + 8 * s, ph ^ 1);
+        tc::mbar_expect_tx(bar_full + 8 * s, A_TILE + B_TILE);
+        const int k0 = (kb_beg + it) * BK;
+        const uint32_t da = sA + s * A_TILE, db = sB + s * B_TILE;
+        if (!a.a_mn) {
+          tc::tma_load_2d(da, &tmA, k0, m0, bar_full + 8 * s);            // box {64 k, 128 m}
+        } else {
+          tc::tma_load_2d(da, &tmA, m0, k0, bar_full + 8 * s);            // box {64 m, 64 k}
+          tc::tma_load_2d(da + A_TILE / 2, &tmA, m0 + 64, k0, bar_full + 8 * s);
+        }
+        if (!a.b_mn) {
+          tc::tma_load_2d(db, &tmB, k0, n0, bar_full + 8 * s);
+        } else {
+          tc::tma_load_2d(db, &tmB, n0, k0, bar_full + 8 * s);
+          tc::tma_load_2d(db + B_TILE / 2, &tmB, n0 + 64, k0, bar_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      for (int it = 0; it < n_kb; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        tc::mbar_wait(bar_full + 8 * s, ph);
+        tc::tc_fence_after();
+        const uint32_t da = sA + s * A_TILE, db = sB + s * B_TILE;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: +32 B per 16 k inside the 128 B swizzle row; MN-major: +16 rows of 128 B
+          const uint64_t ad = a.a_mn ? tc::smem_desc_sw128(da + k * 2048, A_TILE / 2, 1024)
+                                     : tc::smem_desc_sw128(da + k * 32, 16, 1024);
+          const uint64_t bd = a.b_mn ? tc::smem_desc_sw128(db + k * 2048, B_TILE / 2, 1024)
+                                     : tc::smem_desc_sw128(db + k * 32, 16, 1024);
+          tc::umma_bf16(tmem_acc, ad, bd, a.idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        tc::umma_commit(bar_empty + 8 * s);   // smem slot reusable once these MMAs have read it
+      }
+      tc::umma_commit(bar_acc);               // accumulator complete
+    }
+  } else {
+    // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int64_t m = (int64_t)m0 + row;
+    if (n_kb > 0) {
+      tc::mbar_wait(bar_acc, 0);
+      tc::tc_fence_after();
+    }
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t r[32];
+      if (n_kb > 0) {
+        tc::tmem_ld32(taddr + ch * 32, r);
+        tc::tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = 0u;
+      }
+      if (a.splits > 1) {
+        float* dst = a.partial +
+                     (((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * a.splits + blockIdx.z) * BM +
+                      row) * BN + ch * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+      } else if (m < a.M) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float x[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[i + j]);
+          apply_store<8>(a, m, n0 + ch * 32 + i, x);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem_acc, BN);
+  }
+}
+
+// sum the split-K partial tiles in a fixed order and apply the epilogue
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcArgs a, int tiles_x) {
+  const int tile = blockIdx.x;
+  const int m0 = (tile / tiles_x) * BM, n0 = (tile % tiles_x) * BN;
+  const float* src = a.partial + (size_t)tile * a.splits * BM * BN;
+  for (int e = threadIdx.x + blockIdx.y * 256; e < BM * BN / 4; e += 256 * gridDim.y) {
+    const int row = e / (BN / 4), c4 = (e % (BN / 4)) * 4;
+    const int64_t m = (int64_t)m0 + row;
+    if (m >= a.M || n0 + c4 >= a.N) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < a.splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(src + ((size_t)s * BM + row) * BN + c4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float x[4] = {acc.x, acc.y, acc.z, acc.w};
+    apply_store<4>(a, m, n0 + c4, x);
+  }
+}
+
+float* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" int mmemo_set_workspace(void* ptr, int64_t bytes) {
+  g_ws = static_cast<float*>(ptr);
+  g_ws_bytes = ptr ? (size_t)bytes : 0;
+  return MMEMO_OK;
+}
+
+PFN_encodeTiled mm_get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+bool mm_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                       const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_encodeTiled enc = mm_get_encode_tiled();
+  if (!enc) return false;
+  cuuint64_t gd[5], gs[5];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i + 1 < rank) gs[i] = strides_bytes[i];
+  }
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+                         const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+bool gemm_tc_supported(const GemmArgs& g, int c_bf16) {
+  if (g.M < 64 || g.N < 64 || g.K < 64) return false;
+  if ((double)g.M * (double)g.N * (double)g.K < (double)(1 << 22)) return false;
+  if (g.M > (1ll << 31) - 256 || g.N > (1ll << 31) - 256 || g.K > (1ll << 31) - 256) return false;
+  const bool a_k = (g.sAk == 1 && g.sAm % 8 == 0), a_mn = (g.sAm == 1 && g.sAk % 8 == 0);
+  const bool b_k = (g.sBk == 1 && g.sBn % 8 == 0), b_mn = (g.sBn == 1 && g.sBk % 8 == 0);
+  if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
+  if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C)) return false;
+  if (g.ldc % (c_bf16 ? 8 : 4) != 0) return false;
+  if (g.relu_src && (!g.relu_src_bf16)) return false;
+  return true;
+}
+
+int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)SMEM_BYTES));
+    attr_done = true;
+  }
+  const bool a_mn = !(g.sAk == 1 && g.sAm % 8 == 0);
+  const bool b_mn = !(g.sBk == 1 && g.sBn % 8 == 0);
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[2], str[1];
+    uint32_t box[2];
+    if (!a_mn) { dims[0] = g.K; dims[1] = g.M; str[0] = g.sAm * 2; box[0] = 64; box[1] = BM; }
+    else       { dims[0] = g.M; dims[1] = g.K; str[0] = g.sAk * 2; box[0] = 64; box[1] = BK; }
+    if (!mm_make_tmap_bf16(&tmA, g.A, 2, dims, str, box)) {
+      mmemo_set_error("cuTensorMapEncodeTiled(A) failed", __FILE__, __LINE__);
+      return MMEMO_ERR_CUDA;
+    }
+    if (!b_mn) { dims[0] = g.K; dims[1] = g.N; str[0] = g.sBn * 2; box[0] = 64; box[1] = BN; }
+    else       { dims[0] = g.N; dims[1] = g.K; str[0] = g.sBk * 2; box[0] = 64; box[1] = BK; }
+    if (!mm_make_tmap_bf16(&tmB, g.B, 2, dims, str, box)) {
+      mmemo_set_error("cuTensorMapEncodeTiled(B) failed", __FILE__, __LINE__);
+      return MMEMO_ERR_CUDA;
+    }
+  }
+  TcArgs a = {};
+  a.C = g.C; a.ldc = g.ldc; a.M = (int)g.M; a.N = (int)g.N; a.K = (int)g.K; a.c_bf16 = c_bf16;
+  a.bias = g.bias; a.pos = g.pos; a.pos_period = (int)g.pos_period;
+  a.relu_src = static_cast<const bf16*>(g.relu_src); a.ldrelu = g.ldrelu;
+  a.relu = g.relu; a.accumulate = g.accumulate;
+  a.a_mn = a_mn; a.b_mn = b_mn;
+  a.idesc = tc::idesc_bf16(BM, BN, a_mn, b_mn);
+  const int tiles_x = (int)cdiv(g.N, BN), tiles_y = (int)cdiv(g.M, BM);
+  const int tiles = tiles_x * tiles_y;
+  const int kb_total = (int)cdiv(g.K, BK);
+  int splits = 1;
+  if (tiles < 120 && kb_total >= 16) {
+    splits = (int)cdiv(296, tiles);
+    if (splits > kb_total / 4) splits = kb_total / 4;
+    if (splits > 16) splits = 16;
+    const size_t per_split = (size_t)tiles * BM * BN * sizeof(float);
+    if (per_split * (size_t)splits > g_ws_bytes) splits = (int)(g_ws_bytes / per_split);
+    if (splits < 2) splits = 1;
+  }
+  a.splits = splits;
+  a.partial = g_ws;
+  dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)splits);
+  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
+  MM_LAUNCH_OK();
+  if (splits > 1) {
+    int ysplit = (int)cdiv(296, tiles);
+    if (ysplit > 16) ysplit = 16;
+    splitk_reduce_kernel<<<dim3((unsigned)tiles, (unsigned)ysplit), 256, 0, st>>>(a, tiles_x);
+    MM_LAUNCH_OK();
+  }
+  return MMEMO_OK;
+}

@@ -38,8 +38,24 @@ def _p(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+_workspace = {}
+WORKSPACE_BYTES = 64 << 20
+
+
+def _ensure_workspace() -> None:
+    """Register the split-K scratch buffer of the tcgen05 GEMM once per process (one GPU each)."""
+    dev = torch.cuda.current_device()
+    if dev not in _workspace:
+        buf = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=f"cuda:{dev}")
+        _lib.check(_lib.load().mmemo_set_workspace(buf.data_ptr(), buf.numel()), "set_workspace")
+        _workspace.clear()
+        _workspace[dev] = buf
+
+
 def _call(name: str, *args) -> None:
     global launch_count
+    if not _workspace:
+        _ensure_workspace()
     launch_count += 1
     _lib.check(getattr(_lib.load(), name)(*args), name)
 

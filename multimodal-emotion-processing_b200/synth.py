@@ -114,9 +114,11 @@ def robot_batch(seed=1234, B=1, L=(25, 100, 100), n_cls=7):
 
 
 def encoder_batch(seed=1234, B=64, L=128, d=512):
-    """BASELINE config 2: x (B, L, d), mask (B, L)."""
+    """BASELINE config 2: x (B, L, d), mask (B, L); dy = a fixed random cotangent so that parity
+    tests can use loss = mean(out * dy) (mean(out^2) of a LayerNorm output is ~constant and has
+    vanishing gradients)."""
     g = gen(seed)
-    return {"x": feats(g, B, L, d), "mask": prefix_mask(g, (B,), L)}
+    return {"x": feats(g, B, L, d), "mask": prefix_mask(g, (B,), L), "dy": feats(g, B, L, d)}
 
 
 def randomize_gates(state: dict, seed: int = 1) -> dict:
