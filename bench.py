@@ -1,0 +1,455 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json: "train samples/s (fwd+bwd)").
+
+Workload (BASELINE configs[1]): the RealFormer residual-attention encoder of others/realformer.py
+standalone — 6 x Attention_Block(d=512, 8 heads), seq 128, batch 64 PER GPU, bf16 activations /
+GEMM operands with fp32 accumulation, fp32 master weights and gradients; one step = zero_grad ->
+forward -> loss = mean(out^2) -> backward (optimizer excluded, like the metric).  Synthetic N(0,1)
+features with prefix masks, random-init weights with the ReZero gates drawn from U(-0.5, 0.5) (at
+their 0 init every attention/FFN gradient is exactly zero).
+
+    python bench.py --gpus N --steps K --warmup W            # ours
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # data parallel, weak scaling
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events around K
+CUDA-graph replays, max over ranks); `e2e` = the same step driven from pinned HOST buffers through
+the public module API with the H2D copy of the inputs and the D2H read of the loss inside the
+timed region; `roofline` = the dominant kernel family timed live with CUDA events in an
+instrumented eager step; `cpu_baseline` = the oracle (CPU port of the reference algorithm) timed on
+this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train samples/s (fwd+bwd)"
+CFG = dict(dim=512, n_heads=8, n_layers=6, ffn=2, seq_len=128, batch_per_gpu=64)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"],
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi in the background during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "100", "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-kernel instrumentation: CUDA events around every libmmemo launch of one eager step
+# ------------------------------------------------------------------------------------------------
+def _algorithmic(name: str, a: tuple):
+    """(flops, bytes, shape-tag) of one launcher call from its C-ABI arguments (DESIGN.md §kernels;
+    formulas of SURVEY.md §8d)."""
+    bf = name.endswith("_bf16")
+    e = 2 if bf else 4
+    if name.startswith("mmemo_linear_fwd"):
+        M, N, K = a[10], a[11], a[12]
+        ex = 4 if a[1] else e
+        return 2 * M * N * K, ex * M * K + e * N * K + e * M * N, f"{M}x{N}x{K}"
+    if name.startswith("mmemo_linear_bwd_x"):
+        M, N, K = a[8], a[9], a[10]
+        return 2 * M * N * K, e * (M * N + N * K + M * K) + (e * M * K if a[6] else 0), f"{M}x{N}x{K}"
+    if name.startswith("mmemo_linear_bwd_w"):
+        M, N, K = a[8], a[9], a[10]
+        return 2 * M * N * K, e * (M * N + M * K) + 4 * N * K, f"{M}x{N}x{K}"
+    if name.startswith("mmemo_resattn_fwd"):
+        B, H, Lq, Lk, hd = a[15:20]
+        d, S = H * hd, B * H * Lq * Lk
+        by = e * B * d * (Lq + 2 * Lk) + 4 * B * Lk + e * B * Lq * d
+        by += e * S * (1 if a[9] else 0) + e * S * (1 if a[11] else 0)
+        return 4 * B * Lq * Lk * d, by, f"B{B}H{H}L{Lq}x{Lk}hd{hd}"
+    if name.startswith("mmemo_resattn_bwd"):
+        B, H, Lq, Lk, hd = a[27:32]
+        d, S = H * hd, B * H * Lq * Lk
+        by = e * B * d * (2 * Lq + 2 * Lk) + e * B * d * (Lq + 2 * Lk) + e * B * Lq * d
+        by += e * S * (1 if a[11] else 0) + e * S * (1 if a[14] else 0)
+        by += e * S * ((1 if a[12] else 0) + (1 if a[24] else 0))
+        fl = (8 if a[11] else 10) * B * Lq * Lk * d
+        return fl, by, f"B{B}H{H}L{Lq}x{Lk}hd{hd}"
+    if name.startswith("mmemo_add_ln_fwd"):
+        M, d = a[11], a[12]
+        return 8 * M * d, e * M * d * (3 if a[0] else 2), f"{M}x{d}"
+    if name.startswith("mmemo_add_ln_bwd"):
+        M, d = a[19], a[20]
+        return 16 * M * d, e * M * d * (3 + (2 if a[2] else 0)), f"{M}x{d}"
+    if name.startswith("mmemo_cast"):
+        return 0, 6 * a[2], f"{a[2]}"
+    return 0, 0, ""
+
+
+def instrumented_step(step_fn):
+    """Run one eager step with a CUDA-event pair around every libmmemo launch (on the launching
+    stream).  Returns {family: dict(n, ms, flops, bytes)} and the step's total event time."""
+    from mmemo_b200 import ops
+    recs = []
+    real = ops._call
+
+    def timed(name, *args):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        real(name, *args)
+        e.record()
+        recs.append((name, args, s, e))
+
+    ops._call = timed
+    try:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        step_fn()
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops._call = real
+    fam = {}
+    for name, args, s, e in recs:
+        fl, by, tag = _algorithmic(name, args)
+        key = name.replace("mmemo_", "") + (":" + tag if tag else "")
+        r = fam.setdefault(key, dict(n=0, ms=0.0, flops=0, bytes=0))
+        r["n"] += 1
+        r["ms"] += s.elapsed_time(e)
+        r["flops"] += fl
+        r["bytes"] += by
+    return fam, t0.elapsed_time(t1)
+
+
+# ------------------------------------------------------------------------------------------------
+def make_oracle_step(batch, dtype=torch.float32):
+    """fwd+bwd of the same workload through the CPU oracle (port of the reference algorithm)."""
+    from mmemo_b200 import ResidualEncoder, synth
+    from oracle import mmemo_oracle as O
+    torch.manual_seed(0)
+    enc = ResidualEncoder(CFG["dim"], CFG["n_heads"], CFG["n_layers"], CFG["ffn"])
+    sd = synth.randomize_gates({k: v.detach().clone() for k, v in enc.state_dict().items()})
+    sd = {k: v.to(dtype).requires_grad_(True) for k, v in sd.items()}
+    pres = [f"blocks.{i}." for i in range(CFG["n_layers"])]
+    x, mask = batch["x"].to(dtype), batch["mask"].to(dtype)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        out = O.encoder_chain(sd, pres, x, mask, CFG["n_heads"])[0]
+        loss = (out.float() ** 2).mean()
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def time_cpu(steps: int, warmup: int, batch_size: int):
+    from mmemo_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    b = synth.encoder_batch(seed=1234, B=batch_size, L=CFG["seq_len"], d=CFG["dim"])
+    step = make_oracle_step(b)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return batch_size / med, med * 1e3
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference algorithm's CPU path (oracle port; the reference scripts are
+    not importable and /root/reference does not exist on the GPU box) on all host cores."""
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    B = CFG["batch_per_gpu"]
+    v, ms = time_cpu(steps, warm, B)
+    cores = torch.get_num_threads()
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} fwd+bwd steps of one B={B} batch, fp32, "
+                                   f"torch CPU {cores} threads (median)"},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_config(n_gpus):
+    return {"workload": "realformer_encoder_chain(6 x Attention_Block(512, 8 heads, ffn 2), "
+                        "seq 128) fwd+bwd, loss=mean(out^2)",
+            "global_batch": CFG["batch_per_gpu"] * n_gpus, "batch_per_gpu": CFG["batch_per_gpu"],
+            "seq_len": CFG["seq_len"], "d_model": CFG["dim"], "n_heads": CFG["n_heads"],
+            "n_layers": CFG["n_layers"], "parallelism": f"dp{n_gpus}",
+            "l2": "no explicit flush: one step streams ~1 GB of activations/scores/weights "
+                  "through the 126 MB L2",
+            "gates": "a,b,c ~ U(-0.5,0.5)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import mmemo_b200
+    from mmemo_b200 import ops, synth
+    from mmemo_b200 import dp as mdp
+
+    W = max(3, args.warmup)
+    K = args.steps
+    mmemo_b200.set_precision(args.precision)
+    torch.manual_seed(0)
+    model = mmemo_b200.ResidualEncoder(CFG["dim"], CFG["n_heads"], CFG["n_layers"], CFG["ffn"])
+    sd = synth.randomize_gates({k: v.detach().clone() for k, v in model.state_dict().items()})
+    model.load_state_dict(sd)
+    model = model.to(dev).train()
+    B, L, d = CFG["batch_per_gpu"], CFG["seq_len"], CFG["dim"]
+    batch = synth.encoder_batch(seed=1234 + rank, B=B, L=L, d=d)
+    host_x, host_m = batch["x"].pin_memory(), batch["mask"].pin_memory()
+    x_dev = torch.empty_like(host_x, device=dev)
+    m_dev = torch.empty_like(host_m, device=dev)
+    x_dev.copy_(host_x)
+    m_dev.copy_(host_m)
+    loss_dev = torch.zeros((), device=dev)
+    host_loss = torch.zeros((), pin_memory=True)
+
+    reducer = mdp.GradReducer(model, world) if world > 1 else None
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        out = model(x_dev, m_dev)
+        loss = (out.float() ** 2).mean()
+        if reducer is not None:
+            reducer.backward(loss)
+        else:
+            loss.backward()
+        loss_dev.copy_(loss.detach())
+
+    # ---- warm-up (eager) then CUDA-graph capture of the whole step ------------------------------
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = None
+    launches_per_step = 0
+    if not args.no_graph:
+        try:
+            ops.clear_shadow_cache()          # capture the fp32->bf16 weight casts with the step
+            model.zero_grad(set_to_none=True)
+            n0 = ops.launch_count
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step()
+            launches_per_step = ops.launch_count - n0
+        except Exception as ex:  # pragma: no cover
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {ex}); eager mode",
+                      file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    if graph is None:
+        n0 = ops.launch_count
+        step()
+        launches_per_step = ops.launch_count - n0
+    run = graph.replay if graph is not None else step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        run()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        run()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / K
+    value = B * world * K / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step --------------------
+    def e2e_step():
+        x_dev.copy_(host_x, non_blocking=True)
+        m_dev.copy_(host_m, non_blocking=True)
+        run()
+        host_loss.copy_(loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(host_loss)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        last_loss = e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = B * world * K / (e2e_ms * 1e-3)
+
+    # ---- per-kernel roofline (rank 0, eager instrumented step) ------------------------------------
+    roof, kernels = None, []
+    if rank == 0:
+        if reducer is not None:
+            reducer.enabled = False
+        fam, total_ms = instrumented_step(step)
+        fam, total_ms = instrumented_step(step)       # second pass: warm
+        if reducer is not None:
+            reducer.enabled = True
+        pk = peaks()
+        ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
+        ksum = sum(r["ms"] for r in fam.values())
+        for key, r in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+            ai = r["flops"] / r["bytes"] if r["bytes"] else 0.0
+            bound = "tensor" if ai > ridge else "hbm"
+            t_s = r["ms"] * 1e-3
+            ach = (r["flops"] / t_s / 1e12) if bound == "tensor" else (r["bytes"] / t_s / 1e9)
+            peak = pk["tf_sust"] if bound == "tensor" else pk["hbm"]
+            kernels.append({"kernel": key, "launches": r["n"], "us_per_launch": 1e3 * r["ms"] / r["n"],
+                            "share": r["ms"] / ksum if ksum else 0.0, "bound": bound,
+                            "achieved": ach, "peak": peak,
+                            "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                            "frac": ach / peak if peak else None})
+        top = kernels[0]
+        roof = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
+                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": None,
+                "share_of_step": top["share"], "peak_source": pk["src"],
+                "how": "CUDA events around each libmmemo launch of one eager step on the launch "
+                       "stream; achieved = algorithmic bytes|flops / summed launch time"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cms = time_cpu(3, 1, B)
+        cpu = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"3 fwd+bwd steps of one B={B} batch (same shapes/seeds), fp32 oracle, "
+                         f"median, {cms:.0f} ms/step"}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision if args.precision != "fp32" else "f32",
+            "data": "synthetic", "config": workload_config(world), "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "samples/s",
+                    "h2d_bytes_per_step": host_x.numel() * 4 + host_m.numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K,
+                    "how": "pinned host x,mask -> cudaMemcpyAsync -> graph replay -> loss D2H + "
+                           "stream sync, every step"},
+            "gpu_launches": launches_per_step * K,
+            "launches_per_step": launches_per_step,
+            "cuda_graph": graph is not None,
+            "loss": last_loss,
+            "roofline": roof, "cpu_baseline": cpu, "kernels": kernels[:12],
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

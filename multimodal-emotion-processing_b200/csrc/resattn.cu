@@ -21,7 +21,7 @@ int mmemo_resattn_fwd_bf16(const void* q, int64_t ldq, const void* k, int64_t ld
                            const void* s_prev, const float* c, void* s_out, void* o, int64_t ldo,
                            float* lse, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t hd,
                            mmemo_stream_t s) {
-  if (mask_rs == 0 && s_out && lse && resattn_tc_supported(Lq, Lk, hd, ldq, ldk, ldv, ldo))
+  if (mask_rs == 0 && lse && resattn_tc_supported(Lq, Lk, hd, ldq, ldk, ldv, ldo))
     return resattn_fwd_tc(q, ldq, k, ldk, v, ldv, mask, mask_bs, s_prev, c, s_out, o, ldo, lse, B,
                           H, Lq, Lk, hd, mm_stream(s));
   return resattn_fwd_simt(1, q, ldq, k, ldk, v, ldv, mask, mask_bs, mask_rs, s_prev, c, s_out, o,

@@ -1,7 +1,310 @@
-// placeholder until the tcgen05 kernel lands
+// Fused residual-attention core on tcgen05 / TMA (bf16, head_dim 64, Lq = Lk = 128): kernel (a).
+//
+// One CTA per (batch, head).  Everything between the projected Q/K/V and the merged-head output
+// happens on chip; the only score-sized HBM traffic is the mandatory read of S_prev and write of S:
+//
+//   TMA  : Q, K, V tiles (128 x 64 bf16, SWIZZLE_128B) and the S_prev tile (128 x 128 bf16)
+//   UMMA : S_acc = Q K^T            (128 x 128 x 64, fp32 accumulator in 128 TMEM columns)
+//   regs : thread = query row; tcgen05.ld the row, s = acc/sqrt(hd) + c*S_prev - 1e8*(1-mask) in the
+//          reference's fp32 op order, round to bf16, write S back into the S_prev tile in shared
+//          memory (in place), exact single-pass softmax (row max, exp, sum)
+//   TMA  : store S for the next layer / backward
+//   UMMA : O_acc = P V              (128 x 64 x 128; P bf16 K-major, V MN-major as loaded)
+//   TMA  : store O / rowsum into the (B, Lq, H*hd) merged-head layout
+//
+// 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = softmax /
+// epilogue.  80 KB shared memory and 256 TMEM columns per CTA -> two CTAs per SM so one tile's
+// loads and stores overlap the other's math.
+#include <math.h>
+
 #include "common.cuh"
 #include "resattn.h"
-bool resattn_tc_supported(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t) { return false; }
-int resattn_fwd_tc(const void*, int64_t, const void*, int64_t, const void*, int64_t, const float*,
-                   int64_t, const void*, const float*, void*, void*, int64_t, float*, int64_t,
-                   int64_t, int64_t, int64_t, int64_t, cudaStream_t) { return MMEMO_ERR_SHAPE; }
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int L = 128, HD = 64;
+constexpr uint32_t TILE_QKV = L * HD * 2;      // 16 KB
+constexpr uint32_t TILE_S = L * L * 2;         // 32 KB (two 64-column halves of 16 KB)
+constexpr int NTHREADS = 192;
+// smem map (offsets from the 1024-aligned base)
+constexpr uint32_t OFF_Q = 0, OFF_K = TILE_QKV, OFF_V = 2 * TILE_QKV, OFF_S = 3 * TILE_QKV;
+constexpr uint32_t OFF_P = OFF_Q;              // P (32 KB) reuses Q|K once S = QK^T has completed
+constexpr uint32_t OFF_O = OFF_V;              // O staging reuses V once O = PV has completed
+constexpr uint32_t OFF_MASK = OFF_S + TILE_S;  // 128 floats
+constexpr uint32_t OFF_BAR = OFF_MASK + 512;
+constexpr uint32_t SMEM_FWD = OFF_BAR + 128 + 1024;
+
+struct FwdArgs {
+  const float* mask;   // (B, Lk) or null
+  int64_t mask_bs;
+  const float* c;      // device scalar or null
+  float* stat;         // (B, H, Lq, 2)
+  int H;
+  int has_prev, write_s;
+  float sqrt_hd;
+  uint32_t idesc_qk, idesc_pv;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+resattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV,
+                      const __grid_constant__ CUtensorMap tmSprev,
+                      const __grid_constant__ CUtensorMap tmSout,
+                      const __grid_constant__ CUtensorMap tmO, const FwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = tc::smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - raw);
+  const uint32_t bar_qk = base + OFF_BAR, bar_v = bar_qk + 8, bar_sp = bar_qk + 16,
+                 bar_s = bar_qk + 24, bar_p = bar_qk + 32, bar_o = bar_qk + 40;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + 64);
+  float* mask_s = reinterpret_cast<float*>(gbase + OFF_MASK);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int row0 = b * L;                       // first row of this batch in the (B*L, ld) views
+  const int srow0 = (b * a.H + h) * L;          // first row in the (B*H*L, L) score views
+
+  if (threadIdx.x == 0) {
+    tc::mbar_init(bar_qk, 1);
+    tc::mbar_init(bar_v, 1);
+    tc::mbar_init(bar_sp, 1);
+    tc::mbar_init(bar_s, 1);
+    tc::mbar_init(bar_p, 128);
+    tc::mbar_init(bar_o, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(base + OFF_BAR + 64, 256);
+    tc::tmem_relinquish();
+  }
+  if (threadIdx.x >= 64) {  // softmax threads stage the mask row (same for every query)
+    const int j = threadIdx.x - 64;
+    mask_s[j] = a.mask ? a.mask[(int64_t)b * a.mask_bs + j] : 1.0f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::tma_prefetch_desc(&tmQ);
+      tc::tma_prefetch_desc(&tmK);
+      tc::tma_prefetch_desc(&tmV);
+      tc::mbar_expect_tx(bar_qk, 2 * TILE_QKV);
+      tc::tma_load_2d(base + OFF_Q, &tmQ, h * HD, row0, bar_qk);
+      tc::tma_load_2d(base + OFF_K, &tmK, h * HD, row0, bar_qk);
+      if (a.has_prev) {
+        tc::mbar_expect_tx(bar_sp, TILE_S);
+        tc::tma_load_2d(base + OFF_S, &tmSprev, 0, srow0, bar_sp);
+        tc::tma_load_2d(base + OFF_S + TILE_S / 2, &tmSprev, 64, srow0, bar_sp);
+      }
+      tc::mbar_expect_tx(bar_v, TILE_QKV);
+      tc::tma_load_2d(base + OFF_V, &tmV, h * HD, row0, bar_v);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---- S = Q K^T ----
+      tc::mbar_wait(bar_qk, 0);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < HD / 16; ++k) {
+        const uint64_t ad = tc::smem_desc_sw128(base + OFF_Q + k * 32, 16, 1024);
+        const uint64_t bd = tc::smem_desc_sw128(base + OFF_K + k * 32, 16, 1024);
+        tc::umma_bf16(tmem_S, ad, bd, a.idesc_qk, k > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(bar_s);
+      // ---- O = P V ----
+      tc::mbar_wait(bar_p, 0);
+      tc::mbar_wait(bar_v, 0);
+      tc::tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < L / 16; ++k) {
+        const uint64_t ad =
+            tc::smem_desc_sw128(base + OFF_P + (k >> 2) * (TILE_S / 2) + (k & 3) * 32, 16, 1024);
+        const uint64_t bd = tc::smem_desc_sw128(base + OFF_V + k * 2048, TILE_QKV, 1024);
+        tc::umma_bf16(tmem_O, ad, bd, a.idesc_pv, k > 0 ? 1u : 0u);
+      }
+      tc::umma_commit(bar_o);
+    }
+  } else {
+    // ================= softmax / epilogue: thread = query row =================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float cval = (a.has_prev && a.c) ? a.c[0] : 0.f;
+    tc::mbar_wait(bar_s, 0);
+    tc::tc_fence_after();
+    if (a.has_prev) tc::mbar_wait(bar_sp, 0);
+    // pass 1: finish the scores, write them (bf16) into the S tile, track the row max
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < 4; ++ch) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_S + lane_off + ch * 32, r);
+      tc::tmem_ld_wait();
+      const uint32_t half = base + OFF_S + (ch >> 1) * (TILE_S / 2);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t addr = half + tc::sw128_offset(row, (ch & 1) * 4 + q4);
+        uint32_t pv[4] = {0u, 0u, 0u, 0u};
+        if (a.has_prev)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(pv[0]), "=r"(pv[1]), "=r"(pv[2]), "=r"(pv[3])
+                       : "r"(addr));
+        uint32_t out[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = ch * 32 + q4 * 8 + e * 2;
+          float s0 = __uint_as_float(r[q4 * 8 + e * 2]) / a.sqrt_hd;
+          float s1 = __uint_as_float(r[q4 * 8 + e * 2 + 1]) / a.sqrt_hd;
+          if (a.has_prev) {
+            s0 = __fadd_rn(s0, __fmul_rn(cval, bf16_lo(pv[e])));
+            s1 = __fadd_rn(s1, __fmul_rn(cval, bf16_hi(pv[e])));
+          }
+          s0 = __fsub_rn(s0, __fmul_rn(1.0e8f, __fsub_rn(1.0f, mask_s[j])));
+          s1 = __fsub_rn(s1, __fmul_rn(1.0e8f, __fsub_rn(1.0f, mask_s[j + 1])));
+          out[e] = pack_bf16(s0, s1);
+          mx = fmaxf(mx, fmaxf(bf16_lo(out[e]), bf16_hi(out[e])));
+        }
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(out[0]),
+                     "r"(out[1]), "r"(out[2]), "r"(out[3])
+                     : "memory");
+      }
+    }
+    // pass 2: e = exp(s - max) rounded to bf16 -> P tile (unnormalised); sum of the rounded values
+    float sum = 0.f;
+    const float kLog2e = 1.4426950408889634f;
+#pragma unroll 1
+    for (int c16 = 0; c16 < 16; ++c16) {
+      const uint32_t off = (c16 >> 3) * (TILE_S / 2) + tc::sw128_offset(row, c16 & 7);
+      uint32_t sv[4], pe[4];
+      asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(sv[0]), "=r"(sv[1]), "=r"(sv[2]), "=r"(sv[3])
+                   : "r"(base + OFF_S + off));
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float e0 = exp2f((bf16_lo(sv[e]) - mx) * kLog2e);
+        const float e1 = exp2f((bf16_hi(sv[e]) - mx) * kLog2e);
+        pe[e] = pack_bf16(e0, e1);
+        sum += bf16_lo(pe[e]) + bf16_hi(pe[e]);
+      }
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(base + OFF_P + off), "r"(pe[0]),
+                   "r"(pe[1]), "r"(pe[2]), "r"(pe[3])
+                   : "memory");
+    }
+    float* st2 = a.stat + 2 * ((int64_t)srow0 + row);
+    st2[0] = mx;
+    st2[1] = sum;
+    // publish S (TMA store) and P (UMMA operand): generic-proxy writes -> async proxy
+    tc::fence_proxy_async();
+    tc::mbar_arrive(bar_p);
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (a.write_s && threadIdx.x == 64) {
+      tc::tma_store_2d(&tmSout, base + OFF_S, 0, srow0);
+      tc::tma_store_2d(&tmSout, base + OFF_S + TILE_S / 2, 64, srow0);
+      tc::tma_store_commit();
+    }
+    // O epilogue
+    tc::mbar_wait(bar_o, 0);
+    tc::tc_fence_after();
+    const float inv = 1.0f / sum;
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      uint32_t r[32];
+      tc::tmem_ld32(tmem_O + lane_off + ch * 32, r);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint32_t out[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          out[e] = pack_bf16(__uint_as_float(r[q4 * 8 + e * 2]) * inv,
+                             __uint_as_float(r[q4 * 8 + e * 2 + 1]) * inv);
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(
+                         base + OFF_O + tc::sw128_offset(row, ch * 4 + q4)),
+                     "r"(out[0]), "r"(out[1]), "r"(out[2]), "r"(out[3])
+                     : "memory");
+      }
+    }
+    tc::fence_proxy_async();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      tc::tma_store_2d(&tmO, base + OFF_O, h * HD, row0);
+      tc::tma_store_commit();
+      tc::tma_store_wait_read();   // shared memory must outlive the bulk stores' reads
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc::tc_fence_after();
+    tc::tmem_dealloc(tmem, 256);
+  }
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+bool make2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems,
+            uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t str[1] = {ld_elems * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return mm_make_tmap_bf16(tm, base, 2, dims, str, box);
+}
+
+}  // namespace
+
+bool resattn_tc_supported(int64_t Lq, int64_t Lk, int64_t hd, int64_t ldq, int64_t ldk,
+                          int64_t ldv, int64_t ldo) {
+  return Lq == L && Lk == L && hd == HD && ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 &&
+         ldo % 8 == 0;
+}
+
+int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                   int64_t ldv, const float* mask, int64_t mask_bs, const void* s_prev,
+                   const float* c, void* s_out, void* o, int64_t ldo, float* lse, int64_t B,
+                   int64_t H, int64_t Lq, int64_t Lk, int64_t hd, cudaStream_t st) {
+  if (B <= 0 || H <= 0) return MMEMO_OK;
+  MM_REQUIRE(q && k && v && o && lse);
+  if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) ||
+      (s_prev && !aligned16(s_prev)) || (s_out && !aligned16(s_out)))
+    return MMEMO_ERR_ARG;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MM_CUDA_OK(cudaFuncSetAttribute(resattn_fwd_tc_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD));
+    attr_done = true;
+  }
+  CUtensorMap tmQ, tmK, tmV, tmSp, tmSo, tmO;
+  const uint64_t rows = (uint64_t)B * L, srows = (uint64_t)B * H * L, d = (uint64_t)H * HD;
+  bool ok = make2d(&tmQ, q, d, rows, ldq, L) && make2d(&tmK, k, d, rows, ldk, L) &&
+            make2d(&tmV, v, d, rows, ldv, L) && make2d(&tmO, o, d, rows, ldo, L);
+  // the score maps fall back to a valid dummy (the Q map) when the tensor is absent
+  ok = ok && (s_prev ? make2d(&tmSp, s_prev, L, srows, L, L) : make2d(&tmSp, q, d, rows, ldq, L));
+  ok = ok && (s_out ? make2d(&tmSo, s_out, L, srows, L, L) : make2d(&tmSo, q, d, rows, ldq, L));
+  if (!ok) {
+    mmemo_set_error("cuTensorMapEncodeTiled failed (resattn_fwd_tc)", __FILE__, __LINE__);
+    return MMEMO_ERR_CUDA;
+  }
+  FwdArgs a = {};
+  a.mask = mask; a.mask_bs = mask_bs; a.c = c; a.stat = lse; a.H = (int)H;
+  a.has_prev = s_prev != nullptr; a.write_s = s_out != nullptr;
+  a.sqrt_hd = (float)sqrt((double)hd);
+  a.idesc_qk = tc::idesc_bf16(L, L, 0, 0);
+  a.idesc_pv = tc::idesc_bf16(L, HD, 0, 1);
+  dim3 grid((unsigned)H, (unsigned)B);
+  resattn_fwd_tc_kernel<<<grid, NTHREADS, SMEM_FWD, st>>>(tmQ, tmK, tmV, tmSp, tmSo, tmO, a);
+  MM_LAUNCH_OK();
+  return MMEMO_OK;
+}

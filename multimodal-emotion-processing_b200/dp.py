@@ -1,0 +1,149 @@
+"""Data-parallel training plumbing: batch sharding and a bucketed gradient all-reduce that is
+overlapped with backward.  The reference has no multi-GPU code (``device = cuda:0`` everywhere,
+others/realformer.py:16); this is the new exchange step SURVEY.md §8(e) asks for.
+
+One process per GPU (``torch.distributed``, NCCL over NVLink/NVSwitch; gloo on CPU for tests).
+Every op of the model is per-sample and the losses are means over equal shards, so averaging the
+per-rank gradients reproduces the single-process full-batch gradient up to fp32 summation order.
+
+Mechanics: parameters are packed into flat float32 buckets in the order their gradients become
+ready (observed during the first backward, like DDP's bucket rebuild; parameters that never
+receive a gradient, e.g. the first-layer ``c`` of each chain, are left out identically on all
+ranks).  A post-accumulate hook copies each gradient into its bucket slot and re-points
+``p.grad`` at the slot; when a bucket is full its all-reduce is issued asynchronously (NCCL runs
+it on its own stream, so it overlaps the rest of backward, also under CUDA-graph capture).
+``finish()`` joins the collectives.  The loss is pre-scaled by 1/world so a SUM reduction yields
+the average (gloo has no AVG).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int, align: int = 1) -> slice:
+    """Contiguous, equal, ``align``-aligned shard of ``range(n)`` for ``rank``.  ``align=2`` keeps
+    the R-Drop pairs (rows 2i, 2i+1; Ren-MME/run.py:143-146,332-333) on one rank."""
+    if n % (world * align) != 0:
+        raise ValueError(f"batch {n} is not divisible into {world} shards aligned to {align}")
+    per = n // world
+    return slice(rank * per, (rank + 1) * per)
+
+
+def shard_batch(batch, rank: int, world: int, align: int = 1):
+    """Slice every tensor of a (nested) batch along dim 0."""
+    if torch.is_tensor(batch):
+        return batch[shard_bounds(batch.shape[0], rank, world, align)]
+    if isinstance(batch, dict):
+        return {k: shard_batch(v, rank, world, align) for k, v in batch.items()}
+    if isinstance(batch, (list, tuple)):
+        return type(batch)(shard_batch(v, rank, world, align) for v in batch)
+    return batch
+
+
+class _Bucket:
+    __slots__ = ("flat", "params", "offsets", "pending", "work")
+
+    def __init__(self, params: Sequence[torch.nn.Parameter]):
+        self.params = list(params)
+        self.offsets, n = [], 0
+        for p in self.params:
+            self.offsets.append(n)
+            n += (p.numel() + 31) // 32 * 32          # 128-byte aligned slots
+        p0 = self.params[0]
+        self.flat = torch.zeros(n, dtype=torch.float32, device=p0.device)
+        self.pending = len(self.params)
+        self.work = None
+
+
+class GradReducer:
+    def __init__(self, model: torch.nn.Module, world_size: Optional[int] = None,
+                 bucket_bytes: int = 8 << 20, group=None):
+        self.model = model
+        self.group = group
+        self.world = world_size if world_size is not None else dist.get_world_size(group)
+        self.bucket_bytes = bucket_bytes
+        self.enabled = True
+        self.buckets: List[_Bucket] = []
+        self._slot: Dict[torch.nn.Parameter, tuple] = {}
+        self._order: List[torch.nn.Parameter] = []
+        self._built = False
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad)
+                       for p in model.parameters() if p.requires_grad]
+
+    # -- bucket construction ---------------------------------------------------------------
+    def _build(self) -> None:
+        """Pack the parameters that received a gradient, in readiness order, into buckets."""
+        cur, size = [], 0
+        for p in self._order:
+            cur.append(p)
+            size += p.numel() * 4
+            if size >= self.bucket_bytes:
+                self.buckets.append(_Bucket(cur))
+                cur, size = [], 0
+        if cur:
+            self.buckets.append(_Bucket(cur))
+        for bi, b in enumerate(self.buckets):
+            for p, off in zip(b.params, b.offsets):
+                self._slot[p] = (bi, off)
+        self._built = True
+
+    def bucket_layout(self) -> List[List[int]]:
+        """[[numel, ...] per bucket] — identical on every rank (asserted by the tests)."""
+        return [[p.numel() for p in b.params] for b in self.buckets]
+
+    # -- hooks -----------------------------------------------------------------------------
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if not self.enabled or self.world == 1:
+            return
+        if not self._built:
+            self._order.append(p)
+            return
+        bi, off = self._slot[p]
+        b = self.buckets[bi]
+        view = b.flat[off:off + p.numel()].view_as(p)
+        view.copy_(p.grad)
+        p.grad = view
+        b.pending -= 1
+        if b.pending == 0:
+            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    # -- public API --------------------------------------------------------------------------
+    def backward(self, loss: torch.Tensor) -> None:
+        """``loss.backward()`` with the gradient exchange overlapped; on return every ``p.grad``
+        holds the average over ranks."""
+        if not self.enabled or self.world == 1:
+            loss.backward()
+            return
+        for b in self.buckets:
+            b.pending = len(b.params)
+            b.work = None
+        (loss / self.world).backward()
+        self.finish()
+
+    def finish(self) -> None:
+        if not self._built:
+            # first step: discover which parameters get gradients and in which order, then reduce
+            # everything bucket by bucket (no overlap this once)
+            self._build()
+            for b in self.buckets:
+                for p, off in zip(b.params, b.offsets):
+                    view = b.flat[off:off + p.numel()].view_as(p)
+                    view.copy_(p.grad)
+                    p.grad = view
+                dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group)
+            return
+        for b in self.buckets:
+            if b.pending != 0:
+                raise RuntimeError("a bucketed parameter received no gradient this step; the set of "
+                                   "used parameters must not change between steps")
+            if b.work is not None:
+                b.work.wait()
+                b.work = None
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

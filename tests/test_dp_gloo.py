@@ -1,0 +1,102 @@
+"""world_size-2 gloo tests (CPU) of the data-parallel host logic in mmemo_b200/dp.py: sharding, the
+bucket layout, unused-parameter handling and that overlapped bucketed all-reduce reproduces the
+single-process full-batch gradients (tolerance 1e-5)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mmemo_b200 import dp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = torch.nn.Linear(12, 40)
+        self.b = torch.nn.Linear(40, 40)
+        self.unused = torch.nn.Parameter(torch.zeros(3))      # never receives a gradient
+        self.c = torch.nn.Linear(40, 5)
+
+    def forward(self, x):
+        return self.c(torch.relu(self.b(torch.relu(self.a(x)))))
+
+
+def _loss(model, x, y):
+    return ((model(x) - y) ** 2).mean()
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = Net()
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(16, 12, generator=g), torch.randn(16, 5, generator=g)
+    red = dp.GradReducer(model, world, bucket_bytes=4096)
+    shard = dp.shard_batch({"x": x, "y": y}, rank, world, align=2)
+    layouts, grads = [], None
+    for step in range(3):                       # step 0 builds the buckets, 1-2 overlap
+        model.zero_grad(set_to_none=True)
+        red.backward(_loss(model, shard["x"], shard["y"]))
+        layouts.append(red.bucket_layout())
+        grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    q.put((rank, layouts[-1], {k: v.tolist() for k, v in grads.items()}))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_matches_full_batch():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda r: r[0])
+    assert res[0][1] == res[1][1] and len(res[0][1]) >= 2          # same multi-bucket layout
+    torch.manual_seed(0)
+    model = Net()
+    g = torch.Generator().manual_seed(1)
+    x, y = torch.randn(16, 12, generator=g), torch.randn(16, 5, generator=g)
+    _loss(model, x, y).backward()
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            assert k not in res[0][2] and k == "unused"
+            continue
+        for r in res:
+            got = torch.tensor(r[2][k])
+            assert torch.allclose(got, p.grad, rtol=1e-5, atol=1e-7), k
+
+
+def test_shard_bounds_keep_rdrop_pairs_together():
+    for world in (1, 2, 4, 8):
+        seen = []
+        for r in range(world):
+            s = dp.shard_bounds(256, r, world, align=2)
+            assert s.start % 2 == 0 and (s.stop - s.start) == 256 // world
+            seen += list(range(s.start, s.stop))
+        assert seen == list(range(256))
+    with pytest.raises(ValueError):
+        dp.shard_bounds(6, 0, 4, align=2)
+
+
+def test_shard_batch_nested():
+    b = {"inputs": [torch.arange(8), torch.arange(16).view(8, 2)], "label": torch.arange(8)}
+    s = dp.shard_batch(b, 1, 2, align=2)
+    assert s["inputs"][0].tolist() == [4, 5, 6, 7] and s["inputs"][1].shape == (4, 2)
