@@ -47,14 +47,36 @@ template <int VEC>
 __device__ __forceinline__ void apply_store(const TcArgs& a, int64_t m, int n, float* x) {
   if (n >= a.N) return;
   const bool full = (n + VEC <= a.N);
+  if (a.bias || a.pos || a.relu) {
 #pragma unroll
-  for (int j = 0; j < VEC; ++j) {
-    const int nn = n + j;
-    if (nn < a.N) {
-      if (a.bias) x[j] += __ldg(a.bias + nn);
-      if (a.pos) x[j] += __ldg(a.pos + (m % a.pos_period) * a.N + nn);
-      if (a.relu) x[j] = fmaxf(x[j], 0.f);
-      if (a.relu_src && !(to_f(a.relu_src[m * a.ldrelu + nn]) > 0.f)) x[j] = 0.f;
+    for (int j = 0; j < VEC; ++j) {
+      const int nn = n + j;
+      if (nn < a.N) {
+        if (a.bias) x[j] += __ldg(a.bias + nn);
+        if (a.pos) x[j] += __ldg(a.pos + (m % a.pos_period) * a.N + nn);
+        if (a.relu) x[j] = fmaxf(x[j], 0.f);
+      }
+    }
+  }
+  if (a.relu_src) {
+    const bf16* rs = a.relu_src + m * a.ldrelu + n;
+    if (full && (a.ldrelu % 8) == 0) {   // one vector load of VEC bf16 (n is a multiple of VEC)
+      uint32_t w[VEC / 2];
+      if (VEC == 8) {
+        const uint4 t = *reinterpret_cast<const uint4*>(rs);
+        w[0] = t.x; w[1] = t.y; w[VEC / 2 - 2] = t.z; w[VEC / 2 - 1] = t.w;
+      } else {
+        const uint2 t = *reinterpret_cast<const uint2*>(rs);
+        w[0] = t.x; w[1] = t.y;
+      }
+#pragma unroll
+      for (int j = 0; j < VEC / 2; ++j) {
+        if (!(__uint_as_float(w[j] << 16) > 0.f)) x[2 * j] = 0.f;
+        if (!(__uint_as_float(w[j] & 0xFFFF0000u) > 0.f)) x[2 * j + 1] = 0.f;
+      }
+    } else {
+      for (int j = 0; j < VEC && n + j < a.N; ++j)
+        if (!(to_f(rs[j]) > 0.f)) x[j] = 0.f;
     }
   }
   if (a.c_bf16) {
@@ -300,7 +322,7 @@ bool gemm_tc_supported(const GemmArgs& g, int c_bf16) {
   if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
   if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C)) return false;
   if (g.ldc % (c_bf16 ? 8 : 4) != 0) return false;
-  if (g.relu_src && (!g.relu_src_bf16)) return false;
+  if (g.relu_src && (!g.relu_src_bf16 || !aligned16(g.relu_src))) return false;
   return true;
 }
 

@@ -9,7 +9,7 @@ namespace {
 
 // NPL = columns per lane (template): d <= 32*NPL.  fwd: NPL<=32 (d<=1024); bwd keeps 7 row
 // arrays in registers, so NPL<=16 (d<=512).
-constexpr int LN_WARPS = 4;
+constexpr int LN_WARPS = 8;
 
 template <typename T, int NPL>
 __global__ void __launch_bounds__(LN_WARPS * 32)
@@ -176,7 +176,7 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
   MM_REQUIRE(dy && x && gamma && mean && rstd && dx && d > 0 && (!relu || y));
   if (d > 512) return MMEMO_ERR_SHAPE;
   int64_t blocks = cdiv(M, LN_WARPS);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;   // few CTAs: one atomic per column per CTA at the end
   const size_t smem = sizeof(float) * LN_WARPS * 2 * d;
 #define MM_LN_BWD(N_)                                                                          \
   add_ln_bwd_kernel<T, N_><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(                     \

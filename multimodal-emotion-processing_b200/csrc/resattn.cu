@@ -46,6 +46,11 @@ int mmemo_resattn_bwd_bf16(const void* d_o, int64_t lddo, const void* q, int64_t
                            int64_t lddk, void* dv, int64_t lddv, void* ds_prev, float* dc,
                            float* dq_ws, int64_t B, int64_t H, int64_t Lq, int64_t Lk, int64_t hd,
                            mmemo_stream_t s) {
+  if (mask_rs == 0 && d_o && q && lse &&
+      resattn_tc_supported(Lq, Lk, hd, ldq, ldk, ldv, lddo) && lddq % 8 == 0 && lddk % 8 == 0 &&
+      lddv % 8 == 0)
+    return resattn_bwd_tc(d_o, lddo, q, ldq, k, ldk, v, ldv, mask, mask_bs, sc, s_prev, c, ds_next,
+                          lse, dq, lddq, dk, lddk, dv, lddv, ds_prev, dc, B, H, mm_stream(s));
   return resattn_bwd_simt(1, d_o, lddo, q, ldq, k, ldk, v, ldv, mask, mask_bs, mask_rs, sc, s_prev,
                           c, ds_next, o, ldo, lse, dq, lddq, dk, lddk, dv, lddv, ds_prev, dc, dq_ws,
                           B, H, Lq, Lk, hd, mm_stream(s));

@@ -19,6 +19,11 @@ int resattn_bwd_simt(int bf16_mode, const void* d_o, int64_t lddo, const void* q
 // tcgen05 / TMA path (bf16, hd == 64, Lq == Lk == 128)
 bool resattn_tc_supported(int64_t Lq, int64_t Lk, int64_t hd, int64_t ldq, int64_t ldk,
                           int64_t ldv, int64_t ldo);
+int resattn_bwd_tc(const void* d_o, int64_t lddo, const void* q, int64_t ldq, const void* k,
+                   int64_t ldk, const void* v, int64_t ldv, const float* mask, int64_t mask_bs,
+                   const void* s, const void* s_prev, const float* c, const void* ds_next,
+                   const float* lse, void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv,
+                   int64_t lddv, void* ds_prev, float* dc, int64_t B, int64_t H, cudaStream_t st);
 int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                    int64_t ldv, const float* mask, int64_t mask_bs, const void* s_prev,
                    const float* c, void* s_out, void* o, int64_t ldo, float* lse, int64_t B,

@@ -179,6 +179,36 @@ def test_resattn_bf16(shape, prev):
     assert rel_err(sd.float().cpu()[valid], s[valid]) < TOLBF
 
 
+@pytest.mark.parametrize("shape", [(2, 6, 50, 50, 16), (3, 8, 128, 128, 64)])
+@pytest.mark.parametrize("prev", [False, True])
+def test_resattn_bf16_backward(shape, prev):
+    """bf16 backward (tcgen05 kernel for hd=64/L=128, SIMT otherwise) against the fp32 oracle run
+    on the same bf16-rounded inputs.  No stated criterion for bf16 gradients; 3e-2 relative."""
+    B, H, Lq, Lk, hd = shape
+    q, k, v, mask, sp, c = _attn_inputs(*shape, seed=2 + sum(shape), prev=prev)
+    rb = lambda t: t.bfloat16().float()
+    leaf = [rb(t).requires_grad_(True) for t in (q, k, v)]
+    cl = c.clone().requires_grad_(True)
+    spl = rb(sp).requires_grad_(True) if prev else None
+    o, s = O.resattn_core(*leaf, mask, H, cl, spl)
+    gen = g(6)
+    do = rb(rnd(gen, *o.shape))
+    ds = rb(rnd(gen, *s.shape) * 0.1 * mask[:, None, None, :])
+    (o * do).sum().backward(retain_graph=True)
+    (s * ds).sum().backward()
+    dl = [t.detach().bfloat16().to(DEV).requires_grad_(True) for t in leaf]
+    cd = c.to(DEV).requires_grad_(True)
+    spd = sp.bfloat16().to(DEV).requires_grad_(True) if prev else None
+    od, sd, _ = ops.resattn_op(*dl, mask.to(DEV), spd, cd if prev else None, H)
+    ((od.float() * do.to(DEV)).sum() + (sd.float() * ds.to(DEV)).sum()).backward()
+    for a, b_ in zip(dl, leaf):
+        assert rel_err(a.grad.float(), b_.grad) < 3e-2
+    if prev:
+        valid = mask[:, None, None, :].expand_as(s) > 0
+        assert rel_err(spd.grad.float().cpu()[valid], spl.grad[valid]) < 3e-2
+        assert abs(cd.grad.item() - cl.grad.item()) < 3e-2 * max(1.0, abs(cl.grad.item()))
+
+
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("M,d", [(150, 96), (64, 512), (33, 128), (10, 16), (5, 192)])
 @pytest.mark.parametrize("res,gate,relu", [(True, True, False), (False, False, True)])
