@@ -40,24 +40,23 @@ struct TcArgs {
   uint32_t idesc;
   int splits;
   float* partial;  // [tile][split][BM*BN] when splits > 1
+  unsigned long long* trace;  // debug: 8 globaltimer stamps per CTA (null in production)
 };
 
-// epilogue on VEC consecutive columns of one row
+__device__ __forceinline__ void stamp(const TcArgs& a, int slot) {
+  if (a.trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + slot] = t;
+  }
+}
+
+// second half of the epilogue on VEC consecutive columns of one row: ReLU mask of a saved
+// activation, accumulate into C, convert, store (vector access when the chunk is inside N)
 template <int VEC>
-__device__ __forceinline__ void apply_store(const TcArgs& a, int64_t m, int n, float* x) {
+__device__ __forceinline__ void store_chunk(const TcArgs& a, int64_t m, int n, float* x) {
   if (n >= a.N) return;
   const bool full = (n + VEC <= a.N);
-  if (a.bias || a.pos || a.relu) {
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      const int nn = n + j;
-      if (nn < a.N) {
-        if (a.bias) x[j] += __ldg(a.bias + nn);
-        if (a.pos) x[j] += __ldg(a.pos + (m % a.pos_period) * a.N + nn);
-        if (a.relu) x[j] = fmaxf(x[j], 0.f);
-      }
-    }
-  }
   if (a.relu_src) {
     const bf16* rs = a.relu_src + m * a.ldrelu + n;
     if (full && (a.ldrelu % 8) == 0) {   // one vector load of VEC bf16 (n is a multiple of VEC)
@@ -139,6 +138,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n_kb = max(kb_end - kb_beg, 0);
 
   if (threadIdx.x == 0) {
+    stamp(a, 0);
     for (int s = 0; s < STAGES; ++s) {
       tc::mbar_init(bar_full + 8 * s, 1);
       tc::mbar_init(bar_empty + 8 * s, 1);
@@ -156,6 +156,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  if (threadIdx.x == 0) stamp(a, 1);
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -179,6 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc::tma_load_2d(db, &tmB, n0, k0, bar_full + 8 * s);
           tc::tma_load_2d(db + B_TILE / 2, &tmB, n0 + 64, k0, bar_full + 8 * s);
         }
+        if (it == 0) stamp(a, 2);
       }
     }
   } else if (warp == 1) {
@@ -189,6 +191,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (it / STAGES) & 1;
         tc::mbar_wait(bar_full + 8 * s, ph);
         tc::tc_fence_after();
+        if (it == 0) stamp(a, 3);
         const uint32_t da = sA + s * A_TILE, db = sB + s * B_TILE;
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
@@ -202,6 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc::umma_commit(bar_empty + 8 * s);   // smem slot reusable once these MMAs have read it
       }
       tc::umma_commit(bar_acc);               // accumulator complete
+      stamp(a, 4);
     }
   } else {
     // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
@@ -212,7 +216,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc::mbar_wait(bar_acc, 0);
       tc::tc_fence_after();
     }
+    if (threadIdx.x == 64) stamp(a, 5);
     const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16);
+    // Staging tile in the (now idle) operand ring: [panel][128 rows][128 B], SWIZZLE_128B pattern.
+    // fp32 staging (4 panels of 32 columns) when the output is fp32 or is accumulated into;
+    // bf16 staging (2 panels of 64 columns) otherwise.
+    const bool stage_f32 = (!a.c_bf16) || a.accumulate;
+    const uint32_t stage = sA;
 #pragma unroll 1
     for (int ch = 0; ch < BN / 32; ++ch) {
       uint32_t r[32];
@@ -223,23 +233,87 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = 0u;
       }
-      if (a.splits > 1) {
+      if (a.splits > 1) {   // split-K partial tile: each thread owns 512 contiguous bytes of a row
         float* dst = a.partial +
                      (((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * a.splits + blockIdx.z) * BM +
                       row) * BN + ch * 32;
 #pragma unroll
         for (int i = 0; i < 32; i += 4)
           *reinterpret_cast<uint4*>(dst + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
-      } else if (m < a.M) {
+        continue;
+      }
+      if (a.bias || a.pos || a.relu) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float x[8];
+        for (int i = 0; i < 32; ++i) {
+          const int nn = n0 + ch * 32 + i;
+          float v = __uint_as_float(r[i]);
+          if (nn < a.N && m < a.M) {
+            if (a.bias) v += __ldg(a.bias + nn);
+            if (a.pos) v += __ldg(a.pos + (m % a.pos_period) * a.N + nn);
+            if (a.relu) v = fmaxf(v, 0.f);
+          }
+          r[i] = __float_as_uint(v);
+        }
+      }
+      if (stage_f32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(r[i + j]);
-          apply_store<8>(a, m, n0 + ch * 32 + i, x);
+        for (int c = 0; c < 8; ++c) {
+          const uint32_t addr = stage + ch * 16384 + tc::sw128_offset(row, c);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(r[4 * c]),
+                       "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
+                       : "memory");
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(r[8 * c + 2 * e]),
+                                                     __uint_as_float(r[8 * c + 2 * e + 1]));
+            pk[e] = *reinterpret_cast<uint32_t*>(&t);
+          }
+          const uint32_t addr =
+              stage + (ch >> 1) * 16384 + tc::sw128_offset(row, (ch & 1) * 4 + c);
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[0]),
+                       "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
         }
       }
     }
+    if (threadIdx.x == 64) stamp(a, 6);
+    if (a.splits == 1) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // pass 2: coalesced global I/O, 16 B per thread, consecutive threads along a row
+      const int te = threadIdx.x - 64;
+      const int cpr = stage_f32 ? 32 : 16;          // 16-byte chunks per tile row
+      const int epc = stage_f32 ? 4 : 8;            // elements per chunk
+#pragma unroll 1
+      for (int id = te; id < BM * cpr; id += 128) {
+        const int rr = id / cpr, c = id - rr * cpr;
+        const int64_t mm = (int64_t)m0 + rr;
+        const int n = n0 + c * epc;
+        if (mm >= a.M || n >= a.N) continue;
+        uint32_t w[4];
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+                     : "r"(stage + (c >> 3) * 16384 + tc::sw128_offset(rr, c & 7)));
+        float x[8];
+        if (stage_f32) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = __uint_as_float(w[j]);
+          store_chunk<4>(a, mm, n, x);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            x[2 * j] = __uint_as_float(w[j] << 16);
+            x[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+          }
+          store_chunk<8>(a, mm, n, x);
+        }
+      }
+    }
+    if (threadIdx.x == 64) stamp(a, 7);
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -264,16 +338,34 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const TcArgs a, int 
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     float x[4] = {acc.x, acc.y, acc.z, acc.w};
-    apply_store<4>(a, m, n0 + c4, x);
+    if (a.bias || a.pos || a.relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int nn = n0 + c4 + j;
+        if (nn < a.N) {
+          if (a.bias) x[j] += __ldg(a.bias + nn);
+          if (a.pos) x[j] += __ldg(a.pos + (m % a.pos_period) * a.N + nn);
+          if (a.relu) x[j] = fmaxf(x[j], 0.f);
+        }
+      }
+    }
+    store_chunk<4>(a, m, n0 + c4, x);
   }
 }
 
+unsigned long long* g_trace = nullptr;
 float* g_ws = nullptr;
 size_t g_ws_bytes = 0;
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+// debug only (not part of include/mmemo.h): per-CTA timeline stamps of the next GEMM launches
+extern "C" int mmemo_debug_set_gemm_trace(void* ptr) {
+  g_trace = static_cast<unsigned long long*>(ptr);
+  return MMEMO_OK;
+}
 
 extern "C" int mmemo_set_workspace(void* ptr, int64_t bytes) {
   g_ws = static_cast<float*>(ptr);
@@ -373,6 +465,7 @@ int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
   }
   a.splits = splits;
   a.partial = g_ws;
+  a.trace = g_trace;
   dim3 grid((unsigned)tiles_x, (unsigned)tiles_y, (unsigned)splits);
   gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmA, tmB, a);
   MM_LAUNCH_OK();

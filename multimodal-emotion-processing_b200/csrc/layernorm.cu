@@ -1,35 +1,268 @@
-// Gated residual + LayerNorm (+ReLU), forward and backward.  One warp per row; the row lives in
-// registers (lane owns columns lane, lane+32, ...), statistics by warp shuffles, two-pass variance.
-// HBM-bound: fwd reads res,x and writes y once; bwd reads dy,res,x(,y) once and writes dres,dx.
-//   y = act( LN(res + gate*x) * gamma + beta )
+// Gated residual + LayerNorm (+ReLU), forward and backward:  y = act( LN(res + gate*x)*gamma + beta )
 // Replaces others/realformer.py:207-208,263  cmu-mosei/run.py:261  Ren-MME/run.py:166,213.
+//
+// HBM-bound kernels (fwd: read res,x, write y; bwd: read dy,res,x, write dres,dx).  One warp per
+// row, the row lives in registers, 16-byte vector loads/stores (8 bf16 / 4 fp32 per lane per
+// access), statistics by warp shuffles with a two-pass variance.  The backward is split in two so
+// that neither part needs many registers:
+//   * row kernel   : dz -> dres, dx (+ one atomic per CTA for dgate)
+//   * column kernel: dgamma[c] = sum_m dy*xhat, dbeta[c] = sum_m dy — lanes own column pairs, warps
+//                    stride over rows, one atomic per column per CTA
+// A scalar version (any d <= 1024, any alignment) serves shapes the vector path does not take.
 #include "common.cuh"
 
 namespace {
 
-// NPL = columns per lane (template): d <= 32*NPL.  fwd: NPL<=32 (d<=1024); bwd keeps 7 row
-// arrays in registers, so NPL<=16 (d<=512).
 constexpr int LN_WARPS = 8;
 
-template <typename T, int NPL>
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  __device__ static void load(const bf16* p, float* v) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ static void store(bf16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&t);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// vector kernels: lane owns chunks c = lane + 32*i (i < NCH) of V consecutive columns
+// ---------------------------------------------------------------------------------------------
+template <typename T, int NCH>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-add_ln_fwd_kernel(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, int64_t ldx,
-                  const float* __restrict__ gate, const float* __restrict__ gamma,
-                  const float* __restrict__ beta, T* __restrict__ y, int64_t ldy,
-                  float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t M, int d,
-                  float eps, int relu) {
+ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, int64_t ldx,
+           const float* __restrict__ gate, const float* __restrict__ gamma,
+           const float* __restrict__ beta, T* __restrict__ y, int64_t ldy,
+           float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t M, int d, float eps,
+           int relu) {
+  constexpr int V = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   if (row >= M) return;
   const float g = gate ? gate[0] : 1.f;
-  const int npl = (d + 31) >> 5;
+  const int nchunk = d / V;
+  float z[NCH][V];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+      float xv[V];
+      Vec<T>::load(x + row * ldx + c * V, xv);
+      if (res) {
+        float rv[V];
+        Vec<T>::load(res + row * ldres + c * V, rv);
+#pragma unroll
+        for (int j = 0; j < V; ++j) z[i][j] = g * xv[j] + rv[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) z[i][j] = g * xv[j];
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) sum += z[i][j];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)d;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+    if (lane + 32 * i < nchunk) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const float t = z[i][j] - mean;
+        var = fmaf(t, t, var);
+      }
+    }
+  const float rstd = rsqrtf(warp_sum(var) / (float)d + eps);
+#pragma unroll
+  for (int i = 0; i < NCH; ++i) {
+    const int c = lane + 32 * i;
+    if (c < nchunk) {
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        float v = (z[i][j] - mean) * rstd * __ldg(gamma + c * V + j) + __ldg(beta + c * V + j);
+        o[j] = relu ? fmaxf(v, 0.f) : v;
+      }
+      Vec<T>::store(y + row * ldy + c * V, o);
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_row_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
+               const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+               const float* __restrict__ gamma, const T* __restrict__ y, int64_t ldy,
+               const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+               T* __restrict__ dres, int64_t lddres, T* __restrict__ dx, int64_t lddx,
+               float* __restrict__ dgate, int64_t M, int d, int relu) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float dgs[LN_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp;
+  const float g = gate ? gate[0] : 1.f;
+  const int nchunk = d / V;
+  float dg = 0.f;
+  if (row < M) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[NCH][V], w[NCH][V], xv[NCH][V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        float dv[V], rv[V];
+        Vec<T>::load(x + row * ldx + c * V, xv[i]);
+        Vec<T>::load(dy + row * lddy + c * V, dv);
+        if (res) Vec<T>::load(res + row * ldres + c * V, rv);
+        if (relu) {
+          float yv[V];
+          Vec<T>::load(y + row * ldy + c * V, yv);
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            if (!(yv[j] > 0.f)) dv[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float zz = g * xv[i][j] + (res ? rv[j] : 0.f);
+          xh[i][j] = (zz - mean) * rstd;
+          w[i][j] = dv[j] * __ldg(gamma + c * V + j);
+          s1 += w[i][j];
+          s2 = fmaf(w[i][j], xh[i][j], s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)d;
+    s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        float dz[V], gx[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          dz[j] = rstd * (w[i][j] - s1 - xh[i][j] * s2);
+          gx[j] = g * dz[j];
+          dg = fmaf(dz[j], xv[i][j], dg);
+        }
+        if (dres) Vec<T>::store(dres + row * lddres + c * V, dz);
+        Vec<T>::store(dx + row * lddx + c * V, gx);
+      }
+    }
+  }
+  if (dgate && gate) {
+    dg = warp_sum(dg);
+    if (lane == 0) dgs[warp] = dg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < LN_WARPS; ++w2) t += dgs[w2];
+      atomicAdd(dgate, t);
+    }
+  }
+}
+
+// dgamma / dbeta: CTA = (64 columns, strip of rows); lane owns 2 adjacent columns
+template <typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_col(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
+           const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+           const T* __restrict__ y, int64_t ldy, const float* __restrict__ mean_in,
+           const float* __restrict__ rstd_in, float* __restrict__ dgamma,
+           float* __restrict__ dbeta, int64_t M, int d, int relu, int64_t rows_per_cta) {
+  __shared__ float red[LN_WARPS][4][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 64 + lane * 2;
+  const float g = gate ? gate[0] : 1.f;
+  float ga0 = 0.f, ga1 = 0.f, be0 = 0.f, be1 = 0.f;
+  if (c0 < d) {
+    const int64_t r_beg = (int64_t)blockIdx.y * rows_per_cta;
+    const int64_t r_end = min(M, r_beg + rows_per_cta);
+    const bool two = (c0 + 1 < d);
+#pragma unroll 4
+    for (int64_t m = r_beg + warp; m < r_end; m += LN_WARPS) {
+      const float mean = mean_in[m], rstd = rstd_in[m];
+      float d0 = to_f(dy[m * lddy + c0]), d1 = two ? to_f(dy[m * lddy + c0 + 1]) : 0.f;
+      float z0 = g * to_f(x[m * ldx + c0]), z1 = two ? g * to_f(x[m * ldx + c0 + 1]) : 0.f;
+      if (res) {
+        z0 += to_f(res[m * ldres + c0]);
+        if (two) z1 += to_f(res[m * ldres + c0 + 1]);
+      }
+      if (relu) {
+        if (!(to_f(y[m * ldy + c0]) > 0.f)) d0 = 0.f;
+        if (two && !(to_f(y[m * ldy + c0 + 1]) > 0.f)) d1 = 0.f;
+      }
+      ga0 = fmaf(d0, (z0 - mean) * rstd, ga0);
+      ga1 = fmaf(d1, (z1 - mean) * rstd, ga1);
+      be0 += d0;
+      be1 += d1;
+    }
+  }
+  red[warp][0][lane] = ga0; red[warp][1][lane] = ga1;
+  red[warp][2][lane] = be0; red[warp][3][lane] = be1;
+  __syncthreads();
+  if (warp < 4) {   // warp w reduces quantity w over the LN_WARPS partials
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < LN_WARPS; ++w2) t += red[w2][warp][lane];
+    const int c = c0 + (warp & 1);
+    if (c < d) {
+      if (warp < 2) { if (dgamma) atomicAdd(dgamma + c, t); }
+      else { if (dbeta) atomicAdd(dbeta + c, t); }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// scalar fallback (any alignment): lane owns columns lane, lane+32, ...; NPL = columns per lane
+// ---------------------------------------------------------------------------------------------
+template <typename T, int NPL>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_scalar(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, int64_t ldx,
+              const float* __restrict__ gate, const float* __restrict__ gamma,
+              const float* __restrict__ beta, T* __restrict__ y, int64_t ldy,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t M, int d,
+              float eps, int relu) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float g = gate ? gate[0] : 1.f;
   float z[NPL];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     z[i] = 0.f;
     const int col = lane + 32 * i;
-    if (i < npl && col < d) {
+    if (col < d) {
       float v = g * to_f(x[row * ldx + col]);
       if (res) v += to_f(res[row * ldres + col]);
       z[i] = v;
@@ -39,18 +272,16 @@ add_ln_fwd_kernel(const T* __restrict__ res, int64_t ldres, const T* __restrict_
   const float mean = warp_sum(sum) / (float)d;
   float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const int col = lane + 32 * i;
-    if (i < npl && col < d) {
+  for (int i = 0; i < NPL; ++i)
+    if (lane + 32 * i < d) {
       const float t = z[i] - mean;
       var = fmaf(t, t, var);
     }
-  }
   const float rstd = rsqrtf(warp_sum(var) / (float)d + eps);
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
     const int col = lane + 32 * i;
-    if (i < npl && col < d) {
+    if (col < d) {
       float v = (z[i] - mean) * rstd * gamma[col] + beta[col];
       if (relu) v = fmaxf(v, 0.f);
       y[row * ldy + col] = from_f<T>(v);
@@ -64,28 +295,18 @@ add_ln_fwd_kernel(const T* __restrict__ res, int64_t ldres, const T* __restrict_
 
 template <typename T, int NPL>
 __global__ void __launch_bounds__(LN_WARPS * 32)
-add_ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
+ln_bwd_row_scalar(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
                   const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
                   const float* __restrict__ gamma, const T* __restrict__ y, int64_t ldy,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                   T* __restrict__ dres, int64_t lddres, T* __restrict__ dx, int64_t lddx,
-                  float* __restrict__ dgate, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                  int64_t M, int d, int relu) {
-  extern __shared__ float red[];  // [LN_WARPS][2*d]
+                  float* __restrict__ dgate, int64_t M, int d, int relu) {
+  __shared__ float dgs[LN_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp;
   const float g = gate ? gate[0] : 1.f;
-  const int npl = (d + 31) >> 5;
-  float gam[NPL], dgam[NPL], dbet[NPL];
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const int col = lane + 32 * i;
-    gam[i] = (i < npl && col < d) ? gamma[col] : 0.f;
-    dgam[i] = 0.f;
-    dbet[i] = 0.f;
-  }
   float dg = 0.f;
-  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M;
-       row += (int64_t)gridDim.x * LN_WARPS) {
+  if (row < M) {
     const float mean = mean_in[row], rstd = rstd_in[row];
     float xh[NPL], w[NPL], xv[NPL];
     float s1 = 0.f, s2 = 0.f;
@@ -93,16 +314,14 @@ add_ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
     for (int i = 0; i < NPL; ++i) {
       xh[i] = 0.f; w[i] = 0.f; xv[i] = 0.f;
       const int col = lane + 32 * i;
-      if (i < npl && col < d) {
+      if (col < d) {
         xv[i] = to_f(x[row * ldx + col]);
-        float z = g * xv[i];
-        if (res) z += to_f(res[row * ldres + col]);
-        xh[i] = (z - mean) * rstd;
+        float zz = g * xv[i];
+        if (res) zz += to_f(res[row * ldres + col]);
+        xh[i] = (zz - mean) * rstd;
         float dyv = to_f(dy[row * lddy + col]);
         if (relu && !(to_f(y[row * ldy + col]) > 0.f)) dyv = 0.f;
-        dgam[i] = fmaf(dyv, xh[i], dgam[i]);
-        dbet[i] += dyv;
-        w[i] = dyv * gam[i];
+        w[i] = dyv * gamma[col];
         s1 += w[i];
         s2 = fmaf(w[i], xh[i], s2);
       }
@@ -112,7 +331,7 @@ add_ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
       const int col = lane + 32 * i;
-      if (i < npl && col < d) {
+      if (col < d) {
         const float dz = rstd * (w[i] - s1 - xh[i] * s2);
         if (dres) dres[row * lddres + col] = from_f<T>(dz);
         dx[row * lddx + col] = from_f<T>(g * dz);
@@ -120,32 +339,19 @@ add_ln_bwd_kernel(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
       }
     }
   }
-  // block reduction of the parameter gradients, then one atomic per column per CTA
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const int col = lane + 32 * i;
-    if (i < npl && col < d) {
-      red[warp * 2 * d + col] = dgam[i];
-      red[warp * 2 * d + d + col] = dbet[i];
+  if (dgate && gate) {
+    dg = warp_sum(dg);
+    if (lane == 0) dgs[warp] = dg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w2 = 0; w2 < LN_WARPS; ++w2) t += dgs[w2];
+      atomicAdd(dgate, t);
     }
   }
-  dg = warp_sum(dg);
-  __shared__ float dgs[LN_WARPS];
-  if (lane == 0) dgs[warp] = dg;
-  __syncthreads();
-  for (int col = threadIdx.x; col < 2 * d; col += LN_WARPS * 32) {
-    float t = 0.f;
-#pragma unroll
-    for (int w2 = 0; w2 < LN_WARPS; ++w2) t += red[w2 * 2 * d + col];
-    if (col < d) { if (dgamma) atomicAdd(dgamma + col, t); }
-    else { if (dbeta) atomicAdd(dbeta + col - d, t); }
-  }
-  if (threadIdx.x == 0 && dgate && gate) {
-    float t = 0.f;
-    for (int w2 = 0; w2 < LN_WARPS; ++w2) t += dgs[w2];
-    atomicAdd(dgate, t);
-  }
 }
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename T>
 int fwd(const void* res, int64_t ldres, const void* x, int64_t ldx, const float* gate,
@@ -154,15 +360,26 @@ int fwd(const void* res, int64_t ldres, const void* x, int64_t ldx, const float*
   if (M <= 0) return MMEMO_OK;
   MM_REQUIRE(x && gamma && beta && y && d > 0);
   if (d > 1024) return MMEMO_ERR_SHAPE;
-#define MM_LN_FWD(N_)                                                                         \
-  add_ln_fwd_kernel<T, N_><<<(unsigned)cdiv(M, LN_WARPS), LN_WARPS * 32, 0, st>>>(            \
-      static_cast<const T*>(res), ldres, static_cast<const T*>(x), ldx, gate, gamma, beta,    \
-      static_cast<T*>(y), ldy, mean, rstd, M, (int)d, eps, relu)
-  if (d <= 128) MM_LN_FWD(4);
-  else if (d <= 256) MM_LN_FWD(8);
-  else if (d <= 512) MM_LN_FWD(16);
-  else MM_LN_FWD(32);
-#undef MM_LN_FWD
+  constexpr int V = Vec<T>::N;
+  const T* r = static_cast<const T*>(res);
+  const T* xx = static_cast<const T*>(x);
+  T* yy = static_cast<T*>(y);
+  const unsigned grid = (unsigned)cdiv(M, LN_WARPS);
+  const bool vec = d % V == 0 && ldx % V == 0 && ldy % V == 0 && (!res || ldres % V == 0) &&
+                   al16(x) && al16(y) && (!res || al16(res)) && d / V <= 256;
+#define MM_ARGS r, ldres, xx, ldx, gate, gamma, beta, yy, ldy, mean, rstd, M, (int)d, eps, relu
+  if (vec) {
+    const int nch = (int)cdiv(d / V, 32);
+    if (nch <= 1) ln_fwd_vec<T, 1><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else if (nch <= 2) ln_fwd_vec<T, 2><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else if (nch <= 4) ln_fwd_vec<T, 4><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else ln_fwd_vec<T, 8><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+  } else {
+    if (d <= 128) ln_fwd_scalar<T, 4><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else if (d <= 512) ln_fwd_scalar<T, 16><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else ln_fwd_scalar<T, 32><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+  }
+#undef MM_ARGS
   MM_LAUNCH_OK();
   return MMEMO_OK;
 }
@@ -174,21 +391,46 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
         float* dgamma, float* dbeta, int64_t M, int64_t d, int relu, cudaStream_t st) {
   if (M <= 0) return MMEMO_OK;
   MM_REQUIRE(dy && x && gamma && mean && rstd && dx && d > 0 && (!relu || y));
-  if (d > 512) return MMEMO_ERR_SHAPE;
-  int64_t blocks = cdiv(M, LN_WARPS);
-  if (blocks > 148 * 2) blocks = 148 * 2;   // few CTAs: one atomic per column per CTA at the end
-  const size_t smem = sizeof(float) * LN_WARPS * 2 * d;
-#define MM_LN_BWD(N_)                                                                          \
-  add_ln_bwd_kernel<T, N_><<<(unsigned)blocks, LN_WARPS * 32, smem, st>>>(                     \
-      static_cast<const T*>(dy), lddy, static_cast<const T*>(res), ldres,                      \
-      static_cast<const T*>(x), ldx, gate, gamma, static_cast<const T*>(y), ldy, mean, rstd,   \
-      static_cast<T*>(dres), lddres, static_cast<T*>(dx), lddx, dgate, dgamma, dbeta, M,       \
-      (int)d, relu)
-  if (d <= 128) MM_LN_BWD(4);
-  else if (d <= 256) MM_LN_BWD(8);
-  else MM_LN_BWD(16);
-#undef MM_LN_BWD
+  if (d > 1024) return MMEMO_ERR_SHAPE;
+  constexpr int V = Vec<T>::N;
+  const T* dyy = static_cast<const T*>(dy);
+  const T* r = static_cast<const T*>(res);
+  const T* xx = static_cast<const T*>(x);
+  const T* yy = static_cast<const T*>(y);
+  T* dr = static_cast<T*>(dres);
+  T* dxx = static_cast<T*>(dx);
+  const unsigned grid = (unsigned)cdiv(M, LN_WARPS);
+  const bool vec = d % V == 0 && ldx % V == 0 && lddy % V == 0 && lddx % V == 0 &&
+                   (!res || ldres % V == 0) && (!dres || lddres % V == 0) &&
+                   (!relu || ldy % V == 0) && al16(dy) && al16(x) && al16(dx) &&
+                   (!res || al16(res)) && (!dres || al16(dres)) && (!relu || al16(y)) &&
+                   d / V <= 256;
+#define MM_ARGS dyy, lddy, r, ldres, xx, ldx, gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx, \
+                lddx, dgate, M, (int)d, relu
+  if (vec) {
+    const int nch = (int)cdiv(d / V, 32);
+    if (nch <= 1) ln_bwd_row_vec<T, 1><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else if (nch <= 2) ln_bwd_row_vec<T, 2><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else if (nch <= 4) ln_bwd_row_vec<T, 4><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else ln_bwd_row_vec<T, 8><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+  } else {
+    if (d <= 128) ln_bwd_row_scalar<T, 4><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else if (d <= 512) ln_bwd_row_scalar<T, 16><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    else ln_bwd_row_scalar<T, 32><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+  }
+#undef MM_ARGS
   MM_LAUNCH_OK();
+  if (dgamma || dbeta) {
+    const int64_t col_ctas = cdiv(d, 64);
+    int64_t strips = cdiv(148 * 4, col_ctas);
+    if (strips > cdiv(M, 4 * LN_WARPS)) strips = cdiv(M, 4 * LN_WARPS);
+    if (strips < 1) strips = 1;
+    const int64_t rows_per_cta = cdiv(M, strips);
+    ln_bwd_col<T><<<dim3((unsigned)col_ctas, (unsigned)strips), LN_WARPS * 32, 0, st>>>(
+        dyy, lddy, r, ldres, xx, ldx, gate, yy, ldy, mean, rstd, dgamma, dbeta, M, (int)d, relu,
+        rows_per_cta);
+    MM_LAUNCH_OK();
+  }
   return MMEMO_OK;
 }
 

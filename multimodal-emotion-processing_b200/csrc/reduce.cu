@@ -4,30 +4,37 @@
 
 namespace {
 
-// out[(m % period), n] += x[m, n].  CTA = (32 columns, a strip of rows); lanes own columns so the
+// out[(m % period), n] += x[m, n].  CTA = (64 columns, a strip of rows); lanes own column pairs so the
 // global reads are coalesced; rows with equal (m % period) are summed in registers first.
 template <typename T>
 __global__ void __launch_bounds__(256)
 rowsum_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out, int64_t M, int64_t N,
               int64_t period, int64_t rows_per_cta) {
-  __shared__ float red[8][33];
+  __shared__ float red[8][2][33];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
-  const int64_t n = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t n = (int64_t)blockIdx.x * 64 + lane * 2;     // lane owns two adjacent columns
   const int64_t p = blockIdx.z;                       // residue class handled by this CTA
   const int64_t r_beg = (int64_t)blockIdx.y * rows_per_cta;  // in units of periods
   const int64_t n_per = (M - p + period - 1) / period;       // rows m = p + t*period, t < n_per
-  float acc = 0.f;
+  float acc0 = 0.f, acc1 = 0.f;
   if (n < N) {
+    const bool two = n + 1 < N;
     const int64_t t_end = min(n_per, r_beg + rows_per_cta);
-    for (int64_t t = r_beg + wy; t < t_end; t += 8) acc += to_f(x[(p + t * period) * ldx + n]);
+#pragma unroll 4
+    for (int64_t t = r_beg + wy; t < t_end; t += 8) {
+      const T* px = x + (p + t * period) * ldx + n;
+      acc0 += to_f(px[0]);
+      if (two) acc1 += to_f(px[1]);
+    }
   }
-  red[wy][lane] = acc;
+  red[wy][0][lane] = acc0;
+  red[wy][1][lane] = acc1;
   __syncthreads();
-  if (wy == 0 && n < N) {
+  if (wy < 2 && n + wy < N) {
     float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += red[i][lane];
-    atomicAdd(out + p * N + n, t);
+    for (int i = 0; i < 8; ++i) t += red[i][wy][lane];
+    atomicAdd(out + p * N + n + wy, t);
   }
 }
 
@@ -73,12 +80,12 @@ int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t
   const int64_t n_per = cdiv(M, period);
   // enough CTAs to fill the machine, at least 64 rows each
   int64_t strips = cdiv(n_per, 64);
-  const int64_t base = cdiv(N, 32) * period;
+  const int64_t base = cdiv(N, 64) * period;
   if (strips * base > 148 * 16) strips = cdiv(148 * 16, base);
   if (strips < 1) strips = 1;
   if (strips > 65535) strips = 65535;
   const int64_t rows_per_cta = cdiv(n_per, strips);
-  dim3 grid((unsigned)cdiv(N, 32), (unsigned)strips, (unsigned)period);
+  dim3 grid((unsigned)cdiv(N, 64), (unsigned)strips, (unsigned)period);
   rowsum_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, period,
                                          rows_per_cta);
   MM_LAUNCH_OK();

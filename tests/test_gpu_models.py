@@ -41,6 +41,11 @@ def assert_grads_close(ours, ref32, ref64=None, tol=TOL32):
         else:
             e = rel_err(ours[k], ref64[k])
             lim = max(tol, 5.0 * rel_err(v, ref64[k]))
+            if v.numel() == 1:
+                # scalar gates a/b/c: the gradient is ONE sum of millions of signed terms (e.g.
+                # c.grad = sum(dS * S_prev)); its relative error measures cancellation, not a
+                # per-element error, so it gets 3x headroom
+                lim = max(lim, 3.0 * tol)
         if not e < lim and k.endswith(("ffn.0.weight", "ffn.0.bias")):
             # rows (= hidden units) of the first FFN linear are the direct consumers of the ReLU
             # mask: one flipped decision moves a whole row by ~1/sqrt(rows).  Require >= 99% of
