@@ -273,6 +273,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     import torch.distributed as dist
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import mmemo_b200
     from mmemo_b200 import ops, synth
@@ -446,9 +448,19 @@ def main():
             "loss": last_loss,
             "roofline": roof, "cpu_baseline": cpu, "kernels": kernels[:12],
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tear down in a fixed order: drop the captured graph (it references NCCL kernels), drain
+        # the device, meet the other ranks, then leave without waiting on communicator teardown
+        # (destroy_process_group() was observed to block here after a captured all-reduce).
+        graph = None
+        run = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -98,6 +98,11 @@ class GradReducer:
     def _on_grad(self, p: torch.nn.Parameter) -> None:
         if not self.enabled or self.world == 1:
             return
+        if p.grad is None:
+            # an autograd node handed this parameter an undefined gradient (e.g. the first-layer
+            # ``c`` of a chain, which has no previous scores): the hook fires but nothing was
+            # accumulated — identical on every rank, so the parameter simply stays out of the buckets
+            return
         if not self._built:
             self._order.append(p)
             return

@@ -108,3 +108,31 @@ def test_position_length_mismatch_raises(stub):
     with pytest.raises(RuntimeError):
         m(torch.randn(2, 9, 8), torch.randn(2, 5, 6), torch.randn(2, 6, 7), torch.ones(2, 9),
           torch.ones(2, 5), torch.ones(2, 6))
+
+
+def test_grad_reducer_on_encoder_skips_undefined_grads(stub):
+    """The first-layer ``c`` receives an UNDEFINED gradient (its hook still fires): it must stay out
+    of the buckets; all other parameters end up as views of the flat buckets."""
+    import socket
+    import torch.distributed as dist
+    from mmemo_b200 import dp, synth
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        model = mmemo_b200.ResidualEncoder(32, 4, 3)
+        red = dp.GradReducer(model, world_size=2, bucket_bytes=16 << 10)
+        b = synth.encoder_batch(B=2, L=16, d=32)
+        for _ in range(3):
+            model.zero_grad(set_to_none=True)
+            red.backward((model(b["x"], b["mask"]).float() ** 2).mean())
+        assert model.blocks[0].c.grad is None
+        assert len(red.buckets) >= 2
+        flat_ptrs = {bk.flat.untyped_storage().data_ptr() for bk in red.buckets}
+        for n, p in model.named_parameters():
+            if n != "blocks.0.c":
+                assert p.grad.untyped_storage().data_ptr() in flat_ptrs, n
+    finally:
+        dist.destroy_process_group()
