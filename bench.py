@@ -121,7 +121,8 @@ def _algorithmic(name: str, a: tuple):
         d, S = H * hd, B * H * Lq * Lk
         by = e * B * d * (Lq + 2 * Lk) + 4 * B * Lk + e * B * Lq * d
         by += e * S * (1 if a[9] else 0) + e * S * (1 if a[11] else 0)
-        return 4 * B * Lq * Lk * d, by, f"B{B}H{H}L{Lq}x{Lk}hd{hd}"
+        return (4 * B * Lq * Lk * d, by,
+                f"B{B}H{H}L{Lq}x{Lk}hd{hd}{'+prev' if a[9] else ''}{'+S' if a[11] else ''}")
     if name.startswith("mmemo_resattn_bwd"):
         B, H, Lq, Lk, hd = a[27:32]
         d, S = H * hd, B * H * Lq * Lk
@@ -129,7 +130,8 @@ def _algorithmic(name: str, a: tuple):
         by += e * S * (1 if a[11] else 0) + e * S * (1 if a[14] else 0)
         by += e * S * ((1 if a[12] else 0) + (1 if a[24] else 0))
         fl = (8 if a[11] else 10) * B * Lq * Lk * d
-        return fl, by, f"B{B}H{H}L{Lq}x{Lk}hd{hd}"
+        return (fl, by, f"B{B}H{H}L{Lq}x{Lk}hd{hd}{'+S' if a[11] else '+recompute'}"
+                        f"{'+prev' if a[12] else ''}{'+dSnext' if a[14] else ''}")
     if name.startswith("mmemo_add_ln_fwd"):
         M, d = a[11], a[12]
         return 8 * M * d, e * M * d * (3 if a[0] else 2), f"{M}x{d}"
@@ -141,39 +143,66 @@ def _algorithmic(name: str, a: tuple):
     return 0, 0, ""
 
 
-def instrumented_step(step_fn):
-    """Run one eager step with a CUDA-event pair around every libmmemo launch (on the launching
-    stream).  Returns {family: dict(n, ms, flops, bytes)} and the step's total event time."""
+def instrumented_step(step_fn, reps: int = 10):
+    """Per-kernel device time, measured live with CUDA events.
+
+    One eager step is run with a hook on every libmmemo launch.  Timing a launch in place with an
+    event pair would mostly measure the host (an eager step is launch-bound: the GPU idles between
+    kernels), so the FIRST launch of every kernel family (entry point + shape) is re-issued `reps`
+    times from a small CUDA graph while its argument buffers are still alive, and the graph replay
+    is timed with events on its stream.  Inputs are L2-warm, as in the real step where the
+    producer kernel has just written them.  Returns {family: dict(n, ms, flops, bytes)} with ms =
+    launches-per-step x measured time per launch."""
     from mmemo_b200 import ops
-    recs = []
     real = ops._call
+    fam = {}
 
-    def timed(name, *args):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
+    def measure(name, args):
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                st = torch.cuda.current_stream().cuda_stream
+                for _ in range(reps):
+                    real(name, *(args[:-1] + (st,)))
+            g.replay()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            s.record()
+            g.replay()
+            g.replay()
+            e.record()
+            torch.cuda.synchronize()
+            return s.elapsed_time(e) / (2 * reps)
+        except Exception:
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(reps):
+                real(name, *args)
+            e.record()
+            torch.cuda.synchronize()
+            return s.elapsed_time(e) / reps
+
+    def hooked(name, *args):
         real(name, *args)
-        e.record()
-        recs.append((name, args, s, e))
+        fl, by, tag = _algorithmic(name, args)
+        key = name.replace("mmemo_", "") + (":" + tag if tag else "")
+        r = fam.get(key)
+        if r is None:
+            r = fam[key] = dict(n=0, ms_each=measure(name, args), flops=0, bytes=0)
+        r["n"] += 1
+        r["flops"] += fl
+        r["bytes"] += by
 
-    ops._call = timed
+    ops._call = hooked
     try:
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0.record()
         step_fn()
-        t1.record()
         torch.cuda.synchronize()
     finally:
         ops._call = real
-    fam = {}
-    for name, args, s, e in recs:
-        fl, by, tag = _algorithmic(name, args)
-        key = name.replace("mmemo_", "") + (":" + tag if tag else "")
-        r = fam.setdefault(key, dict(n=0, ms=0.0, flops=0, bytes=0))
-        r["n"] += 1
-        r["ms"] += s.elapsed_time(e)
-        r["flops"] += fl
-        r["bytes"] += by
-    return fam, t0.elapsed_time(t1)
+    for r in fam.values():
+        r["ms"] = r["ms_each"] * r["n"]
+    return fam, sum(r["ms"] for r in fam.values())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -399,7 +428,6 @@ def main():
         if reducer is not None:
             reducer.enabled = False
         fam, total_ms = instrumented_step(step)
-        fam, total_ms = instrumented_step(step)       # second pass: warm
         if reducer is not None:
             reducer.enabled = True
         pk = peaks()
@@ -420,8 +448,10 @@ def main():
         roof = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
                 "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": None,
                 "share_of_step": top["share"], "peak_source": pk["src"],
-                "how": "CUDA events around each libmmemo launch of one eager step on the launch "
-                       "stream; achieved = algorithmic bytes|flops / summed launch time"}
+                "how": "first launch of each kernel family re-issued 10x from a CUDA graph inside "
+                       "an eager step (buffers alive, L2-warm), graph replay timed with CUDA events; "
+                       "achieved = algorithmic bytes|flops per launch / time per launch",
+                "kernel_time_sum_ms": total_ms}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
     cpu = None

@@ -74,6 +74,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src
                "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// C[tile] += smem tile, performed by the L2 (element type from the tensor map: fp32 here)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, uint32_t src, int c0,
+                                                  int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1,
                                              int c2, int c3) {
   asm volatile(
@@ -195,3 +202,5 @@ PFN_encodeTiled mm_get_encode_tiled();
 // dims 1..rank-1.  Returns false on failure.
 bool mm_make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                        const uint64_t* strides_bytes, const uint32_t* box);
+bool mm_make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box);
