@@ -60,10 +60,21 @@ ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, in
            int relu) {
   constexpr int V = Vec<T>::N;
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
-  if (row >= M) return;
   const float g = gate ? gate[0] : 1.f;
   const int nchunk = d / V;
+  float gm[NCH][V], bt[NCH][V];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+    if (lane + 32 * i < nchunk) {
+      Vec<float>::load(gamma + (lane + 32 * i) * V, gm[i]);
+      Vec<float>::load(beta + (lane + 32 * i) * V, bt[i]);
+      if (V == 8) {
+        Vec<float>::load(gamma + (lane + 32 * i) * V + 4, gm[i] + 4);
+        Vec<float>::load(beta + (lane + 32 * i) * V + 4, bt[i] + 4);
+      }
+    }
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < M;
+       row += (int64_t)gridDim.x * LN_WARPS) {
   float z[NCH][V];
   float sum = 0.f;
 #pragma unroll
@@ -104,7 +115,7 @@ ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, in
       float o[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        float v = (z[i][j] - mean) * rstd * __ldg(gamma + c * V + j) + __ldg(beta + c * V + j);
+        float v = (z[i][j] - mean) * rstd * gm[i][j] + bt[i][j];
         o[j] = relu ? fmaxf(v, 0.f) : v;
       }
       Vec<T>::store(y + row * ldy + c * V, o);
@@ -114,6 +125,7 @@ ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, in
     if (mean_out) mean_out[row] = mean;
     if (rstd_out) rstd_out[row] = rstd;
   }
+  }  // row loop
 }
 
 template <typename T, int NCH>
@@ -127,11 +139,18 @@ ln_bwd_row_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res
   constexpr int V = Vec<T>::N;
   __shared__ float dgs[LN_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp;
   const float g = gate ? gate[0] : 1.f;
   const int nchunk = d / V;
   float dg = 0.f;
-  if (row < M) {
+  float gm[NCH][V];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+    if (lane + 32 * i < nchunk) {
+      Vec<float>::load(gamma + (lane + 32 * i) * V, gm[i]);
+      if (V == 8) Vec<float>::load(gamma + (lane + 32 * i) * V + 4, gm[i] + 4);
+    }
+  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + warp; row < M;
+       row += (int64_t)gridDim.x * LN_WARPS) {
     const float mean = mean_in[row], rstd = rstd_in[row];
     float xh[NCH][V], w[NCH][V], xv[NCH][V];
     float s1 = 0.f, s2 = 0.f;
@@ -154,7 +173,7 @@ ln_bwd_row_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res
         for (int j = 0; j < V; ++j) {
           const float zz = g * xv[i][j] + (res ? rv[j] : 0.f);
           xh[i][j] = (zz - mean) * rstd;
-          w[i][j] = dv[j] * __ldg(gamma + c * V + j);
+          w[i][j] = dv[j] * gm[i][j];
           s1 += w[i][j];
           s2 = fmaf(w[i][j], xh[i][j], s2);
         }
@@ -364,9 +383,12 @@ int fwd(const void* res, int64_t ldres, const void* x, int64_t ldx, const float*
   const T* r = static_cast<const T*>(res);
   const T* xx = static_cast<const T*>(x);
   T* yy = static_cast<T*>(y);
-  const unsigned grid = (unsigned)cdiv(M, LN_WARPS);
+  int64_t grid64 = cdiv(M, LN_WARPS);
+  if (grid64 > 148 * 6) grid64 = 148 * 6;       // persistent: 6 CTAs (48 warps) per SM, rows strided
+  const unsigned grid = (unsigned)grid64;
   const bool vec = d % V == 0 && ldx % V == 0 && ldy % V == 0 && (!res || ldres % V == 0) &&
-                   al16(x) && al16(y) && (!res || al16(res)) && d / V <= 256;
+                   al16(x) && al16(y) && (!res || al16(res)) && al16(gamma) && al16(beta) &&
+                   d / V <= 256;
 #define MM_ARGS r, ldres, xx, ldx, gate, gamma, beta, yy, ldy, mean, rstd, M, (int)d, eps, relu
   if (vec) {
     const int nch = (int)cdiv(d / V, 32);
@@ -399,12 +421,14 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
   const T* yy = static_cast<const T*>(y);
   T* dr = static_cast<T*>(dres);
   T* dxx = static_cast<T*>(dx);
-  const unsigned grid = (unsigned)cdiv(M, LN_WARPS);
+  int64_t grid64 = cdiv(M, LN_WARPS);
+  if (grid64 > 148 * 6) grid64 = 148 * 6;       // persistent: 6 CTAs (48 warps) per SM, rows strided
+  const unsigned grid = (unsigned)grid64;
   const bool vec = d % V == 0 && ldx % V == 0 && lddy % V == 0 && lddx % V == 0 &&
                    (!res || ldres % V == 0) && (!dres || lddres % V == 0) &&
                    (!relu || ldy % V == 0) && al16(dy) && al16(x) && al16(dx) &&
                    (!res || al16(res)) && (!dres || al16(dres)) && (!relu || al16(y)) &&
-                   d / V <= 256;
+                   al16(gamma) && d / V <= 256;
 #define MM_ARGS dyy, lddy, r, ldres, xx, ldx, gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx, \
                 lddx, dgate, M, (int)d, relu
   if (vec) {
