@@ -1,29 +1,37 @@
 // Persistent tcgen05 / TMA GEMM for sm_100a:  C[M,N] (+)= epi( A * B^T ), bf16 operands, fp32
-// accumulation in TMEM.  One CTA per SM loops over 128 x 128 output tiles (x split-K slices).
+// accumulation in TMEM.  Two configurations of one kernel template:
+//
+//   CTA2 = true  (default when N >= 256): CTA PAIRS (cluster of 2, cta_group::2).  A pair owns a
+//       256 x 256 output tile: each CTA stages its own 128 rows of A and its own 128 columns of B
+//       (32 KB per k-block per CTA), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256,
+//       N = 256) that reads both CTAs' shared memory, and each CTA's TMEM receives its 128 x 256
+//       half of the accumulator.  Bytes staged per flop are half those of a 128 x 128 tile — the
+//       128 x 128 version was L2-bandwidth-bound (profiles/).
+//   CTA2 = false: one CTA per 128 x 128 tile (small N, and the ragged shapes).
 //
 //   warp 0   TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) into a 4-stage shared-memory ring
-//   warp 1   MMA issuer   : one thread issues tcgen05.mma (UMMA 128x128x16, cta_group::1) into one
-//                           of TWO 128-column TMEM accumulators; tcgen05.commit frees ring slots and
-//                           hands the finished accumulator to the epilogue
+//   warp 1   MMA issuer   : one thread (of the leader CTA) issues the UMMAs into one of TWO TMEM
+//                           accumulators; tcgen05.commit frees ring slots (in both CTAs) and hands
+//                           the finished accumulator to the epilogue warps (of both CTAs)
 //   warps 2-5 epilogue    : tcgen05.ld (thread = row) -> bias / position table / ReLU / ReLU-mask /
-//                           accumulate -> bf16 or fp32 tile in swizzled shared memory -> TMA store.
-//                           While they drain accumulator i, the MMA warp already fills i+1.
+//                           accumulate -> bf16 or fp32 tile in swizzled shared memory -> TMA store,
+//                           128 columns at a time, overlapped with the MMAs of the next tile.
 // All global traffic goes through TMA: operands, the optional "aux" tile (old C for accumulate, or
-// the saved activation whose sign masks a ReLU gradient; prefetched one tile ahead) and the output.
+// the saved activation whose sign masks a ReLU gradient; prefetched one step ahead) and the output.
 // Operand "majors" are encoded in the UMMA descriptors, so y = x w^T (K-major A, B), dx = dy w
 // (B MN-major) and dw = dy^T x (A and B MN-major) run without transposes in HBM.
-// Split-K (weight gradients: tiny output, K = B*L rows): partial fp32 tiles go by TMA to a
-// caller-provided workspace; a second kernel reduces them in a fixed order (deterministic).
+// Split-K (weight gradients: tiny output, K = B*L rows): fp32 slices are summed into C by TMA
+// reduce-add; bf16 outputs use a caller-provided workspace + a fixed-order reduce kernel.
 #include "common.cuh"
 #include "gemm.h"
 #include "tc_common.cuh"
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64, STAGES = 4;
-constexpr uint32_t A_TILE = BM * BK * 2, B_TILE = BN * BK * 2;
-constexpr uint32_t RING = STAGES * (A_TILE + B_TILE);   // 128 KB
-constexpr uint32_t OUT_BYTES = 64 * 1024;                // fp32 staging, or bf16 staging + aux tile
+constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr uint32_t A_TILE = BM * BK * 2, B_TILE = 128 * BK * 2;   // per CTA per stage: 16 KB + 16 KB
+constexpr uint32_t RING = STAGES * (A_TILE + B_TILE);             // 128 KB
+constexpr uint32_t OUT_BYTES = 64 * 1024;    // fp32 staging (128x128), or bf16 staging + aux tile
 constexpr int NTHREADS = 192;
 constexpr uint32_t SMEM_BYTES = RING + OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
 constexpr int AUX_NONE = 0, AUX_ACC = 1, AUX_RELU = 2;
@@ -39,20 +47,17 @@ struct TcArgs {
   uint32_t idesc;
   int splits, kb_per, kb_total;
   int reduce_add;          // split-K slices are summed into the fp32 C by TMA reduce-add
-  int tiles_m, tiles_n;
+  int tiles_m, tiles_n;    // in units of the (pair) tile: TM x BN
 };
 
-__device__ __forceinline__ void decode(const TcArgs& a, int w, int& tm, int& tn, int& sp) {
-  sp = w % a.splits;
-  const int t = w / a.splits;
-  tm = t / a.tiles_n;
-  tn = t - tm * a.tiles_n;
-}
-
+template <bool CTA2>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
                const TcArgs a) {
+  constexpr int BN = CTA2 ? 256 : 128;        // accumulator columns per tile
+  constexpr int TM = CTA2 ? 256 : 128;        // output rows per work item (pair or CTA)
+  constexpr int NHALF = BN / 128;             // epilogue works on 128 columns at a time
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = tc::smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -64,10 +69,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_slot = bar_aux + 8;
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-  float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));   // bias of this tile
+  float* sbias = reinterpret_cast<float*>(smem_raw + (bars + 256 - raw));   // bias of this half tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? tc::cluster_ctarank() : 0u;      // 0 = leader of the pair
+  const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int total = a.tiles_m * a.tiles_n * a.splits;
+
+  auto decode = [&](int w, int& m0, int& n0, int& sp, int& tile) {
+    sp = w % a.splits;
+    tile = w / a.splits;
+    const int tm = tile / a.tiles_n, tn = tile - tm * a.tiles_n;
+    m0 = tm * TM + (int)rank * BM;     // rows owned by this CTA
+    n0 = tn * BN;                      // first column of the (pair) tile
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -76,7 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(bar_accf + 8 * i, 1);
-      tc::mbar_init(bar_acce + 8 * i, 128);
+      tc::mbar_init(bar_acce + 8 * i, CTA2 ? 2 : 1);   // one elected epilogue thread per CTA
     }
     tc::mbar_init(bar_aux, 1);
     tc::fence_barrier_init();
@@ -85,54 +101,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc::tma_prefetch_desc(&tmC);
   }
   if (warp == 1) {
-    tc::tmem_alloc(tmem_slot, 2 * BN);
-    tc::tmem_relinquish();
+    if (CTA2) { tc::tmem_alloc_2sm(tmem_slot, 2 * BN); tc::tmem_relinquish_2sm(); }
+    else      { tc::tmem_alloc(tmem_slot, 2 * BN); tc::tmem_relinquish(); }
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (CTA2) tc::cluster_sync(); else __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (every CTA stages its own rows of A and columns of B) =========
     if (lane == 0) {
       uint32_t it = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        int tm, tn, sp;
-        decode(a, w, tm, tn, sp);
-        const int m0 = tm * BM, n0 = tn * BN;
+      for (int w = unit; w < total; w += units) {
+        int m0, n0, sp, tile;
+        decode(w, m0, n0, sp, tile);
+        const int nb = n0 + (int)rank * 128;           // this CTA's 128 columns of B
         const int kb_beg = sp * a.kb_per, kb_end = min(a.kb_total, kb_beg + a.kb_per);
         for (int kb = kb_beg; kb < kb_end; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           tc::mbar_wait(bar_empty + 8 * s, ph ^ 1);
-          tc::mbar_expect_tx(bar_full + 8 * s, A_TILE + B_TILE);
+          const uint32_t fb = bar_full + 8 * s;
+          if (rank == 0) tc::mbar_expect_tx(fb, (CTA2 ? 2u : 1u) * (A_TILE + B_TILE));
           const int k0 = kb * BK;
           const uint32_t da = sA + s * A_TILE, db = sB + s * B_TILE;
+          auto ld = [&](uint32_t dst, const CUtensorMap* tm, int c0, int c1) {
+            if (CTA2) tc::tma_load_2d_2sm(dst, tm, c0, c1, fb);   // credits the leader's barrier
+            else tc::tma_load_2d(dst, tm, c0, c1, fb);
+          };
           if (!a.a_mn) {
-            tc::tma_load_2d(da, &tmA, k0, m0, bar_full + 8 * s);            // box {64 k, 128 m}
+            ld(da, &tmA, k0, m0);                                // box {64 k, 128 m}
           } else {
-            tc::tma_load_2d(da, &tmA, m0, k0, bar_full + 8 * s);            // box {64 m, 64 k}
-            tc::tma_load_2d(da + A_TILE / 2, &tmA, m0 + 64, k0, bar_full + 8 * s);
+            ld(da, &tmA, m0, k0);                                // box {64 m, 64 k}
+            ld(da + A_TILE / 2, &tmA, m0 + 64, k0);
           }
           if (!a.b_mn) {
-            tc::tma_load_2d(db, &tmB, k0, n0, bar_full + 8 * s);
+            ld(db, &tmB, k0, nb);
           } else {
-            tc::tma_load_2d(db, &tmB, n0, k0, bar_full + 8 * s);
-            tc::tma_load_2d(db + B_TILE / 2, &tmB, n0 + 64, k0, bar_full + 8 * s);
+            ld(db, &tmB, nb, k0);
+            ld(db + B_TILE / 2, &tmB, nb + 64, k0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (lane == 0 && rank == 0) {
       uint32_t it = 0, ti = 0;
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
-        int tm, tn, sp;
-        decode(a, w, tm, tn, sp);
+      for (int w = unit; w < total; w += units, ++ti) {
+        const int sp = w % a.splits;
         const int kb_beg = sp * a.kb_per, kb_end = min(a.kb_total, kb_beg + a.kb_per);
         const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
-        tc::mbar_wait(bar_acce + 8 * buf, aph ^ 1);     // epilogue has drained this accumulator
+        tc::mbar_wait(bar_acce + 8 * buf, aph ^ 1);     // epilogues have drained this accumulator
         tc::tc_fence_after();
         const uint32_t tacc = tmem_base + buf * BN;
         for (int kb = kb_beg; kb < kb_end; ++kb, ++it) {
@@ -147,11 +167,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                        : tc::smem_desc_sw128(da + k * 32, 16, 1024);
             const uint64_t bd = a.b_mn ? tc::smem_desc_sw128(db + k * 2048, B_TILE / 2, 1024)
                                        : tc::smem_desc_sw128(db + k * 32, 16, 1024);
-            tc::umma_bf16(tacc, ad, bd, a.idesc, (kb > kb_beg || k > 0) ? 1u : 0u);
+            const uint32_t acc = (kb > kb_beg || k > 0) ? 1u : 0u;
+            if (CTA2) tc::umma_bf16_2sm(tacc, ad, bd, a.idesc, acc);
+            else tc::umma_bf16(tacc, ad, bd, a.idesc, acc);
           }
-          tc::umma_commit(bar_empty + 8 * s);   // ring slot reusable once these MMAs have read it
+          // ring slot reusable (in both CTAs) once these MMAs have read it
+          if (CTA2) tc::umma_commit_2sm(bar_empty + 8 * s, 3); else tc::umma_commit(bar_empty + 8 * s);
         }
-        tc::umma_commit(bar_accf + 8 * buf);    // accumulator complete
+        // accumulator complete -> epilogue warps of both CTAs
+        if (CTA2) tc::umma_commit_2sm(bar_accf + 8 * buf, 3); else tc::umma_commit(bar_accf + 8 * buf);
       }
     }
   } else {
@@ -161,125 +185,140 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int te = threadIdx.x - 64;
     const bool partial = a.splits > 1;
     const bool out_f32 = partial || !a.c_bf16;
-    auto issue_aux = [&](int w) {   // old C (accumulate) or saved activation (ReLU mask), bf16
-      int tm, tn, sp;
-      decode(a, w, tm, tn, sp);
+    // step = (work item, 128-column half); aux tile of a step: old C (accumulate) or the saved
+    // activation (ReLU mask), bf16, prefetched one step ahead
+    auto issue_aux = [&](int w, int half) {
+      int m0, n0, sp, tile;
+      decode(w, m0, n0, sp, tile);
       tc::mbar_expect_tx(bar_aux, 32 * 1024);
-      tc::tma_load_2d(sAux, &tmAux, tn * BN, tm * BM, bar_aux);
-      tc::tma_load_2d(sAux + 16384, &tmAux, tn * BN + 64, tm * BM, bar_aux);
+      tc::tma_load_2d(sAux, &tmAux, n0 + half * 128, m0, bar_aux);
+      tc::tma_load_2d(sAux + 16384, &tmAux, n0 + half * 128 + 64, m0, bar_aux);
     };
-    if (a.aux && te == 0 && (int)blockIdx.x < total) issue_aux(blockIdx.x);
-    uint32_t ti = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++ti) {
-      int tm, tn, sp;
-      decode(a, w, tm, tn, sp);
-      const int m0 = tm * BM, n0 = tn * BN;
+    if (a.aux && te == 0 && unit < total) issue_aux(unit, 0);
+    uint32_t ti = 0, step = 0;
+    for (int w = unit; w < total; w += units, ++ti) {
+      int m0, n0, sp, tile;
+      decode(w, m0, n0, sp, tile);
       const int64_t m = (int64_t)m0 + row;
       const int pos_row = a.pos ? (int)((uint32_t)(m0 + row) % (uint32_t)a.pos_period) : 0;
       const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
       tc::mbar_wait(bar_accf + 8 * buf, aph);
       tc::tc_fence_after();
-      if (te == 0) tc::tma_store_wait_read();          // previous tile's store has left staging
-      if (a.bias) sbias[te] = (n0 + te < a.N) ? __ldg(a.bias + n0 + te) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (a.aux) tc::mbar_wait(bar_aux, ti & 1);
-      const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tc::tmem_ld32(taddr + ch * 32, r);
-        tc::tmem_ld_wait();
-        // rows >= M / columns >= N hold zeros or junk that the TMA store clips: no guards needed
-        if (a.bias) {
+      for (int half = 0; half < NHALF; ++half, ++step) {
+        const int nh = n0 + half * 128;                  // first column of this half
+        if (te == 0) tc::tma_store_wait_read();          // previous store has left the staging tile
+        if (a.bias) sbias[te] = (nh + te < a.N) ? __ldg(a.bias + nh + te) : 0.f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (a.aux) tc::mbar_wait(bar_aux, step & 1);
+        const uint32_t taddr =
+            tmem_base + buf * BN + half * 128 + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t r[32];
+          tc::tmem_ld32(taddr + ch * 32, r);
+          tc::tmem_ld_wait();
+          // rows >= M / columns >= N hold zeros or junk that the TMA store clips: no guards needed
+          if (a.bias) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            r[i] = __float_as_uint(__uint_as_float(r[i]) + sbias[ch * 32 + i]);
-        }
-        if (a.pos && m < a.M) {   // position table row of this output row (period = seq length)
-          const float* prow = a.pos + (int64_t)pos_row * a.N + n0 + ch * 32;
+            for (int i = 0; i < 32; ++i)
+              r[i] = __float_as_uint(__uint_as_float(r[i]) + sbias[ch * 32 + i]);
+          }
+          if (a.pos && m < a.M) {   // position table row of this output row (period = seq length)
+            const float* prow = a.pos + (int64_t)pos_row * a.N + nh + ch * 32;
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n0 + ch * 32 + i < a.N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(prow + i));
-        }
-        if (a.relu) {
+            for (int i = 0; i < 32; ++i)
+              if (nh + ch * 32 + i < a.N)
+                r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(prow + i));
+          }
+          if (a.relu) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
-        }
-        if (a.aux) {
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(fmaxf(__uint_as_float(r[i]), 0.f));
+          }
+          if (a.aux) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t x[4];
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
-                         : "r"(sAux + (ch >> 1) * 16384 + tc::sw128_offset(row, (ch & 1) * 4 + c)));
+            for (int c = 0; c < 4; ++c) {
+              uint32_t x[4];
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3])
+                           : "r"(sAux + (ch >> 1) * 16384 +
+                                 tc::sw128_offset(row, (ch & 1) * 4 + c)));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float lo = __uint_as_float(x[e] << 16), hi = __uint_as_float(x[e] & 0xFFFF0000u);
-              float v0 = __uint_as_float(r[8 * c + 2 * e]), v1 = __uint_as_float(r[8 * c + 2 * e + 1]);
-              if (a.aux == AUX_ACC) { v0 += lo; v1 += hi; }
-              else { if (!(lo > 0.f)) v0 = 0.f; if (!(hi > 0.f)) v1 = 0.f; }
-              r[8 * c + 2 * e] = __float_as_uint(v0);
-              r[8 * c + 2 * e + 1] = __float_as_uint(v1);
+              for (int e = 0; e < 4; ++e) {
+                const float lo = __uint_as_float(x[e] << 16);
+                const float hi = __uint_as_float(x[e] & 0xFFFF0000u);
+                float v0 = __uint_as_float(r[8 * c + 2 * e]);
+                float v1 = __uint_as_float(r[8 * c + 2 * e + 1]);
+                if (a.aux == AUX_ACC) { v0 += lo; v1 += hi; }
+                else { if (!(lo > 0.f)) v0 = 0.f; if (!(hi > 0.f)) v1 = 0.f; }
+                r[8 * c + 2 * e] = __float_as_uint(v0);
+                r[8 * c + 2 * e + 1] = __float_as_uint(v1);
+              }
+            }
+          }
+          if (out_f32) {      // 4 panels of 32 fp32 columns: [128 rows][128 B]
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(
+                               sOut + ch * 16384 + tc::sw128_offset(row, c)),
+                           "r"(r[4 * c]), "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
+                           : "memory");
+          } else {            // 2 panels of 64 bf16 columns
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(r[8 * c + 2 * e]),
+                                                         __uint_as_float(r[8 * c + 2 * e + 1]));
+                pk[e] = *reinterpret_cast<uint32_t*>(&t);
+              }
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(
+                               sOut + (ch >> 1) * 16384 + tc::sw128_offset(row, (ch & 1) * 4 + c)),
+                           "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                           : "memory");
             }
           }
         }
-        if (out_f32) {      // 4 panels of 32 fp32 columns: [128 rows][128 B]
+        tc::tc_fence_before();
+        tc::fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (te == 0) {
+          if (half == NHALF - 1) {   // whole accumulator drained by this CTA -> tell the MMA issuer
+            if (CTA2) tc::mbar_arrive_cta(bar_acce + 8 * buf, 0); else tc::mbar_arrive(bar_acce + 8 * buf);
+          }
+          if (partial && a.reduce_add) {   // C += slice, summed by the L2
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(
-                             sOut + ch * 16384 + tc::sw128_offset(row, c)),
-                         "r"(r[4 * c]), "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
-                         : "memory");
-        } else {            // 2 panels of 64 bf16 columns
+            for (int p = 0; p < 4; ++p)
+              if (nh + p * 32 < a.N) tc::tma_reduce_add_2d(&tmC, sOut + p * 16384, nh + p * 32, m0);
+          } else if (partial) {   // workspace: [(tile*splits + split)*TM rows][BN fp32 columns]
+            const int prow = (tile * a.splits + sp) * TM + (int)rank * BM;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t pk[4];
+            for (int p = 0; p < 4; ++p)
+              tc::tma_store_2d(&tmC, sOut + p * 16384, half * 128 + p * 32, prow);
+          } else if (out_f32) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 t = __floats2bfloat162_rn(__uint_as_float(r[8 * c + 2 * e]),
-                                                       __uint_as_float(r[8 * c + 2 * e + 1]));
-              pk[e] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(
-                             sOut + (ch >> 1) * 16384 + tc::sw128_offset(row, (ch & 1) * 4 + c)),
-                         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                         : "memory");
+            for (int p = 0; p < 4; ++p)
+              if (nh + p * 32 < a.N) tc::tma_store_2d(&tmC, sOut + p * 16384, nh + p * 32, m0);
+          } else {
+            if (nh < a.N) tc::tma_store_2d(&tmC, sOut, nh, m0);
+            if (nh + 64 < a.N) tc::tma_store_2d(&tmC, sOut + 16384, nh + 64, m0);
+          }
+          tc::tma_store_commit();
+          if (a.aux) {   // prefetch the aux tile of the next step
+            if (half + 1 < NHALF) issue_aux(w, half + 1);
+            else if (w + units < total) issue_aux(w + units, 0);
           }
         }
-      }
-      // accumulator drained -> MMA warp may reuse it; staging complete -> TMA store
-      tc::tc_fence_before();
-      tc::mbar_arrive(bar_acce + 8 * buf);
-      tc::fence_proxy_async();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (te == 0) {
-        if (partial && a.reduce_add) {   // C += slice, summed by the L2
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            if (n0 + p * 32 < a.N) tc::tma_reduce_add_2d(&tmC, sOut + p * 16384, n0 + p * 32, m0);
-        } else if (partial) {   // workspace viewed as [(tile*splits + split)*128 rows][128 fp32 cols]
-          const int prow = ((tm * a.tiles_n + tn) * a.splits + sp) * BM;
-#pragma unroll
-          for (int p = 0; p < 4; ++p) tc::tma_store_2d(&tmC, sOut + p * 16384, p * 32, prow);
-        } else if (out_f32) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            if (n0 + p * 32 < a.N) tc::tma_store_2d(&tmC, sOut + p * 16384, n0 + p * 32, m0);
-        } else {
-          tc::tma_store_2d(&tmC, sOut, n0, m0);
-          if (n0 + 64 < a.N) tc::tma_store_2d(&tmC, sOut + 16384, n0 + 64, m0);
-        }
-        tc::tma_store_commit();
-        if (a.aux && w + (int)gridDim.x < total) issue_aux(w + gridDim.x);   // prefetch next aux
       }
     }
     if (te == 0) tc::tma_store_wait_all();
   }
   tc::tc_fence_before();
-  __syncthreads();
+  if (CTA2) tc::cluster_sync(); else __syncthreads();   // the peer may still signal our barriers
   if (warp == 1) {
     tc::tc_fence_after();
-    tc::tmem_dealloc(tmem_base, 2 * BN);
+    if (CTA2) tc::tmem_dealloc_2sm(tmem_base, 2 * BN); else tc::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -287,36 +326,27 @@ struct ReduceArgs {
   const float* partial;
   void* C;
   int64_t ldc;
-  int M, N, splits, tiles_n, c_bf16, accumulate;
+  int M, N, splits, tiles_n, c_bf16, accumulate, tm_rows, bn_cols;
   const float* bias;
 };
 
-// sum the split-K partial tiles in a fixed order, then bias / accumulate / convert / store
+// bf16 outputs only: sum the split-K partial tiles in a fixed order, bias / accumulate / convert
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceArgs a) {
   const int tile = blockIdx.x;
-  const int m0 = (tile / a.tiles_n) * BM, n0 = (tile % a.tiles_n) * BN;
-  const float* src = a.partial + (size_t)tile * a.splits * BM * BN;
-  for (int e = threadIdx.x + blockIdx.y * 256; e < BM * BN / 4; e += 256 * gridDim.y) {
-    const int row = e / (BN / 4), c4 = (e % (BN / 4)) * 4;
+  const int TMr = a.tm_rows, BNc = a.bn_cols;
+  const int m0 = (tile / a.tiles_n) * TMr, n0 = (tile % a.tiles_n) * BNc;
+  const float* src = a.partial + (size_t)tile * a.splits * TMr * BNc;
+  for (int e = threadIdx.x + blockIdx.y * 256; e < TMr * BNc / 4; e += 256 * gridDim.y) {
+    const int row = e / (BNc / 4), c4 = (e % (BNc / 4)) * 4;
     const int64_t m = (int64_t)m0 + row;
     const int n = n0 + c4;
     if (m >= a.M || n >= a.N) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < a.splits; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(src + ((size_t)s * BM + row) * BN + c4);
+      const float4 v = *reinterpret_cast<const float4*>(src + ((size_t)s * TMr + row) * BNc + c4);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     float x[4] = {acc.x, acc.y, acc.z, acc.w};
-    if (!a.c_bf16 && n + 4 <= a.N && !a.bias) {   // common case (weight gradients): one 16-byte store
-      float4* c = reinterpret_cast<float4*>(static_cast<float*>(a.C) + m * a.ldc + n);
-      float4 v = make_float4(x[0], x[1], x[2], x[3]);
-      if (a.accumulate) {
-        const float4 o = *c;
-        v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-      }
-      *c = v;
-      continue;
-    }
     for (int j = 0; j < 4 && n + j < a.N; ++j) {
       if (a.bias) x[j] += __ldg(a.bias + n + j);
       if (a.c_bf16) {
@@ -332,6 +362,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceArgs a) 
 
 float* g_ws = nullptr;
 size_t g_ws_bytes = 0;
+int g_force_1cta = 0;   // debug / A-B switch (mmemo_debug_gemm_force_1cta)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -371,6 +402,11 @@ extern "C" int mmemo_set_workspace(void* ptr, int64_t bytes) {
   g_ws_bytes = ptr ? (size_t)bytes : 0;
   return MMEMO_OK;
 }
+// debug only (not part of include/mmemo.h): force the one-CTA 128x128 configuration
+extern "C" int mmemo_debug_gemm_force_1cta(int on) {
+  g_force_1cta = on;
+  return MMEMO_OK;
+}
 
 PFN_encodeTiled mm_get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
@@ -397,7 +433,7 @@ bool mm_make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64
 bool gemm_tc_supported(const GemmArgs& g, int c_bf16) {
   if (g.M < 64 || g.N < 64 || g.K < 64) return false;
   if ((double)g.M * (double)g.N * (double)g.K < (double)(1 << 22)) return false;
-  if (g.M > (1ll << 31) - 256 || g.N > (1ll << 31) - 256 || g.K > (1ll << 31) - 256) return false;
+  if (g.M > (1ll << 31) - 512 || g.N > (1ll << 31) - 512 || g.K > (1ll << 31) - 512) return false;
   const bool a_k = (g.sAk == 1 && g.sAm % 8 == 0), a_mn = (g.sAm == 1 && g.sAk % 8 == 0);
   const bool b_k = (g.sBk == 1 && g.sBn % 8 == 0), b_mn = (g.sBn == 1 && g.sBk % 8 == 0);
   if (!(a_k || a_mn) || !(b_k || b_mn)) return false;
@@ -412,26 +448,32 @@ bool gemm_tc_supported(const GemmArgs& g, int c_bf16) {
 int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)SMEM_BYTES));
+    MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_done = true;
   }
   const bool a_mn = !(g.sAk == 1 && g.sAm % 8 == 0);
   const bool b_mn = !(g.sBk == 1 && g.sBn % 8 == 0);
-  const int tiles_n = (int)cdiv(g.N, BN), tiles_m = (int)cdiv(g.M, BM);
+  // CTA pairs (256 x 256 tiles) when the output is wide and tall enough to fill them
+  const bool cta2 = !g_force_1cta && g.N >= 256 && g.M >= 256;
+  const int TM = cta2 ? 256 : 128, BN = cta2 ? 256 : 128;
+  const int tiles_n = (int)cdiv(g.N, BN), tiles_m = (int)cdiv(g.M, TM);
   const int tiles = tiles_m * tiles_n;
   const int kb_total = (int)cdiv(g.K, BK);
   const int sms = num_sms();
+  const int units_max = cta2 ? sms / 2 : sms;      // schedulable work units (pairs or CTAs)
   // split-K when the output has too few tiles to occupy the machine and K is long (needs a linear
-  // epilogue: bias and accumulate are applied by the reduce kernel)
+  // epilogue: bias and accumulate are applied after the reduction)
   int splits = 1;
   const bool reduce_add = !c_bf16 && !g.bias;   // fp32 C: slices are summed by TMA reduce-add
-  if (tiles * 2 <= sms && kb_total >= 16 && !g.relu && !g.relu_src && !g.pos) {
-    splits = sms / tiles;                               // one balanced round of work items
+  if (tiles * 2 <= units_max && kb_total >= 16 && !g.relu && !g.relu_src && !g.pos) {
+    splits = units_max / tiles;                         // one balanced round of work items
     if (splits > kb_total / 4) splits = kb_total / 4;
     if (splits > 32) splits = 32;
     if (!reduce_add) {
-      const size_t per_split = (size_t)tiles * BM * BN * sizeof(float);
+      const size_t per_split = (size_t)tiles * TM * BN * sizeof(float);
       if (per_split * (size_t)splits > g_ws_bytes) splits = (int)(g_ws_bytes / per_split);
     }
     if (splits < 2) splits = 1;
@@ -448,11 +490,12 @@ int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
     if (!a_mn) { dims[0] = g.K; dims[1] = g.M; str[0] = g.sAm * 2; box[0] = 64; box[1] = BM; }
     else       { dims[0] = g.M; dims[1] = g.K; str[0] = g.sAk * 2; box[0] = 64; box[1] = BK; }
     bool ok = mm_make_tmap_bf16(&tmA, g.A, 2, dims, str, box);
-    if (!b_mn) { dims[0] = g.K; dims[1] = g.N; str[0] = g.sBn * 2; box[0] = 64; box[1] = BN; }
+    if (!b_mn) { dims[0] = g.K; dims[1] = g.N; str[0] = g.sBn * 2; box[0] = 64; box[1] = 128; }
     else       { dims[0] = g.N; dims[1] = g.K; str[0] = g.sBk * 2; box[0] = 64; box[1] = BK; }
     ok = ok && mm_make_tmap_bf16(&tmB, g.B, 2, dims, str, box);
     if (partial && !reduce_add) {
-      dims[0] = BN; dims[1] = (uint64_t)tiles * splits * BM; str[0] = BN * 4; box[0] = 32; box[1] = BM;
+      dims[0] = BN; dims[1] = (uint64_t)tiles * splits * TM; str[0] = (uint64_t)BN * 4;
+      box[0] = 32; box[1] = BM;
       ok = ok && mm_make_tmap_f32(&tmC, g_ws, 2, dims, str, box);
     } else if (!c_bf16) {
       dims[0] = g.N; dims[1] = g.M; str[0] = g.ldc * 4; box[0] = 32; box[1] = BM;
@@ -481,20 +524,37 @@ int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
   a.pos = g.pos; a.pos_period = (int)g.pos_period;
   a.relu = g.relu; a.aux = aux;
   a.a_mn = a_mn; a.b_mn = b_mn;
-  a.idesc = tc::idesc_bf16(BM, BN, a_mn, b_mn);
+  a.idesc = tc::idesc_bf16(TM, BN, a_mn, b_mn);
   a.splits = splits; a.kb_per = kb_per; a.kb_total = kb_total;
   a.reduce_add = partial && reduce_add;
   a.tiles_m = tiles_m; a.tiles_n = tiles_n;
   const int total = tiles * splits;
-  const int grid = total < sms ? total : sms;
+  const int units = total < units_max ? total : units_max;
   if (a.reduce_add && !g.accumulate)   // the slices accumulate into C: start from zero
     MM_CUDA_OK(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
-  gemm_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC, tmAux, a);
-  MM_LAUNCH_OK();
+  if (cta2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * units));
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA, tmB, tmC, tmAux, a));
+  } else {
+    gemm_tc_kernel<false><<<units, NTHREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC, tmAux, a);
+    MM_LAUNCH_OK();
+  }
   if (partial && !a.reduce_add) {
     ReduceArgs r = {};
     r.partial = g_ws; r.C = g.C; r.ldc = g.ldc; r.M = (int)g.M; r.N = (int)g.N;
     r.splits = splits; r.tiles_n = tiles_n; r.c_bf16 = c_bf16; r.accumulate = g.accumulate;
+    r.tm_rows = TM; r.bn_cols = BN;
     r.bias = g.bias;
     int ysplit = (int)cdiv(2 * sms, tiles);
     if (ysplit > 16) ysplit = 16;
