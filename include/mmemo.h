@@ -42,6 +42,10 @@ const char* mmemo_last_error(void); /* host string describing the last MMEMO_ERR
  * never allocates: the host registers one device buffer per process (one process per GPU); kernels
  * that need more than `bytes` simply do not split.  Launches that use it must be stream-ordered. */
 int mmemo_set_workspace(void* ptr, int64_t bytes);
+/* Number of SMs the persistent (one CTA per SM) kernels may occupy; 0 = all.  Data-parallel
+ * training sets it below the SM count so that the NCCL all-reduce kernels overlapped with backward
+ * have SMs of their own instead of delaying the last CTAs of a persistent grid. */
+int mmemo_set_sm_budget(int n_sms);
 /* 1 if (M,N,K,mode) is served by the tcgen05/TMA tensor-core GEMM, 0 if by the SIMT GEMM */
 int mmemo_gemm_uses_tensor_cores(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                  int64_t ldc, int mode);

@@ -33,6 +33,7 @@ _DROPOUT = [_vp, _vp, _i64, _f32, _u64, _vp]
 SIGNATURES = {
     "mmemo_version": [],
     "mmemo_set_workspace": [_vp, _i64],
+    "mmemo_set_sm_budget": [_i32],
     "mmemo_gemm_uses_tensor_cores": [_i64, _i64, _i64, _i64, _i64, _i64, _i32],
     "mmemo_resattn_uses_tensor_cores": [_i64, _i64, _i64, _i64],
     "mmemo_linear_fwd_f32": _LINEAR_FWD, "mmemo_linear_fwd_bf16": _LINEAR_FWD,

@@ -363,6 +363,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceArgs a) 
 float* g_ws = nullptr;
 size_t g_ws_bytes = 0;
 int g_force_1cta = 0;   // debug / A-B switch (mmemo_debug_gemm_force_1cta)
+int g_sm_budget = 0;    // SMs the persistent kernels may occupy (0 = all); mmemo_set_sm_budget
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -374,7 +375,9 @@ int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       n = 148;
   }
-  return n;
+  // a communication kernel running concurrently (NCCL all-reduce overlapped with backward) holds
+  // some SMs; a persistent grid larger than what is free would serialise its last CTAs
+  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
 }
 
 bool make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank,
@@ -400,6 +403,10 @@ bool make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int r
 extern "C" int mmemo_set_workspace(void* ptr, int64_t bytes) {
   g_ws = static_cast<float*>(ptr);
   g_ws_bytes = ptr ? (size_t)bytes : 0;
+  return MMEMO_OK;
+}
+extern "C" int mmemo_set_sm_budget(int n_sms) {
+  g_sm_budget = n_sms;
   return MMEMO_OK;
 }
 // debug only (not part of include/mmemo.h): force the one-CTA 128x128 configuration

@@ -19,8 +19,12 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
+import os
+
 import torch
 import torch.distributed as dist
+
+_NO_COMM = os.environ.get("MMEMO_DP_NO_COMM") == "1"   # debug: measure the bucket plumbing alone
 
 
 def shard_bounds(n: int, rank: int, world: int, align: int = 1) -> slice:
@@ -44,7 +48,7 @@ def shard_batch(batch, rank: int, world: int, align: int = 1):
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "offsets", "pending", "work")
+    __slots__ = ("flat", "params", "offsets", "pending", "work", "todo")
 
     def __init__(self, params: Sequence[torch.nn.Parameter]):
         self.params = list(params)
@@ -56,17 +60,24 @@ class _Bucket:
         self.flat = torch.zeros(n, dtype=torch.float32, device=p0.device)
         self.pending = len(self.params)
         self.work = None
+        self.todo = []      # (parameter, slot view) pairs whose gradient still has to be copied in
 
 
 class GradReducer:
     def __init__(self, model: torch.nn.Module, world_size: Optional[int] = None,
-                 bucket_bytes: int = 8 << 20, group=None):
+                 bucket_bytes: int = 8 << 20, group=None, zero_copy: bool = True,
+                 sm_reserve: int = 16, reserve_launches: int = 5):
         self.model = model
         self.group = group
         self.world = world_size if world_size is not None else dist.get_world_size(group)
         self.bucket_bytes = bucket_bytes
         self.enabled = True
+        self.zero_copy = zero_copy
         self.buckets: List[_Bucket] = []
+        # SMs left to the NCCL kernel of a bucket for the next `reserve_launches` GEMM launches after
+        # the all-reduce is issued (set sm_reserve to NCCL_MAX_CTAS; 0 disables)
+        self.sm_reserve = sm_reserve if next(model.parameters()).is_cuda else 0
+        self.reserve_launches = reserve_launches
         self._slot: Dict[torch.nn.Parameter, tuple] = {}
         self._order: List[torch.nn.Parameter] = []
         self._built = False
@@ -88,6 +99,10 @@ class GradReducer:
         for bi, b in enumerate(self.buckets):
             for p, off in zip(b.params, b.offsets):
                 self._slot[p] = (bi, off)
+                if p.is_cuda and p.dim() >= 2 and self.zero_copy:
+                    # large weights: the fused backward writes dW straight into this slot
+                    from . import ops
+                    ops.register_grad_dest(p, b.flat, off)
         self._built = True
 
     def bucket_layout(self) -> List[List[int]]:
@@ -108,12 +123,21 @@ class GradReducer:
             return
         bi, off = self._slot[p]
         b = self.buckets[bi]
-        view = b.flat[off:off + p.numel()].view_as(p)
-        view.copy_(p.grad)
-        p.grad = view
+        if p.grad.data_ptr() != b.flat.data_ptr() + 4 * off:     # not produced in place
+            b.todo.append((p, b.flat[off:off + p.numel()].view_as(p)))
         b.pending -= 1
         if b.pending == 0:
-            b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            if b.todo:   # one multi-tensor copy for all small gradients of the bucket
+                torch._foreach_copy_([v for _, v in b.todo], [q.grad for q, _ in b.todo])
+                for q, v in b.todo:
+                    q.grad = v
+                b.todo = []
+            if not _NO_COMM:
+                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group,
+                                         async_op=True)
+                if self.sm_reserve:
+                    from . import ops
+                    ops.reserve_sms_for(self.reserve_launches, self.sm_reserve)
 
     # -- public API --------------------------------------------------------------------------
     def backward(self, loss: torch.Tensor) -> None:
@@ -122,9 +146,17 @@ class GradReducer:
         if not self.enabled or self.world == 1:
             loss.backward()
             return
+        in_place_ok = True
         for b in self.buckets:
             b.pending = len(b.params)
             b.work = None
+            b.todo = []
+            # writing gradients straight into the bucket is only sound when autograd will ASSIGN
+            # (p.grad is None), not accumulate into the very same memory
+            in_place_ok = in_place_ok and all(p.grad is None for p in b.params)
+        if self.zero_copy:
+            from . import ops
+            ops.grad_dest_enabled = in_place_ok
         (loss / self.world).backward()
         self.finish()
 
@@ -140,6 +172,9 @@ class GradReducer:
                     p.grad = view
                 dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group)
             return
+        if self.sm_reserve:
+            from . import ops
+            ops.release_sms()
         for b in self.buckets:
             if b.pending != 0:
                 raise RuntimeError("a bucketed parameter received no gradient this step; the set of "

@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 
-from .blocks import FullAttentionBlock
+from .blocks import FullAttentionBlock, as_act
 
 
 class ResidualEncoder(nn.Module):
@@ -18,6 +18,7 @@ class ResidualEncoder(nn.Module):
                                      for _ in range(n_layers)])
 
     def forward(self, x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        x = as_act(x)                        # one cast for the whole chain (bf16 mode)
         q, s = x, None
         n = len(self.blocks)
         for i, blk in enumerate(self.blocks):
