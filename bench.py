@@ -406,21 +406,52 @@ def main():
     value = B * world * K / (ms * 1e-3)
 
     # ---- end to end: pinned host inputs -> H2D -> step -> D2H loss, every step --------------------
-    def e2e_step():
-        x_dev.copy_(host_x, non_blocking=True)
-        m_dev.copy_(host_m, non_blocking=True)
-        run()
-        host_loss.copy_(loss_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(host_loss)
+    # Software-pipelined like a real input pipeline: the H2D copy of step i+1 runs on a copy stream
+    # into a second staging buffer while step i computes; the loss of step i is read on the host one
+    # step later.  Every step's inputs cross PCIe and every step's loss reaches the host inside the
+    # timed region.
+    copy_stream = torch.cuda.Stream()
+    x_stage = [torch.empty_like(x_dev) for _ in range(2)]
+    m_stage = [torch.empty_like(m_dev) for _ in range(2)]
+    ev_h2d = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_loss = [torch.cuda.Event() for _ in range(2)]
+    host_losses = [torch.zeros((), pin_memory=True) for _ in range(2)]
 
-    for _ in range(2):
-        e2e_step()
+    def issue_h2d(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[s])          # compute no longer reads this stage
+            x_stage[s].copy_(host_x, non_blocking=True)
+            m_stage[s].copy_(host_m, non_blocking=True)
+            ev_h2d[s].record(copy_stream)
+
+    def e2e_run(n):
+        last = float("nan")
+        cur = torch.cuda.current_stream()
+        issue_h2d(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                issue_h2d(i + 1)
+            cur.wait_event(ev_h2d[s])
+            x_dev.copy_(x_stage[s], non_blocking=True)
+            m_dev.copy_(m_stage[s], non_blocking=True)
+            ev_free[s].record(cur)
+            run()
+            host_losses[s].copy_(loss_dev, non_blocking=True)
+            ev_loss[s].record(cur)
+            if i >= 1:
+                ev_loss[1 - s].synchronize()
+                last = float(host_losses[1 - s])
+        ev_loss[(n - 1) % 2].synchronize()
+        return float(host_losses[(n - 1) % 2])
+
+    e2e_run(3)
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    for _ in range(K):
-        last_loss = e2e_step()
+    last_loss = e2e_run(K)
     e1.record()
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
@@ -478,8 +509,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "samples/s",
                     "h2d_bytes_per_step": host_x.numel() * 4 + host_m.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / K,
-                    "how": "pinned host x,mask -> cudaMemcpyAsync -> graph replay -> loss D2H + "
-                           "stream sync, every step"},
+                    "how": "pinned host x,mask -> cudaMemcpyAsync on a copy stream (double-buffered, "
+                           "overlaps the previous step) -> graph replay -> loss D2H, read on the host "
+                           "one step later; all inside the timed region"},
             "gpu_launches": launches_per_step * K,
             "launches_per_step": launches_per_step,
             "cuda_graph": graph is not None,

@@ -88,7 +88,8 @@ resattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   if (threadIdx.x >= 64) {  // softmax threads stage the mask row (same for every query)
     const int j = threadIdx.x - 64;
-    mask_s[j] = a.mask ? a.mask[(int64_t)b * a.mask_bs + j] : 1.0f;
+    // additive mask term 1e8*(1-m), computed once per key (same fp32 ops as the reference)
+    mask_s[j] = a.mask ? __fmul_rn(1.0e8f, __fsub_rn(1.0f, a.mask[(int64_t)b * a.mask_bs + j])) : 0.0f;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -166,14 +167,14 @@ resattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = ch * 32 + q4 * 8 + e * 2;
-          float s0 = __uint_as_float(r[q4 * 8 + e * 2]) / a.sqrt_hd;
-          float s1 = __uint_as_float(r[q4 * 8 + e * 2 + 1]) / a.sqrt_hd;
+          float s0 = __uint_as_float(r[q4 * 8 + e * 2]) * 0.125f;   // == / sqrt(64), exact
+          float s1 = __uint_as_float(r[q4 * 8 + e * 2 + 1]) * 0.125f;   // == / sqrt(64), exact
           if (a.has_prev) {
             s0 = __fadd_rn(s0, __fmul_rn(cval, bf16_lo(pv[e])));
             s1 = __fadd_rn(s1, __fmul_rn(cval, bf16_hi(pv[e])));
           }
-          s0 = __fsub_rn(s0, __fmul_rn(1.0e8f, __fsub_rn(1.0f, mask_s[j])));
-          s1 = __fsub_rn(s1, __fmul_rn(1.0e8f, __fsub_rn(1.0f, mask_s[j + 1])));
+          s0 = __fsub_rn(s0, mask_s[j]);
+          s1 = __fsub_rn(s1, mask_s[j + 1]);
           out[e] = pack_bf16(s0, s1);
           mx = fmaxf(mx, fmaxf(bf16_lo(out[e]), bf16_hi(out[e])));
         }
@@ -392,7 +393,8 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   if (threadIdx.x >= 64) {
     const int j = threadIdx.x - 64;
-    mask_s[j] = a.mask ? a.mask[(int64_t)b * a.mask_bs + j] : 1.0f;
+    // additive mask term 1e8*(1-m), computed once per key (same fp32 ops as the reference)
+    mask_s[j] = a.mask ? __fmul_rn(1.0e8f, __fsub_rn(1.0f, a.mask[(int64_t)b * a.mask_bs + j])) : 0.0f;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -497,14 +499,14 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             s0 = bf16_lo(sv[e]);
             s1 = bf16_hi(sv[e]);
           } else {
-            s0 = __uint_as_float(sa[i0]) / a.sqrt_hd;
-            s1 = __uint_as_float(sa[i0 + 1]) / a.sqrt_hd;
+            s0 = __uint_as_float(sa[i0]) * 0.125f;   // == / sqrt(64), exact
+            s1 = __uint_as_float(sa[i0 + 1]) * 0.125f;   // == / sqrt(64), exact
             if (a.has_prev) {
               s0 = __fadd_rn(s0, __fmul_rn(cval, bf16_lo(pv[e])));
               s1 = __fadd_rn(s1, __fmul_rn(cval, bf16_hi(pv[e])));
             }
-            s0 = __fsub_rn(s0, __fmul_rn(1.0e8f, __fsub_rn(1.0f, mask_s[j])));
-            s1 = __fsub_rn(s1, __fmul_rn(1.0e8f, __fsub_rn(1.0f, mask_s[j + 1])));
+            s0 = __fsub_rn(s0, mask_s[j]);
+            s1 = __fsub_rn(s1, mask_s[j + 1]);
             const uint32_t rr = pack_bf16(s0, s1);   // the forward softmax saw bf16-rounded scores
             s0 = bf16_lo(rr);
             s1 = bf16_hi(rr);
@@ -566,7 +568,7 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     // ---- epilogue: dV, dK, dQ -> bf16 staging (V, K, Q tiles are dead) -> TMA stores ---------------
     tc::mbar_wait(bar_mm2, 0);
     tc::tc_fence_after();
-    const float inv_sqrt = 1.0f / a.sqrt_hd;
+    const float inv_sqrt = 1.0f * 0.125f;   // == / sqrt(64), exact
 #pragma unroll 1
     for (int t = 0; t < 3; ++t) {
       const uint32_t src = t == 0 ? tm_dV : (t == 1 ? tm_dK : tm_dQ);
