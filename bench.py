@@ -106,6 +106,15 @@ def _algorithmic(name: str, a: tuple):
     formulas of SURVEY.md §8d)."""
     bf = name.endswith("_bf16")
     e = 2 if bf else 4
+    if "_grouped_" in name:   # host arrays of per-problem M, N, K
+        i0 = 8 if name.startswith("mmemo_linear_fwd") else 7
+        Ms, Ns, Ks = list(a[i0]), list(a[i0 + 1]), list(a[i0 + 2])
+        fl = sum(2 * m * n * k for m, n, k in zip(Ms, Ns, Ks))
+        if name.startswith("mmemo_linear_bwd_w"):
+            by = sum(e * (m * n + m * k) + 4 * n * k for m, n, k in zip(Ms, Ns, Ks))
+        else:
+            by = sum(e * (m * k + n * k + m * n) for m, n, k in zip(Ms, Ns, Ks))
+        return fl, by, "+".join(f"{m}x{n}x{k}" for m, n, k in zip(Ms, Ns, Ks))
     if name.startswith("mmemo_linear_fwd"):
         M, N, K = a[10], a[11], a[12]
         ex = 4 if a[1] else e

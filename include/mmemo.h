@@ -81,6 +81,24 @@ int mmemo_linear_bwd_w_bf16(const void* dy, int64_t lddy, const void* x, int x_i
                             float* dw, int64_t lddw, float* dbias, int64_t M, int64_t N, int64_t K,
                             int accumulate, mmemo_stream_t stream);
 
+/* Grouped variants (bf16): n <= 6 independent problems of the kinds above in ONE persistent
+ * tensor-core launch (the Q and K|V projections of a block; its five weight gradients), so that
+ * GEMMs too small to fill 148 SMs share a wave.  All arrays are HOST arrays of length n.  Falls
+ * back to n single launches when a problem does not meet the tensor-core kernel's constraints. */
+int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ldx,
+                                  const void* const* w, const int64_t* ldw,
+                                  const float* const* bias, void* const* y, const int64_t* ldy,
+                                  const int64_t* M, const int64_t* N, const int64_t* K,
+                                  const int* relu, mmemo_stream_t stream);
+int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
+                                    const void* const* w, const int64_t* ldw, void* const* dx,
+                                    const int64_t* lddx, const int64_t* M, const int64_t* N,
+                                    const int64_t* K, const int* accumulate, mmemo_stream_t stream);
+int mmemo_linear_bwd_w_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
+                                    const void* const* x, const int64_t* ldx, float* const* dw,
+                                    const int64_t* lddw, const int64_t* M, const int64_t* N,
+                                    const int64_t* K, int accumulate, mmemo_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused residual-attention core (kernel a / a').  Replaces
  *   others/realformer.py:189-203  cmu-mosei/run.py:242-256  Ren-MME/run.py:194-208

@@ -26,3 +26,5 @@ int gemm_simt(const GemmArgs& g, int a_bf16, int b_bf16, int c_bf16, cudaStream_
 // Returns 1 if it accepts the shape/layout.
 bool gemm_tc_supported(const GemmArgs& g, int c_bf16);
 int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st);
+// up to 6 independent problems in one persistent launch (every problem must be gemm_tc_supported)
+int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t st);

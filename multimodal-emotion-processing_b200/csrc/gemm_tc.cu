@@ -50,11 +50,20 @@ struct TcArgs {
   int tiles_m, tiles_n;    // in units of the (pair) tile: TM x BN
 };
 
+// One launch can serve up to MAXG independent GEMMs ("grouped"): the work items of all problems
+// form one list that the persistent CTAs walk, so small GEMMs that would each leave the machine
+// half empty (the five weight gradients of a block, the Q and K|V projections) share one wave.
+constexpr int MAXG = 6;
+struct TmapGroup { CUtensorMap a[MAXG], b[MAXG], c[MAXG], aux[MAXG]; };
+struct GroupArgs {
+  int n;
+  int item_start[MAXG + 1];
+  TcArgs p[MAXG];
+};
+
 template <bool CTA2>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAux,
-               const TcArgs a) {
+gemm_tc_kernel(const __grid_constant__ TmapGroup TMS, const __grid_constant__ GroupArgs G) {
   constexpr int BN = CTA2 ? 256 : 128;        // accumulator columns per tile
   constexpr int TM = CTA2 ? 256 : 128;        // output rows per work item (pair or CTA)
   constexpr int NHALF = BN / 128;             // epilogue works on 128 columns at a time
@@ -75,11 +84,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t rank = CTA2 ? tc::cluster_ctarank() : 0u;      // 0 = leader of the pair
   const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int total = a.tiles_m * a.tiles_n * a.splits;
+  const int total = G.item_start[G.n];
 
-  auto decode = [&](int w, int& m0, int& n0, int& sp, int& tile) {
-    sp = w % a.splits;
-    tile = w / a.splits;
+  // global work item -> (problem, item within the problem)
+  auto locate = [&](int w, int& g, int& lw) {
+    g = 0;
+    while (g + 1 < G.n && w >= G.item_start[g + 1]) ++g;
+    lw = w - G.item_start[g];
+  };
+  auto decode = [&](const TcArgs& a, int lw, int& m0, int& n0, int& sp, int& tile) {
+    sp = lw % a.splits;
+    tile = lw / a.splits;
     const int tm = tile / a.tiles_n, tn = tile - tm * a.tiles_n;
     m0 = tm * TM + (int)rank * BM;     // rows owned by this CTA
     n0 = tn * BN;                      // first column of the (pair) tile
@@ -96,9 +111,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc::mbar_init(bar_aux, 1);
     tc::fence_barrier_init();
-    tc::tma_prefetch_desc(&tmA);
-    tc::tma_prefetch_desc(&tmB);
-    tc::tma_prefetch_desc(&tmC);
+    tc::tma_prefetch_desc(&TMS.a[0]);
+    tc::tma_prefetch_desc(&TMS.b[0]);
+    tc::tma_prefetch_desc(&TMS.c[0]);
   }
   if (warp == 1) {
     if (CTA2) { tc::tmem_alloc_2sm(tmem_slot, 2 * BN); tc::tmem_relinquish_2sm(); }
@@ -114,8 +129,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;
       for (int w = unit; w < total; w += units) {
-        int m0, n0, sp, tile;
-        decode(w, m0, n0, sp, tile);
+        int g, lw, m0, n0, sp, tile;
+        locate(w, g, lw);
+        const TcArgs& a = G.p[g];
+        const CUtensorMap* tmA = &TMS.a[g];
+        const CUtensorMap* tmB = &TMS.b[g];
+        decode(a, lw, m0, n0, sp, tile);
         const int nb = n0 + (int)rank * 128;           // this CTA's 128 columns of B
         const int kb_beg = sp * a.kb_per, kb_end = min(a.kb_total, kb_beg + a.kb_per);
         for (int kb = kb_beg; kb < kb_end; ++kb, ++it) {
@@ -130,16 +149,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else tc::tma_load_2d(dst, tm, c0, c1, fb);
           };
           if (!a.a_mn) {
-            ld(da, &tmA, k0, m0);                                // box {64 k, 128 m}
+            ld(da, tmA, k0, m0);                                 // box {64 k, 128 m}
           } else {
-            ld(da, &tmA, m0, k0);                                // box {64 m, 64 k}
-            ld(da + A_TILE / 2, &tmA, m0 + 64, k0);
+            ld(da, tmA, m0, k0);                                 // box {64 m, 64 k}
+            ld(da + A_TILE / 2, tmA, m0 + 64, k0);
           }
           if (!a.b_mn) {
-            ld(db, &tmB, k0, nb);
+            ld(db, tmB, k0, nb);
           } else {
-            ld(db, &tmB, nb, k0);
-            ld(db + B_TILE / 2, &tmB, nb + 64, k0);
+            ld(db, tmB, nb, k0);
+            ld(db + B_TILE / 2, tmB, nb + 64, k0);
           }
         }
       }
@@ -149,7 +168,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0 && rank == 0) {
       uint32_t it = 0, ti = 0;
       for (int w = unit; w < total; w += units, ++ti) {
-        const int sp = w % a.splits;
+        int g, lw;
+        locate(w, g, lw);
+        const TcArgs& a = G.p[g];
+        const int sp = lw % a.splits;
         const int kb_beg = sp * a.kb_per, kb_end = min(a.kb_total, kb_beg + a.kb_per);
         const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
         tc::mbar_wait(bar_acce + 8 * buf, aph ^ 1);     // epilogues have drained this accumulator
@@ -183,34 +205,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const int te = threadIdx.x - 64;
-    const bool partial = a.splits > 1;
-    const bool out_f32 = partial || !a.c_bf16;
     // step = (work item, 128-column half); aux tile of a step: old C (accumulate) or the saved
-    // activation (ReLU mask), bf16, prefetched one step ahead
+    // activation (ReLU mask), bf16, prefetched one step ahead (issue order == consumption order)
     auto issue_aux = [&](int w, int half) {
-      int m0, n0, sp, tile;
-      decode(w, m0, n0, sp, tile);
+      int g, lw, m0, n0, sp, tile;
+      locate(w, g, lw);
+      if (!G.p[g].aux) return;
+      decode(G.p[g], lw, m0, n0, sp, tile);
       tc::mbar_expect_tx(bar_aux, 32 * 1024);
-      tc::tma_load_2d(sAux, &tmAux, n0 + half * 128, m0, bar_aux);
-      tc::tma_load_2d(sAux + 16384, &tmAux, n0 + half * 128 + 64, m0, bar_aux);
+      tc::tma_load_2d(sAux, &TMS.aux[g], n0 + half * 128, m0, bar_aux);
+      tc::tma_load_2d(sAux + 16384, &TMS.aux[g], n0 + half * 128 + 64, m0, bar_aux);
     };
-    if (a.aux && te == 0 && unit < total) issue_aux(unit, 0);
-    uint32_t ti = 0, step = 0;
+    if (te == 0 && unit < total) issue_aux(unit, 0);
+    uint32_t ti = 0, aux_ctr = 0;
     for (int w = unit; w < total; w += units, ++ti) {
-      int m0, n0, sp, tile;
-      decode(w, m0, n0, sp, tile);
+      int g, lw, m0, n0, sp, tile;
+      locate(w, g, lw);
+      const TcArgs& a = G.p[g];
+      const CUtensorMap* tmC = &TMS.c[g];
+      const bool partial = a.splits > 1;
+      const bool out_f32 = partial || !a.c_bf16;
+      decode(a, lw, m0, n0, sp, tile);
       const int64_t m = (int64_t)m0 + row;
       const int pos_row = a.pos ? (int)((uint32_t)(m0 + row) % (uint32_t)a.pos_period) : 0;
       const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
       tc::mbar_wait(bar_accf + 8 * buf, aph);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < NHALF; ++half, ++step) {
+      for (int half = 0; half < NHALF; ++half) {
         const int nh = n0 + half * 128;                  // first column of this half
         if (te == 0) tc::tma_store_wait_read();          // previous store has left the staging tile
         if (a.bias) sbias[te] = (nh + te < a.N) ? __ldg(a.bias + nh + te) : 0.f;
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (a.aux) tc::mbar_wait(bar_aux, step & 1);
+        if (a.aux) { tc::mbar_wait(bar_aux, aux_ctr & 1); ++aux_ctr; }
         const uint32_t taddr =
             tmem_base + buf * BN + half * 128 + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
@@ -290,25 +317,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (partial && a.reduce_add) {   // C += slice, summed by the L2
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              if (nh + p * 32 < a.N) tc::tma_reduce_add_2d(&tmC, sOut + p * 16384, nh + p * 32, m0);
+              if (nh + p * 32 < a.N) tc::tma_reduce_add_2d(tmC, sOut + p * 16384, nh + p * 32, m0);
           } else if (partial) {   // workspace: [(tile*splits + split)*TM rows][BN fp32 columns]
             const int prow = (tile * a.splits + sp) * TM + (int)rank * BM;
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              tc::tma_store_2d(&tmC, sOut + p * 16384, half * 128 + p * 32, prow);
+              tc::tma_store_2d(tmC, sOut + p * 16384, half * 128 + p * 32, prow);
           } else if (out_f32) {
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              if (nh + p * 32 < a.N) tc::tma_store_2d(&tmC, sOut + p * 16384, nh + p * 32, m0);
+              if (nh + p * 32 < a.N) tc::tma_store_2d(tmC, sOut + p * 16384, nh + p * 32, m0);
           } else {
-            if (nh < a.N) tc::tma_store_2d(&tmC, sOut, nh, m0);
-            if (nh + 64 < a.N) tc::tma_store_2d(&tmC, sOut + 16384, nh + 64, m0);
+            if (nh < a.N) tc::tma_store_2d(tmC, sOut, nh, m0);
+            if (nh + 64 < a.N) tc::tma_store_2d(tmC, sOut + 16384, nh + 64, m0);
           }
           tc::tma_store_commit();
-          if (a.aux) {   // prefetch the aux tile of the next step
-            if (half + 1 < NHALF) issue_aux(w, half + 1);
-            else if (w + units < total) issue_aux(w + units, 0);
-          }
+          // prefetch the aux tile of the next step (if that step has one)
+          if (half + 1 < NHALF) issue_aux(w, half + 1);
+          else if (w + units < total) issue_aux(w + units, 0);
         }
       }
     }
@@ -452,7 +478,8 @@ bool gemm_tc_supported(const GemmArgs& g, int c_bf16) {
   return true;
 }
 
-int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
+int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t st) {
+  if (n < 1 || n > MAXG) return MMEMO_ERR_ARG;
   static bool attr_done = false;
   if (!attr_done) {
     MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>,
@@ -461,84 +488,103 @@ int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     attr_done = true;
   }
-  const bool a_mn = !(g.sAk == 1 && g.sAm % 8 == 0);
-  const bool b_mn = !(g.sBk == 1 && g.sBn % 8 == 0);
-  // CTA pairs (256 x 256 tiles) when the output is wide and tall enough to fill them
-  const bool cta2 = !g_force_1cta && g.N >= 256 && g.M >= 256;
+  // CTA pairs (256 x 256 tiles) when every output is wide and tall enough to fill them
+  bool cta2 = !g_force_1cta;
+  for (int i = 0; i < n; ++i) cta2 = cta2 && gs[i].N >= 256 && gs[i].M >= 256;
   const int TM = cta2 ? 256 : 128, BN = cta2 ? 256 : 128;
-  const int tiles_n = (int)cdiv(g.N, BN), tiles_m = (int)cdiv(g.M, TM);
-  const int tiles = tiles_m * tiles_n;
-  const int kb_total = (int)cdiv(g.K, BK);
   const int sms = num_sms();
   const int units_max = cta2 ? sms / 2 : sms;      // schedulable work units (pairs or CTAs)
-  // split-K when the output has too few tiles to occupy the machine and K is long (needs a linear
-  // epilogue: bias and accumulate are applied after the reduction)
+  // split-K when the outputs have too few tiles to occupy the machine and K is long (needs linear
+  // epilogues: bias and accumulate are applied after / by the reduction)
+  int tiles_sum = 0, kb_min = 1 << 30;
+  bool linear = true, all_reduce_add = true;
+  for (int i = 0; i < n; ++i) {
+    const GemmArgs& g = gs[i];
+    tiles_sum += (int)(cdiv(g.M, TM) * cdiv(g.N, BN));
+    const int kb = (int)cdiv(g.K, BK);
+    kb_min = kb < kb_min ? kb : kb_min;
+    linear = linear && !g.relu && !g.relu_src && !g.pos;
+    all_reduce_add = all_reduce_add && !c_bf16s[i] && !g.bias;   // fp32 C summed by TMA reduce-add
+  }
   int splits = 1;
-  const bool reduce_add = !c_bf16 && !g.bias;   // fp32 C: slices are summed by TMA reduce-add
-  if (tiles * 2 <= units_max && kb_total >= 16 && !g.relu && !g.relu_src && !g.pos) {
-    splits = units_max / tiles;                         // one balanced round of work items
-    if (splits > kb_total / 4) splits = kb_total / 4;
+  if (tiles_sum * 2 <= units_max && kb_min >= 16 && linear && (all_reduce_add || n == 1)) {
+    splits = units_max / tiles_sum;                     // one balanced round of work items
+    if (splits > kb_min / 4) splits = kb_min / 4;
     if (splits > 32) splits = 32;
-    if (!reduce_add) {
-      const size_t per_split = (size_t)tiles * TM * BN * sizeof(float);
+    if (!all_reduce_add) {
+      const size_t per_split = (size_t)tiles_sum * TM * BN * sizeof(float);
       if (per_split * (size_t)splits > g_ws_bytes) splits = (int)(g_ws_bytes / per_split);
     }
     if (splits < 2) splits = 1;
   }
-  const int kb_per = (int)cdiv(kb_total, splits);
-  splits = (int)cdiv(kb_total, kb_per);               // every slice owns >= 1 k-block
-  const bool partial = splits > 1;
-  const int aux = partial ? AUX_NONE : (g.relu_src ? AUX_RELU : (g.accumulate ? AUX_ACC : AUX_NONE));
 
-  CUtensorMap tmA, tmB, tmC, tmAux;
-  {
+  static TmapGroup tms;     // host staging (copied by value into the launch)
+  GroupArgs G = {};
+  G.n = n;
+  int items = 0;
+  bool ok = true;
+  for (int i = 0; i < n; ++i) {
+    const GemmArgs& g = gs[i];
+    const int c_bf16 = c_bf16s[i];
+    const bool a_mn = !(g.sAk == 1 && g.sAm % 8 == 0);
+    const bool b_mn = !(g.sBk == 1 && g.sBn % 8 == 0);
+    const int tiles_n = (int)cdiv(g.N, BN), tiles_m = (int)cdiv(g.M, TM);
+    const int tiles = tiles_m * tiles_n;
+    const int kb_total = (int)cdiv(g.K, BK);
+    const int kb_per = (int)cdiv(kb_total, splits);
+    const int sp = (int)cdiv(kb_total, kb_per);        // every slice owns >= 1 k-block
+    const bool partial = sp > 1;
+    const bool reduce_add = partial && all_reduce_add;
+    const int aux = partial ? AUX_NONE : (g.relu_src ? AUX_RELU : (g.accumulate ? AUX_ACC : AUX_NONE));
     uint64_t dims[2], str[1];
     uint32_t box[2];
     if (!a_mn) { dims[0] = g.K; dims[1] = g.M; str[0] = g.sAm * 2; box[0] = 64; box[1] = BM; }
     else       { dims[0] = g.M; dims[1] = g.K; str[0] = g.sAk * 2; box[0] = 64; box[1] = BK; }
-    bool ok = mm_make_tmap_bf16(&tmA, g.A, 2, dims, str, box);
+    ok = ok && mm_make_tmap_bf16(&tms.a[i], g.A, 2, dims, str, box);
     if (!b_mn) { dims[0] = g.K; dims[1] = g.N; str[0] = g.sBn * 2; box[0] = 64; box[1] = 128; }
     else       { dims[0] = g.N; dims[1] = g.K; str[0] = g.sBk * 2; box[0] = 64; box[1] = BK; }
-    ok = ok && mm_make_tmap_bf16(&tmB, g.B, 2, dims, str, box);
-    if (partial && !reduce_add) {
-      dims[0] = BN; dims[1] = (uint64_t)tiles * splits * TM; str[0] = (uint64_t)BN * 4;
+    ok = ok && mm_make_tmap_bf16(&tms.b[i], g.B, 2, dims, str, box);
+    if (partial && !reduce_add) {     // n == 1 here
+      dims[0] = BN; dims[1] = (uint64_t)tiles * sp * TM; str[0] = (uint64_t)BN * 4;
       box[0] = 32; box[1] = BM;
-      ok = ok && mm_make_tmap_f32(&tmC, g_ws, 2, dims, str, box);
+      ok = ok && mm_make_tmap_f32(&tms.c[i], g_ws, 2, dims, str, box);
     } else if (!c_bf16) {
       dims[0] = g.N; dims[1] = g.M; str[0] = g.ldc * 4; box[0] = 32; box[1] = BM;
-      ok = ok && mm_make_tmap_f32(&tmC, g.C, 2, dims, str, box);
+      ok = ok && mm_make_tmap_f32(&tms.c[i], g.C, 2, dims, str, box);
     } else {
       dims[0] = g.N; dims[1] = g.M; str[0] = g.ldc * 2; box[0] = 64; box[1] = BM;
-      ok = ok && mm_make_tmap_bf16(&tmC, g.C, 2, dims, str, box);
+      ok = ok && mm_make_tmap_bf16(&tms.c[i], g.C, 2, dims, str, box);
     }
     if (aux == AUX_RELU) {
       dims[0] = g.N; dims[1] = g.M; str[0] = g.ldrelu * 2; box[0] = 64; box[1] = BM;
-      ok = ok && mm_make_tmap_bf16(&tmAux, g.relu_src, 2, dims, str, box);
+      ok = ok && mm_make_tmap_bf16(&tms.aux[i], g.relu_src, 2, dims, str, box);
     } else if (aux == AUX_ACC) {
       dims[0] = g.N; dims[1] = g.M; str[0] = g.ldc * 2; box[0] = 64; box[1] = BM;
-      ok = ok && mm_make_tmap_bf16(&tmAux, g.C, 2, dims, str, box);
+      ok = ok && mm_make_tmap_bf16(&tms.aux[i], g.C, 2, dims, str, box);
     } else {
-      tmAux = tmA;
+      tms.aux[i] = tms.a[i];
     }
-    if (!ok) {
-      mmemo_set_error("cuTensorMapEncodeTiled failed (gemm_tc)", __FILE__, __LINE__);
-      return MMEMO_ERR_CUDA;
-    }
+    TcArgs& a = G.p[i];
+    a.M = (int)g.M; a.N = (int)g.N; a.K = (int)g.K; a.c_bf16 = c_bf16;
+    a.bias = partial ? nullptr : g.bias;
+    a.pos = g.pos; a.pos_period = (int)g.pos_period;
+    a.relu = g.relu; a.aux = aux;
+    a.a_mn = a_mn; a.b_mn = b_mn;
+    a.idesc = tc::idesc_bf16(TM, BN, a_mn, b_mn);
+    a.splits = sp; a.kb_per = kb_per; a.kb_total = kb_total;
+    a.reduce_add = reduce_add;
+    a.tiles_m = tiles_m; a.tiles_n = tiles_n;
+    G.item_start[i] = items;
+    items += tiles * sp;
+    if (reduce_add && !g.accumulate)   // the slices accumulate into C: start from zero
+      MM_CUDA_OK(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
   }
-  TcArgs a = {};
-  a.M = (int)g.M; a.N = (int)g.N; a.K = (int)g.K; a.c_bf16 = c_bf16;
-  a.bias = partial ? nullptr : g.bias;
-  a.pos = g.pos; a.pos_period = (int)g.pos_period;
-  a.relu = g.relu; a.aux = aux;
-  a.a_mn = a_mn; a.b_mn = b_mn;
-  a.idesc = tc::idesc_bf16(TM, BN, a_mn, b_mn);
-  a.splits = splits; a.kb_per = kb_per; a.kb_total = kb_total;
-  a.reduce_add = partial && reduce_add;
-  a.tiles_m = tiles_m; a.tiles_n = tiles_n;
-  const int total = tiles * splits;
-  const int units = total < units_max ? total : units_max;
-  if (a.reduce_add && !g.accumulate)   // the slices accumulate into C: start from zero
-    MM_CUDA_OK(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
+  G.item_start[n] = items;
+  if (!ok) {
+    mmemo_set_error("cuTensorMapEncodeTiled failed (gemm_tc)", __FILE__, __LINE__);
+    return MMEMO_ERR_CUDA;
+  }
+  const int units = items < units_max ? items : units_max;
   if (cta2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * units));
@@ -552,21 +598,28 @@ int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    MM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tmA, tmB, tmC, tmAux, a));
+    MM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tms, G));
   } else {
-    gemm_tc_kernel<false><<<units, NTHREADS, SMEM_BYTES, st>>>(tmA, tmB, tmC, tmAux, a);
+    gemm_tc_kernel<false><<<units, NTHREADS, SMEM_BYTES, st>>>(tms, G);
     MM_LAUNCH_OK();
   }
-  if (partial && !a.reduce_add) {
+  if (n == 1 && G.p[0].splits > 1 && !G.p[0].reduce_add) {
+    const GemmArgs& g = gs[0];
     ReduceArgs r = {};
     r.partial = g_ws; r.C = g.C; r.ldc = g.ldc; r.M = (int)g.M; r.N = (int)g.N;
-    r.splits = splits; r.tiles_n = tiles_n; r.c_bf16 = c_bf16; r.accumulate = g.accumulate;
+    r.splits = G.p[0].splits; r.tiles_n = G.p[0].tiles_n; r.c_bf16 = c_bf16s[0];
+    r.accumulate = g.accumulate;
     r.tm_rows = TM; r.bn_cols = BN;
     r.bias = g.bias;
+    const int tiles = G.p[0].tiles_m * G.p[0].tiles_n;
     int ysplit = (int)cdiv(2 * sms, tiles);
     if (ysplit > 16) ysplit = 16;
     splitk_reduce_kernel<<<dim3((unsigned)tiles, (unsigned)ysplit), 256, 0, st>>>(r);
     MM_LAUNCH_OK();
   }
   return MMEMO_OK;
+}
+
+int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
+  return gemm_tc_grouped(&g, &c_bf16, 1, st);
 }

@@ -83,6 +83,87 @@ int mmemo_gemm_uses_tensor_cores(int64_t M, int64_t N, int64_t K, int64_t lda, i
   }
 }
 
+// ---- grouped variants (bf16): n independent problems, ONE tensor-core launch when all qualify ----
+int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ldx,
+                                  const void* const* w, const int64_t* ldw,
+                                  const float* const* bias, void* const* y, const int64_t* ldy,
+                                  const int64_t* M, const int64_t* N, const int64_t* K,
+                                  const int* relu, mmemo_stream_t s) {
+  if (n < 1 || n > 6) return MMEMO_ERR_ARG;
+  GemmArgs g[6] = {};
+  int cb[6];
+  bool tc_ok = true;
+  for (int i = 0; i < n; ++i) {
+    MM_REQUIRE(x[i] && w[i] && y[i]);
+    g[i].A = x[i]; g[i].sAm = ldx[i]; g[i].sAk = 1;
+    g[i].B = w[i]; g[i].sBn = ldw[i]; g[i].sBk = 1;
+    g[i].C = y[i]; g[i].ldc = ldy[i];
+    g[i].M = M[i]; g[i].N = N[i]; g[i].K = K[i];
+    g[i].bias = bias ? bias[i] : nullptr; g[i].pos_period = 1;
+    g[i].relu = relu ? relu[i] : 0;
+    cb[i] = 1;
+    tc_ok = tc_ok && gemm_tc_supported(g[i], 1);
+  }
+  if (tc_ok) return gemm_tc_grouped(g, cb, n, mm_stream(s));
+  for (int i = 0; i < n; ++i) {
+    const int rc = run(g[i], 1, 1, 1, mm_stream(s));
+    if (rc) return rc;
+  }
+  return MMEMO_OK;
+}
+int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
+                                    const void* const* w, const int64_t* ldw, void* const* dx,
+                                    const int64_t* lddx, const int64_t* M, const int64_t* N,
+                                    const int64_t* K, const int* accumulate, mmemo_stream_t s) {
+  if (n < 1 || n > 6) return MMEMO_ERR_ARG;
+  GemmArgs g[6] = {};
+  int cb[6];
+  bool tc_ok = true;
+  for (int i = 0; i < n; ++i) {
+    MM_REQUIRE(dy[i] && w[i] && dx[i]);
+    g[i].A = dy[i]; g[i].sAm = lddy[i]; g[i].sAk = 1;
+    g[i].B = w[i]; g[i].sBn = 1; g[i].sBk = ldw[i];
+    g[i].C = dx[i]; g[i].ldc = lddx[i];
+    g[i].M = M[i]; g[i].N = K[i]; g[i].K = N[i];
+    g[i].pos_period = 1;
+    g[i].accumulate = accumulate ? accumulate[i] : 0;
+    cb[i] = 1;
+    tc_ok = tc_ok && gemm_tc_supported(g[i], 1);
+  }
+  if (tc_ok) return gemm_tc_grouped(g, cb, n, mm_stream(s));
+  for (int i = 0; i < n; ++i) {
+    const int rc = run(g[i], 1, 1, 1, mm_stream(s));
+    if (rc) return rc;
+  }
+  return MMEMO_OK;
+}
+int mmemo_linear_bwd_w_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
+                                    const void* const* x, const int64_t* ldx, float* const* dw,
+                                    const int64_t* lddw, const int64_t* M, const int64_t* N,
+                                    const int64_t* K, int accumulate, mmemo_stream_t s) {
+  if (n < 1 || n > 6) return MMEMO_ERR_ARG;
+  GemmArgs g[6] = {};
+  int cb[6];
+  bool tc_ok = true;
+  for (int i = 0; i < n; ++i) {
+    MM_REQUIRE(dy[i] && x[i] && dw[i]);
+    g[i].A = dy[i]; g[i].sAm = 1; g[i].sAk = lddy[i];
+    g[i].B = x[i]; g[i].sBn = 1; g[i].sBk = ldx[i];
+    g[i].C = dw[i]; g[i].ldc = lddw[i];
+    g[i].M = N[i]; g[i].N = K[i]; g[i].K = M[i];
+    g[i].pos_period = 1;
+    g[i].accumulate = accumulate;
+    cb[i] = 0;
+    tc_ok = tc_ok && gemm_tc_supported(g[i], 0);
+  }
+  if (tc_ok) return gemm_tc_grouped(g, cb, n, mm_stream(s));
+  for (int i = 0; i < n; ++i) {
+    const int rc = run(g[i], 1, 1, 0, mm_stream(s));
+    if (rc) return rc;
+  }
+  return MMEMO_OK;
+}
+
 #define MM_LINEAR(SUF, BF)                                                                        \
   int mmemo_linear_fwd_##SUF(const void* x, int x_is_f32, int64_t ldx, const void* w, int64_t ldw, \
                              const float* bias, const float* pos, int64_t pos_period, void* y,    \

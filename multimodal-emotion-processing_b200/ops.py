@@ -231,6 +231,64 @@ def _linear_bwd_w(bf16, dy, x, dw, dbias=None, accumulate=False, N=None, K=None)
           int(accumulate), _stream())
 
 
+def _arr(ctype, vals):
+    return (ctype * len(vals))(*vals)
+
+
+def _linear_fwd_group(bf16, items):
+    """items: [(x, w, bias, out2d, relu)].  One grouped tensor-core launch in bf16 mode."""
+    if not bf16 or len(items) == 1:
+        for x, w, b, out, relu in items:
+            _linear_fwd(bf16, x, w, b, None, out, relu=relu)
+        return
+    xs = [_rows(it[0]) for it in items]
+    _call("mmemo_linear_fwd_grouped_bf16", len(items),
+          _arr(C.c_void_p, [x.data_ptr() for x, _, _ in xs]), _arr(C.c_int64, [ld for _, _, ld in xs]),
+          _arr(C.c_void_p, [it[1].data_ptr() for it in items]),
+          _arr(C.c_int64, [it[1].stride(0) for it in items]),
+          _arr(C.c_void_p, [_p(it[2]) for it in items]),
+          _arr(C.c_void_p, [it[3].data_ptr() for it in items]),
+          _arr(C.c_int64, [it[3].stride(-2) for it in items]),
+          _arr(C.c_int64, [M for _, M, _ in xs]), _arr(C.c_int64, [it[1].shape[0] for it in items]),
+          _arr(C.c_int64, [x.shape[-1] for x, _, _ in xs]),
+          _arr(C.c_int, [int(it[4]) for it in items]), _stream())
+
+
+def _linear_bwd_x_group(bf16, items):
+    """items: [(dy, w, dx2d, accumulate)] — outputs must not alias each other."""
+    if not bf16 or len(items) == 1:
+        for dy, w, dx, acc in items:
+            _linear_bwd_x(bf16, dy, w, dx, accumulate=acc)
+        return
+    dys = [_rows(it[0]) for it in items]
+    _call("mmemo_linear_bwd_x_grouped_bf16", len(items),
+          _arr(C.c_void_p, [d.data_ptr() for d, _, _ in dys]), _arr(C.c_int64, [ld for _, _, ld in dys]),
+          _arr(C.c_void_p, [it[1].data_ptr() for it in items]),
+          _arr(C.c_int64, [it[1].stride(0) for it in items]),
+          _arr(C.c_void_p, [it[2].data_ptr() for it in items]),
+          _arr(C.c_int64, [it[2].stride(-2) for it in items]),
+          _arr(C.c_int64, [M for _, M, _ in dys]), _arr(C.c_int64, [it[1].shape[0] for it in items]),
+          _arr(C.c_int64, [it[1].shape[1] for it in items]),
+          _arr(C.c_int, [int(it[3]) for it in items]), _stream())
+
+
+def _linear_bwd_w_group(bf16, items):
+    """items: [(dy, x, dw)] -> dw = dy^T x (float32), all in one grouped launch in bf16 mode."""
+    if not bf16 or len(items) == 1:
+        for dy, x, dw in items:
+            _linear_bwd_w(bf16, dy, x, dw)
+        return
+    dys = [_rows(it[0]) for it in items]
+    xs = [_rows(it[1]) for it in items]
+    _call("mmemo_linear_bwd_w_grouped_bf16", len(items),
+          _arr(C.c_void_p, [d.data_ptr() for d, _, _ in dys]), _arr(C.c_int64, [ld for _, _, ld in dys]),
+          _arr(C.c_void_p, [x.data_ptr() for x, _, _ in xs]), _arr(C.c_int64, [ld for _, _, ld in xs]),
+          _arr(C.c_void_p, [it[2].data_ptr() for it in items]),
+          _arr(C.c_int64, [it[2].stride(0) for it in items]),
+          _arr(C.c_int64, [M for _, M, _ in dys]), _arr(C.c_int64, [d.shape[-1] for d, _, _ in dys]),
+          _arr(C.c_int64, [x.shape[-1] for x, _, _ in xs]), 0, _stream())
+
+
 def _add_ln_fwd(bf16, res, x, gate, gamma, beta, relu=False):
     x2, M, ldx = _rows(x)
     d = x.shape[-1]
@@ -506,8 +564,8 @@ def block_full_op(q: Tensor, kv: Tensor, mask: Optional[Tensor], s_prev: Optiona
     # Q projection and fused [K|V] projection (one GEMM, N = 2d)
     qp = torch.empty(B, Lq, d, dtype=dt, device=dev)
     kvp = torch.empty(B, Lk, 2 * d, dtype=dt, device=dev)
-    _linear_fwd(bf16, q, _weight(bf16, wq), None, None, qp.view(-1, d))
-    _linear_fwd(bf16, kv, _weight(bf16, wk, wv), None, None, kvp.view(-1, 2 * d))
+    _linear_fwd_group(bf16, [(q, _weight(bf16, wq), None, qp.view(-1, d), False),
+                             (kv, _weight(bf16, wk, wv), None, kvp.view(-1, 2 * d), False)])
     kp, vp = kvp[..., :d], kvp[..., d:]
     o, s, stat = _attn_fwd(bf16, qp, kp, vp, mask, s_prev, gc, n_heads, emit_s)
     # output projection, gated residual + LN1
@@ -546,38 +604,42 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     _linear_bwd_x(bf16, df2, _weight(bf16, f2w), df1.view(-1, dff), relu_src=f1.view(-1, dff))
     dw_f2, r_f2 = _wgrad(f2w, d, dff)
     db_f2 = torch.zeros(d, dtype=F32, device=dev)
-    _linear_bwd_w(bf16, df2.view(-1, d), f1.view(-1, dff), dw_f2, db_f2)
+    _rowsum(bf16, df2.view(-1, d), db_f2)
     _linear_bwd_x(bf16, df1, _weight(bf16, f1w), dh1.view(-1, d), accumulate=True)
     dw_f1, r_f1 = _wgrad(f1w, dff, d)
     db_f1 = torch.zeros(dff, dtype=F32, device=dev)
-    _linear_bwd_w(bf16, df1.view(-1, dff), h1.view(-1, d), dw_f1, db_f1)
+    _rowsum(bf16, df1.view(-1, dff), db_f1)
     # LN1: h1 = LN(q + a*x)
     dq, dx, dp1 = _add_ln_bwd(bf16, dh1, q, x, ga, n1w, None, st1, False, True)
     # output projection
     do = torch.empty(B, Lq, d, dtype=dt, device=dev)
     _linear_bwd_x(bf16, dx, _weight(bf16, wo), do.view(-1, d))
     dw_o, r_o = _wgrad(wo, d, d)
-    _linear_bwd_w(bf16, dx.view(-1, d), o.view(-1, d), dw_o)
     # attention core
     dqp = torch.empty(B, Lq, d, dtype=dt, device=dev)
     dkvp = torch.empty(B, Lk, 2 * d, dtype=dt, device=dev)
     ds_prev, dc = _attn_bwd(bf16, do, qp, kvp[..., :d], kvp[..., d:], mask, s, s_prev, gc, ds_next,
                             o, stat, n_heads, dqp, dkvp[..., :d], dkvp[..., d:], need_dsprev)
     # projections: dq += dqp Wq ; dkv = dkvp [Wk;Wv]
-    _linear_bwd_x(bf16, dqp, _weight(bf16, wq), dq.view(-1, d), accumulate=True)
     dw_q, r_q = _wgrad(wq, d, d)
-    _linear_bwd_w(bf16, dqp.view(-1, d), q.view(-1, d), dw_q)
     dw_kv = _dest_pair(wk, wv)
     r_kv = torch.empty(0, device=dev)
     if dw_kv is None:
         dw_kv = r_kv = torch.empty(2 * d, d, dtype=F32, device=dev)
-    _linear_bwd_w(bf16, dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)
-    if same_qkv:
+    if same_qkv:   # both input gradients accumulate into dq: keep them ordered
+        _linear_bwd_x(bf16, dqp, _weight(bf16, wq), dq.view(-1, d), accumulate=True)
         _linear_bwd_x(bf16, dkvp, _weight(bf16, wk, wv), dq.view(-1, d), accumulate=True)
         dkv = torch.empty(0, device=dev)
     else:
         dkv = torch.empty(B, Lk, d, dtype=dt, device=dev)
-        _linear_bwd_x(bf16, dkvp, _weight(bf16, wk, wv), dkv.view(-1, d))
+        _linear_bwd_x_group(bf16, [(dqp, _weight(bf16, wq), dq.view(-1, d), True),
+                                   (dkvp, _weight(bf16, wk, wv), dkv.view(-1, d), False)])
+    # the five weight gradients of the block: one grouped launch (each alone fills < 1/4 of the GPU)
+    _linear_bwd_w_group(bf16, [(df2.view(-1, d), f1.view(-1, dff), dw_f2),
+                               (df1.view(-1, dff), h1.view(-1, d), dw_f1),
+                               (dx.view(-1, d), o.view(-1, d), dw_o),
+                               (dqp.view(-1, d), q.view(-1, d), dw_q),
+                               (dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)])
     return [dq, dkv, ds_prev if ds_prev is not None else torch.empty(0, device=dev),
             dc if dc is not None else torch.empty(0, device=dev),
             r_q, r_kv, r_o, dp1, dp2, r_f1, db_f1, r_f2, db_f2]
