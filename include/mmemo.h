@@ -179,6 +179,9 @@ int mmemo_rowsum_bf16(const void* x, int64_t ldx, float* out, int64_t M, int64_t
 /* dtype conversion of n contiguous elements (bf16 shadow copies of float32 master weights) */
 int mmemo_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mmemo_stream_t stream);
 int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_t stream);
+/* `count` <= 8 tensors in one launch (host arrays): all bf16 weight shadows of one block */
+int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const* dst,
+                                 const int64_t* n, mmemo_stream_t stream);
 /* y = x * keep/(1-p), keep ~ Bernoulli(1-p) from a counter-based RNG keyed by (seed, element).
  * Forward and backward are the same call (nn.Dropout at others/realformer.py:139,159,167,222). */
 int mmemo_dropout_f32(const void* x, void* y, int64_t n, float p, uint64_t seed,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "mmemo_rowsum_f32": _ROWSUM, "mmemo_rowsum_bf16": _ROWSUM,
     "mmemo_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mmemo_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
+    "mmemo_cast_f32_to_bf16_multi": [_i32, _vp, _vp, _vp, _vp],
     "mmemo_dropout_f32": _DROPOUT, "mmemo_dropout_bf16": _DROPOUT,
     "mmemo_pool_fwd_f32": _POOL_FWD, "mmemo_pool_fwd_bf16": _POOL_FWD,
     "mmemo_pool_bwd_f32": _POOL_BWD, "mmemo_pool_bwd_bf16": _POOL_BWD,

@@ -71,6 +71,34 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64
   if (i < n) y[i] = from_f<T>(hash_uniform(seed, (uint64_t)i) >= p ? to_f(x[i]) * scale : 0.f);
 }
 
+// several float32 tensors -> bf16 in ONE launch (all bf16 weight shadows of a block)
+struct CastTable {
+  const float* src[8];
+  bf16* dst[8];
+  long long n[8];
+  int count;
+};
+__global__ void __launch_bounds__(256) cast_multi_kernel(CastTable t) {
+  const int which = blockIdx.y;
+  if (which >= t.count) return;
+  const float* __restrict__ s = t.src[which];
+  bf16* __restrict__ d = t.dst[which];
+  const long long n = t.n[which];
+  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4; i < n;
+       i += (long long)gridDim.x * 1024) {
+    if (i + 3 < n) {
+      const float4 v = *reinterpret_cast<const float4*>(s + i);
+      __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(d + i) = o;
+    } else {
+      for (long long j = i; j < n; ++j) d[j] = __float2bfloat16_rn(s[j]);
+    }
+  }
+}
+
 template <typename T>
 int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
            cudaStream_t st) {
@@ -118,6 +146,30 @@ int mmemo_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mmemo_stream_
   MM_REQUIRE(src && dst);
   cast_f2b_kernel<<<(unsigned)cdiv(cdiv(n, 4), 256), 256, 0, mm_stream(s)>>>(
       src, static_cast<bf16*>(dst), n);
+  MM_LAUNCH_OK();
+  return MMEMO_OK;
+}
+int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const* dst,
+                                 const int64_t* n, mmemo_stream_t s) {
+  if (count <= 0) return MMEMO_OK;
+  if (count > 8) return MMEMO_ERR_ARG;
+  CastTable t = {};
+  t.count = count;
+  int64_t nmax = 0;
+  for (int i = 0; i < count; ++i) {
+    MM_REQUIRE(src[i] && dst[i] && n[i] >= 0);
+    // 16-byte aligned sources / 8-byte aligned destinations (vector accesses)
+    MM_REQUIRE((reinterpret_cast<uintptr_t>(src[i]) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(dst[i]) & 7) == 0);
+    t.src[i] = src[i];
+    t.dst[i] = static_cast<bf16*>(dst[i]);
+    t.n[i] = n[i];
+    nmax = n[i] > nmax ? n[i] : nmax;
+  }
+  int64_t bx = cdiv(cdiv(nmax, 4), 256);
+  if (bx > 148) bx = 148;
+  if (bx < 1) bx = 1;
+  cast_multi_kernel<<<dim3((unsigned)bx, (unsigned)count), 256, 0, mm_stream(s)>>>(t);
   MM_LAUNCH_OK();
   return MMEMO_OK;
 }

@@ -134,6 +134,37 @@ def shadow_bf16(*ws: Tensor) -> Tensor:
     return out
 
 
+def shadow_bf16_block(groups: Sequence[Sequence[Tensor]]) -> List[Tensor]:
+    """bf16 shadows of several weight groups (each group = weights concatenated along dim 0) with
+    ONE cast launch; also fills the per-group cache used by ``shadow_bf16``."""
+    keys = [tuple((w.data_ptr(), w._version, tuple(w.shape)) for w in g) for g in groups]
+    if all(k in _shadow for k in keys):
+        return [_shadow[k] for k in keys]
+    flat = [w for g in groups for w in g]
+    if len(flat) > 8:
+        return [shadow_bf16(*g) for g in groups]
+    outs, srcs, dsts, ns = [], [], [], []
+    for g, k in zip(groups, keys):
+        ptrs = {e[0] for e in k}
+        for old in [o for o in _shadow if any(e[0] in ptrs for e in o) and len(o) == len(k)]:
+            del _shadow[old]
+        rows = sum(w.shape[0] for w in g)
+        out = torch.empty(rows, g[0].numel() // g[0].shape[0], dtype=BF, device=g[0].device)
+        r = 0
+        for w in g:
+            wd = w.detach()
+            wd = wd if wd.is_contiguous() else wd.contiguous()
+            srcs.append(wd)
+            dsts.append(out[r:].data_ptr())
+            ns.append(wd.numel())
+            r += w.shape[0]
+        _shadow[k] = out
+        outs.append(out)
+    _call("mmemo_cast_f32_to_bf16_multi", len(srcs), _arr(C.c_void_p, [t.data_ptr() for t in srcs]),
+          _arr(C.c_void_p, dsts), _arr(C.c_int64, ns), _stream())
+    return outs
+
+
 def _weight(bf16: bool, *ws: Tensor) -> Tensor:
     if bf16:
         return shadow_bf16(*ws)
@@ -304,7 +335,7 @@ def _add_ln_fwd(bf16, res, x, gate, gamma, beta, relu=False):
     return y, stat
 
 
-def _add_ln_bwd(bf16, dy, res, x, gate, gamma, y, stat, relu, want_dres, dres_out=None):
+def _add_ln_bwd(bf16, dy, res, x, gate, gamma, y, stat, relu, want_dres, dres_out=None, dpar=None):
     """Returns (dres, dx, dparams) with dparams = float32 [1 + 2d] = (dgate | dgamma | dbeta)."""
     dy, M, lddy = _rows(dy)
     x2, _, ldx = _rows(x)
@@ -317,7 +348,8 @@ def _add_ln_bwd(bf16, dy, res, x, gate, gamma, y, stat, relu, want_dres, dres_ou
     if want_dres:
         dres = dres_out if dres_out is not None else torch.empty(x.shape, dtype=x.dtype,
                                                                  device=x.device)
-    dpar = torch.zeros(1 + 2 * d, dtype=F32, device=x.device)
+    if dpar is None:
+        dpar = torch.zeros(1 + 2 * d, dtype=F32, device=x.device)
     _call(f"mmemo_add_ln_bwd_{_sfx(bf16)}", dy.data_ptr(), lddy, _p(res), ldres, x2.data_ptr(),
           ldx, _p(gate), gamma.data_ptr(), _p(y) if relu else None, d, stat[0].data_ptr(),
           stat[1].data_ptr(), _p(dres), d, dx.data_ptr(), d, dpar.data_ptr(),
@@ -561,6 +593,8 @@ def block_full_op(q: Tensor, kv: Tensor, mask: Optional[Tensor], s_prev: Optiona
     dt, dev = _act_dtype(bf16), q.device
     q = q.contiguous()
     kv = q if same_qkv else kv.contiguous()
+    if bf16:   # all bf16 weight shadows of the block in one cast launch
+        shadow_bf16_block([[wq], [wk, wv], [wo], [f1w], [f2w]])
     # Q projection and fused [K|V] projection (one GEMM, N = 2d)
     qp = torch.empty(B, Lq, d, dtype=dt, device=dev)
     kvp = torch.empty(B, Lk, 2 * d, dtype=dt, device=dev)
@@ -597,20 +631,24 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     q = q.contiguous()
     kv = q if same_qkv else kv.contiguous()
     dh2 = dh2.contiguous()
+    # one zero-filled buffer for every "+=" output of the block (LN params, biases, dc)
+    zbuf = torch.zeros(2 * (1 + 2 * d) + d + dff + 32, dtype=F32, device=dev)
+    z_dp2, z_dp1 = zbuf[:1 + 2 * d], zbuf[1 + 2 * d:2 * (1 + 2 * d)]
+    zo = 2 * (1 + 2 * d)
     # LN2: h2 = LN(h1 + b*f2)
-    dh1, df2, dp2 = _add_ln_bwd(bf16, dh2, h1, f2, gb, n2w, None, st2, False, True)
+    dh1, df2, dp2 = _add_ln_bwd(bf16, dh2, h1, f2, gb, n2w, None, st2, False, True, dpar=z_dp2)
     # FFN backward; df1 = (df2 W2) * (f1 > 0) fused in the GEMM epilogue
     df1 = torch.empty(B, Lq, dff, dtype=dt, device=dev)
     _linear_bwd_x(bf16, df2, _weight(bf16, f2w), df1.view(-1, dff), relu_src=f1.view(-1, dff))
     dw_f2, r_f2 = _wgrad(f2w, d, dff)
-    db_f2 = torch.zeros(d, dtype=F32, device=dev)
+    db_f2 = zbuf[zo:zo + d]
     _rowsum(bf16, df2.view(-1, d), db_f2)
     _linear_bwd_x(bf16, df1, _weight(bf16, f1w), dh1.view(-1, d), accumulate=True)
     dw_f1, r_f1 = _wgrad(f1w, dff, d)
-    db_f1 = torch.zeros(dff, dtype=F32, device=dev)
+    db_f1 = zbuf[zo + d:zo + d + dff]
     _rowsum(bf16, df1.view(-1, dff), db_f1)
     # LN1: h1 = LN(q + a*x)
-    dq, dx, dp1 = _add_ln_bwd(bf16, dh1, q, x, ga, n1w, None, st1, False, True)
+    dq, dx, dp1 = _add_ln_bwd(bf16, dh1, q, x, ga, n1w, None, st1, False, True, dpar=z_dp1)
     # output projection
     do = torch.empty(B, Lq, d, dtype=dt, device=dev)
     _linear_bwd_x(bf16, dx, _weight(bf16, wo), do.view(-1, d))
@@ -642,7 +680,7 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
                                (dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)])
     return [dq, dkv, ds_prev if ds_prev is not None else torch.empty(0, device=dev),
             dc if dc is not None else torch.empty(0, device=dev),
-            r_q, r_kv, r_o, dp1, dp2, r_f1, db_f1, r_f2, db_f2]
+            r_q, r_kv, r_o, zbuf, r_f1, r_f2]
 
 
 def _block_full_setup(ctx, inputs, output):
@@ -663,9 +701,14 @@ def _block_full_backward(ctx, grads):
         dh2 = torch.zeros_like(q)
     d = q.shape[-1]
     need_dsprev = s_prev is not None and ctx.needs_input_grad[3]
-    (dq, dkv, ds_prev, dc, dw_q, dw_kv, dw_o, dp1, dp2, dw_f1, db_f1, dw_f2,
-     db_f2) = block_full_bwd_op(dh2, ds_next, q, kv, mask, s_prev, s, saved, params, H, bf16,
+    (dq, dkv, ds_prev, dc, dw_q, dw_kv, dw_o, zbuf, dw_f1,
+     dw_f2) = block_full_bwd_op(dh2, ds_next, q, kv, mask, s_prev, s, saved, params, H, bf16,
                                 same_qkv, need_dsprev)
+    # the small "+=" outputs share one zero-initialised buffer: [dp2 | dp1 | db_f2 | db_f1]
+    dff = params[8].shape[0]
+    dp2, dp1 = zbuf[:1 + 2 * d], zbuf[1 + 2 * d:2 * (1 + 2 * d)]
+    zo = 2 * (1 + 2 * d)
+    db_f2, db_f1 = zbuf[zo:zo + d], zbuf[zo + d:zo + d + dff]
     has_prev = s_prev is not None
     # weight gradients written straight into DP bucket slots come back as empty placeholders
     wq, wk, wv, wo, f1w, f2w = params[0], params[1], params[2], params[3], params[8], params[10]
