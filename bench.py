@@ -342,9 +342,11 @@ def main():
     reducer = None
     if world > 1:   # knobs for experiments; the defaults are the product configuration
         reducer = mdp.GradReducer(
-            model, world, bucket_bytes=int(float(os.environ.get("MMEMO_BUCKET_MB", "8")) * (1 << 20)),
+            model, world, bucket_bytes=int(float(os.environ.get("MMEMO_BUCKET_MB", "16")) * (1 << 20)),
             zero_copy=os.environ.get("MMEMO_ZERO_COPY", "1") == "1",
-            sm_reserve=int(os.environ.get("MMEMO_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "16"))))
+            sm_reserve=int(os.environ.get("MMEMO_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "16"))),
+            transport=os.environ.get("MMEMO_DP_TRANSPORT", "auto"),
+            comm_blocks=int(os.environ.get("MMEMO_COMM_BLOCKS", "16")))
 
     def step():
         model.zero_grad(set_to_none=True)

@@ -241,6 +241,22 @@ int mmemo_rdrop_kl_fwd(const float* logits, float* out, int64_t B, int64_t C,
 int mmemo_rdrop_kl_bwd(const float* dout, const float* logits, float* dlogits, int64_t B, int64_t C,
                        mmemo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (new; the reference is single-GPU, others/realformer.py:16).
+ * Two-shot SUM all-reduce, in place, of n_elems float32 starting offset_elems into a buffer that
+ * every rank allocated symmetrically (same size; peer mappings exchanged by the host).
+ *   multicast_ptr       : NVLS multicast mapping of the buffer, or NULL -> plain peer loads/stores
+ *   buffer_ptrs_dev     : device array [world] of the ranks' mappings of the buffer
+ *   signal_pad_ptrs_dev : device array [world] of the ranks' uint32 flag pads (zero-initialised);
+ *                         slots [signal_slot_base, signal_slot_base + blocks*world) are used
+ * n_elems must be a multiple of 4*world, offset_elems of 4.  Every rank must launch the same
+ * sequence of calls.  A rank that waits > 20 s for a peer traps instead of hanging.
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_allreduce_sum_f32(void* multicast_ptr, void* const* buffer_ptrs_dev,
+                            void* const* signal_pad_ptrs_dev, int64_t signal_slot_base,
+                            int64_t offset_elems, int64_t n_elems, int rank, int world, int blocks,
+                            mmemo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mmemo_circle_loss_bwd": [_vp, _vp, _vp, _vp, _i64, _i64, _vp],
     "mmemo_rdrop_kl_fwd": [_vp, _vp, _i64, _i64, _vp],
     "mmemo_rdrop_kl_bwd": [_vp, _vp, _vp, _i64, _i64, _vp],
+    "mmemo_allreduce_sum_f32": [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp],
 }
 
 _lib = None

@@ -14,6 +14,14 @@ ranks).  A post-accumulate hook copies each gradient into its bucket slot and re
 it on its own stream, so it overlaps the rest of backward, also under CUDA-graph capture).
 ``finish()`` joins the collectives.  The loss is pre-scaled by 1/world so a SUM reduction yields
 the average (gloo has no AVG).
+
+Transport: on CUDA the buckets are carved out of ONE symmetric-memory allocation
+(``torch.distributed._symmetric_memory``: same layout on every rank, peer and NVLS multicast
+mappings) and reduced by libmmemo's own two-shot kernel (csrc/allreduce.cu) on a side stream:
+``multimem.ld_reduce`` lets the NVSwitch sum a slice across all replicas, ``multimem.st``
+broadcasts it back.  The kernel uses no shared memory and a handful of CTAs, so it co-resides
+with the persistent GEMM CTAs of backward instead of taking SMs from them the way NCCL's
+kernels do.  ``transport="nccl"`` (and every CPU/gloo run) uses ``dist.all_reduce`` per bucket.
 """
 from __future__ import annotations
 
@@ -48,16 +56,26 @@ def shard_batch(batch, rank: int, world: int, align: int = 1):
 
 
 class _Bucket:
-    __slots__ = ("flat", "params", "offsets", "pending", "work", "todo")
+    __slots__ = ("flat", "params", "offsets", "pending", "work", "todo", "base")
 
-    def __init__(self, params: Sequence[torch.nn.Parameter]):
-        self.params = list(params)
-        self.offsets, n = [], 0
-        for p in self.params:
-            self.offsets.append(n)
+    ALIGN = 1024        # bucket length granularity: 4 floats x up to 16 ranks x 16
+
+    @classmethod
+    def layout(cls, params: Sequence[torch.nn.Parameter]):
+        offsets, n = [], 0
+        for p in params:
+            offsets.append(n)
             n += (p.numel() + 31) // 32 * 32          # 128-byte aligned slots
+        return offsets, (n + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], flat: Optional[torch.Tensor] = None,
+                 base: int = 0):
+        self.params = list(params)
+        self.offsets, n = self.layout(self.params)
         p0 = self.params[0]
-        self.flat = torch.zeros(n, dtype=torch.float32, device=p0.device)
+        self.flat = (torch.zeros(n, dtype=torch.float32, device=p0.device) if flat is None
+                     else flat[base:base + n])
+        self.base = base    # offset of this bucket inside the shared symmetric buffer
         self.pending = len(self.params)
         self.work = None
         self.todo = []      # (parameter, slot view) pairs whose gradient still has to be copied in
@@ -65,8 +83,9 @@ class _Bucket:
 
 class GradReducer:
     def __init__(self, model: torch.nn.Module, world_size: Optional[int] = None,
-                 bucket_bytes: int = 8 << 20, group=None, zero_copy: bool = True,
-                 sm_reserve: int = 16, reserve_launches: int = 5):
+                 bucket_bytes: int = 16 << 20, group=None, zero_copy: bool = True,
+                 sm_reserve: int = 16, reserve_launches: int = 5, transport: str = "auto",
+                 comm_blocks: int = 16):
         self.model = model
         self.group = group
         self.world = world_size if world_size is not None else dist.get_world_size(group)
@@ -76,7 +95,14 @@ class GradReducer:
         self.buckets: List[_Bucket] = []
         # SMs left to the NCCL kernel of a bucket for the next `reserve_launches` GEMM launches after
         # the all-reduce is issued (set sm_reserve to NCCL_MAX_CTAS; 0 disables)
-        self.sm_reserve = sm_reserve if next(model.parameters()).is_cuda else 0
+        on_cuda = next(model.parameters()).is_cuda
+        if transport not in ("auto", "nccl", "symm"):
+            raise ValueError(f"unknown transport {transport!r}")
+        # "auto": libmmemo's symmetric-memory all-reduce on CUDA, the process group's otherwise
+        self.transport = "nccl" if (transport == "nccl" or not on_cuda) else "symm"
+        self.comm_blocks = comm_blocks
+        self._symm = None           # (handle, comm stream) once the buckets are built
+        self.sm_reserve = sm_reserve if (on_cuda and self.transport == "nccl") else 0
         self.reserve_launches = reserve_launches
         self._slot: Dict[torch.nn.Parameter, tuple] = {}
         self._order: List[torch.nn.Parameter] = []
@@ -87,15 +113,20 @@ class GradReducer:
     # -- bucket construction ---------------------------------------------------------------
     def _build(self) -> None:
         """Pack the parameters that received a gradient, in readiness order, into buckets."""
-        cur, size = [], 0
+        groups, cur, size = [], [], 0
         for p in self._order:
             cur.append(p)
             size += p.numel() * 4
             if size >= self.bucket_bytes:
-                self.buckets.append(_Bucket(cur))
+                groups.append(cur)
                 cur, size = [], 0
         if cur:
-            self.buckets.append(_Bucket(cur))
+            groups.append(cur)
+        flat, bases = None, [0] * len(groups)
+        if self.transport == "symm" and groups:
+            flat, bases = self._alloc_symmetric([_Bucket.layout(g)[1] for g in groups],
+                                                groups[0][0].device)
+        self.buckets = [_Bucket(g, flat, base) for g, base in zip(groups, bases)]
         for bi, b in enumerate(self.buckets):
             for p, off in zip(b.params, b.offsets):
                 self._slot[p] = (bi, off)
@@ -104,6 +135,42 @@ class GradReducer:
                     from . import ops
                     ops.register_grad_dest(p, b.flat, off)
         self._built = True
+
+    def _alloc_symmetric(self, sizes: List[int], device):
+        """One symmetric allocation for all buckets + rendezvous (collective, first step only)."""
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        bases, total = [], 0
+        for n in sizes:
+            bases.append(total)
+            total += n
+        flat = symm_mem.empty(total, dtype=torch.float32, device=device)
+        flat.zero_()
+        handle = symm_mem.rendezvous(flat, group)
+        if handle.world_size != self.world:
+            raise RuntimeError("symmetric-memory group size does not match the reducer's world size")
+        # our flag slots live in the upper half of the signal pad (torch's own barriers use the
+        # lower part); one slot per (block, peer)
+        self._slot_base = handle.signal_pad_size // 8
+        if (self._slot_base + self.comm_blocks * self.world) * 4 > handle.signal_pad_size:
+            raise RuntimeError("signal pad too small for comm_blocks x world flags")
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+        self._symm = (handle, torch.cuda.Stream(device=device))
+        return flat, bases
+
+    def _launch_symm(self, b: _Bucket) -> None:
+        """Issue the in-place all-reduce of one bucket on the side stream."""
+        from . import ops
+        handle, comm = self._symm
+        comm.wait_stream(torch.cuda.current_stream())
+        ops._call("mmemo_allreduce_sum_f32", handle.multicast_ptr or None, handle.buffer_ptrs_dev,
+                  handle.signal_pad_ptrs_dev, self._slot_base, b.base, b.flat.numel(), handle.rank,
+                  self.world, self.comm_blocks, comm.cuda_stream)
+
+    @property
+    def uses_multicast(self) -> bool:
+        return self._symm is not None and bool(self._symm[0].multicast_ptr)
 
     def bucket_layout(self) -> List[List[int]]:
         """[[numel, ...] per bucket] — identical on every rank (asserted by the tests)."""
@@ -132,7 +199,11 @@ class GradReducer:
                 for q, v in b.todo:
                     q.grad = v
                 b.todo = []
-            if not _NO_COMM:
+            if _NO_COMM:
+                return
+            if self._symm is not None:
+                self._launch_symm(b)
+            else:
                 b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group,
                                          async_op=True)
                 if self.sm_reserve:
@@ -170,7 +241,12 @@ class GradReducer:
                     view = b.flat[off:off + p.numel()].view_as(p)
                     view.copy_(p.grad)
                     p.grad = view
-                dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group)
+                if self._symm is not None:
+                    self._launch_symm(b)
+                else:
+                    dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self._symm is not None:
+                torch.cuda.current_stream().wait_stream(self._symm[1])
             return
         if self.sm_reserve:
             from . import ops
@@ -182,6 +258,8 @@ class GradReducer:
             if b.work is not None:
                 b.work.wait()
                 b.work = None
+        if self._symm is not None:
+            torch.cuda.current_stream().wait_stream(self._symm[1])
 
     def remove(self) -> None:
         for h in self._hooks:

@@ -1,0 +1,131 @@
+"""GPU tests of the data-parallel gradient exchange: libmmemo's symmetric-memory all-reduce kernel
+(csrc/allreduce.cu, NVLS multicast and plain peer path) and GradReducer on top of it.  The
+single-GPU cases run a world of one; the two-rank cases need two GPUs and skip otherwise."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed._symmetric_memory as symm_mem
+
+    from mmemo_b200 import ops
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        n = 1024 * 300
+        flat = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        h = symm_mem.rendezvous(flat, dist.group.WORLD)
+        src = torch.randn(n, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+        ref = src.clone()
+        dist.all_reduce(ref)
+        out = {"multicast": bool(h.multicast_ptr)}
+        for name, mc in (("nvls", h.multicast_ptr), ("peer", 0)):
+            if name == "nvls" and not mc:
+                continue
+            flat.copy_(src)
+            torch.cuda.synchronize()
+            dist.barrier()
+            off, cnt = 2048, 1024 * 200
+            ops._call("mmemo_allreduce_sum_f32", mc or None, h.buffer_ptrs_dev,
+                      h.signal_pad_ptrs_dev, h.signal_pad_size // 8, off, cnt, rank, world, 4,
+                      torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            dist.barrier()
+            out[name] = (
+                float((flat[off:off + cnt] - ref[off:off + cnt]).abs().max()),
+                bool(torch.equal(flat[:off], src[:off])
+                     and torch.equal(flat[off + cnt:], src[off + cnt:])))
+        q.put((rank, out))
+        dist.barrier()
+        torch.cuda.synchronize()
+    except Exception as ex:  # pragma: no cover
+        q.put((rank, repr(ex)))
+    os._exit(0)
+
+
+def _reducer_worker(rank, world, port, q):
+    from mmemo_b200 import dp, synth
+    from mmemo_b200.encoder import ResidualEncoder
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        torch.manual_seed(0)
+        model = ResidualEncoder(64, 4, 2)
+        model.load_state_dict(synth.randomize_gates(model.state_dict(), seed=3))
+        model = model.to(dev)
+        batch = synth.encoder_batch(seed=11, B=8, L=16, d=64)
+        x, mask, dy = batch["x"], batch["mask"], batch["dy"]
+        sl = dp.shard_bounds(8, rank, world)
+        grads = {}
+        for transport in ("nccl", "symm"):
+            red = dp.GradReducer(model, world, bucket_bytes=64 << 10, transport=transport)
+            for _ in range(3):                      # first step builds the buckets, then overlapped
+                model.zero_grad(set_to_none=True)
+                out = model(x[sl].to(dev), mask[sl].to(dev))
+                red.backward((out * dy[sl].to(dev)).mean())
+            torch.cuda.synchronize()
+            grads[transport] = {k: p.grad.detach().cpu().clone()
+                                for k, p in model.named_parameters() if p.grad is not None}
+            red.remove()
+        worst = max(float((grads["nccl"][k] - grads["symm"][k]).abs().max()
+                          / grads["nccl"][k].abs().max().clamp_min(1e-20)) for k in grads["nccl"])
+        q.put((rank, worst))
+        dist.barrier()
+        torch.cuda.synchronize()
+    except Exception as ex:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    os._exit(0)
+
+
+def _run(worker, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    return res
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_symmetric_allreduce_kernel(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    res = _run(_allreduce_worker, world)
+    for rank, out in res.items():
+        assert isinstance(out, dict), out
+        for name in ("nvls", "peer"):
+            if name in out:
+                err, untouched = out[name]
+                assert err <= 1e-5, (rank, name, err)
+                assert untouched, (rank, name)
+
+
+def test_grad_reducer_symm_matches_nccl():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _run(_reducer_worker, 2)
+    for rank, worst in res.items():
+        assert isinstance(worst, float), worst
+        assert worst <= 1e-5, (rank, worst)
