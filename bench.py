@@ -145,7 +145,7 @@ def _algorithmic(name: str, a: tuple):
         M, d = a[11], a[12]
         return 8 * M * d, e * M * d * (3 if a[0] else 2), f"{M}x{d}"
     if name.startswith("mmemo_add_ln_bwd"):
-        M, d = a[19], a[20]
+        M, d = a[20], a[21]
         return 16 * M * d, e * M * d * (3 + (2 if a[2] else 0)), f"{M}x{d}"
     if name.startswith("mmemo_cast"):
         return 0, 6 * a[2], f"{a[2]}"

@@ -147,7 +147,8 @@ int mmemo_resattn_uses_tensor_cores(int64_t Lq, int64_t Lk, int64_t hd, int64_t 
  * Gated residual + LayerNorm (+ReLU).  y = act( LN( res + gate * x ) * gamma + beta ), eps 1e-5.
  * Replaces others/realformer.py:207-208,263  cmu-mosei/run.py:261  Ren-MME/run.py:166,213
  * robot_demo.py:372-373.  res == null -> LN(gate*x); gate == null -> 1.  mean/rstd (M) saved.
- * bwd: dres (nullable) and dx written; dgate, dgamma, dbeta are "+=" float32.
+ * bwd: dres (nullable) and dx written; dgate, dgamma, dbeta are "+=" float32; dxsum (nullable,
+ * "+=" float32 [d]) receives sum_m dx[m,:], the bias gradient of the Linear that produced x.
  * ------------------------------------------------------------------------------------------- */
 int mmemo_add_ln_fwd_f32(const void* res, int64_t ldres, const void* x, int64_t ldx,
                          const float* gate, const float* gamma, const float* beta, void* y,
@@ -161,14 +162,14 @@ int mmemo_add_ln_bwd_f32(const void* dy, int64_t lddy, const void* res, int64_t 
                          const void* x, int64_t ldx, const float* gate, const float* gamma,
                          const void* y, int64_t ldy, const float* mean, const float* rstd,
                          void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgate,
-                         float* dgamma, float* dbeta, int64_t M, int64_t d, int relu,
-                         mmemo_stream_t stream);
+                         float* dgamma, float* dbeta, float* dxsum, int64_t M, int64_t d,
+                         int relu, mmemo_stream_t stream);
 int mmemo_add_ln_bwd_bf16(const void* dy, int64_t lddy, const void* res, int64_t ldres,
                           const void* x, int64_t ldx, const float* gate, const float* gamma,
                           const void* y, int64_t ldy, const float* mean, const float* rstd,
                           void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgate,
-                          float* dgamma, float* dbeta, int64_t M, int64_t d, int relu,
-                          mmemo_stream_t stream);
+                          float* dgamma, float* dbeta, float* dxsum, int64_t M, int64_t d,
+                          int relu, mmemo_stream_t stream);
 
 /* out[m % period, n] += x[m, n]  (float32 out).  Bias gradients (period 1) and position-table
  * gradients (period L; backward of others/realformer.py:225-227). */

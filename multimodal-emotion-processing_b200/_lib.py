@@ -24,7 +24,7 @@ _ATTN_BWD = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _vp, _
              _i64, _vp]
 _LN_FWD = [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _f32, _i32, _vp]
 _LN_BWD = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64,
-           _vp, _vp, _vp, _i64, _i64, _i32, _vp]
+           _vp, _vp, _vp, _vp, _i64, _i64, _i32, _vp]
 _ROWSUM = [_vp, _i64, _vp, _i64, _i64, _i64, _vp]
 _POOL_FWD = [_vp, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp]
 _POOL_BWD = [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp]

@@ -3,7 +3,8 @@
 //
 // HBM-bound kernels (fwd: read res,x, write y; bwd: read dy,res,x, write dres,dx).  One warp per
 // row, the row lives in registers, 16-byte vector loads/stores (8 bf16 / 4 fp32 per lane per
-// access), statistics by warp shuffles with a two-pass variance.  The backward is split in two so
+// access), statistics by warp shuffles with a two-pass variance.  The backward is a single pass
+// (ln_bwd_fused_vec) while a lane owns <= 16 columns (d <= 512); wider rows are split in two so
 // that neither part needs many registers:
 //   * row kernel   : dz -> dres, dx (+ one atomic per CTA for dgate)
 //   * column kernel: dgamma[c] = sum_m dy*xhat, dbeta[c] = sum_m dy — lanes own column pairs, warps
@@ -210,6 +211,131 @@ ln_bwd_row_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res
   }
 }
 
+// Single-pass backward (vector path): one read of dy/res/x, dres/dx written once, and the column
+// sums (dgamma, dbeta and optionally dxsum = sum_m dx[m,:], the bias gradient of the layer that
+// produced x) accumulated per lane in registers over the warp's rows, then reduced through shared
+// memory and added to global memory once per CTA.
+constexpr int LNB_WARPS = 16;
+
+template <typename T, int NCH, bool DXSUM>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
+ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
+                 const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+                 const float* __restrict__ gamma, const T* __restrict__ y, int64_t ldy,
+                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                 T* __restrict__ dres, int64_t lddres, T* __restrict__ dx, int64_t lddx,
+                 float* __restrict__ dgate, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                 float* __restrict__ dxsum, int64_t M, int d, int relu) {
+  constexpr int V = Vec<T>::N;
+  extern __shared__ __align__(16) float ln_sm[];   // gamma [d] | staging [LNB_WARPS][d]
+  float* sg = ln_sm;
+  float* stage = ln_sm + d;
+  __shared__ float dgs[LNB_WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < d; i += LNB_WARPS * 32) sg[i] = gamma[i];
+  __syncthreads();
+  const float g = gate ? gate[0] : 1.f;
+  const int nchunk = d / V;
+  float dg = 0.f;
+  float accg[NCH][V], accb[NCH][V], accx[DXSUM ? NCH : 1][V];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      accg[i][j] = 0.f;
+      accb[i][j] = 0.f;
+      if (DXSUM) accx[i][j] = 0.f;
+    }
+  for (int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp; row < M;
+       row += (int64_t)gridDim.x * LNB_WARPS) {
+    const float mean = mean_in[row], rstd = rstd_in[row];
+    float xh[NCH][V], dv[NCH][V], xv[NCH][V];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        float rv[V];
+        Vec<T>::load(x + row * ldx + c * V, xv[i]);
+        Vec<T>::load(dy + row * lddy + c * V, dv[i]);
+        if (res) Vec<T>::load(res + row * ldres + c * V, rv);
+        if (relu) {
+          float yv[V];
+          Vec<T>::load(y + row * ldy + c * V, yv);
+#pragma unroll
+          for (int j = 0; j < V; ++j)
+            if (!(yv[j] > 0.f)) dv[i][j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          const float zz = g * xv[i][j] + (res ? rv[j] : 0.f);
+          xh[i][j] = (zz - mean) * rstd;
+          const float w = dv[i][j] * sg[c * V + j];
+          s1 += w;
+          s2 = fmaf(w, xh[i][j], s2);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)d;
+    s2 = warp_sum(s2) / (float)d;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        float dz[V], gx[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+          dz[j] = rstd * (dv[i][j] * sg[c * V + j] - s1 - xh[i][j] * s2);
+          gx[j] = g * dz[j];
+          dg = fmaf(dz[j], xv[i][j], dg);
+          accg[i][j] = fmaf(dv[i][j], xh[i][j], accg[i][j]);
+          accb[i][j] += dv[i][j];
+          if (DXSUM) accx[i][j] += gx[j];
+        }
+        if (dres) Vec<T>::store(dres + row * lddres + c * V, dz);
+        Vec<T>::store(dx + row * lddx + c * V, gx);
+      }
+    }
+  }
+  // column partials: registers -> shared [warp][column] -> one sum per column -> one global atomic
+  // per column per CTA; the three quantities take turns in the same staging buffer
+  if (dgate && gate) {
+    dg = warp_sum(dg);
+    if (lane == 0) dgs[warp] = dg;
+  }
+#pragma unroll
+  for (int q = 0; q < (DXSUM ? 3 : 2); ++q) {
+    float* out = q == 0 ? dgamma : (q == 1 ? dbeta : dxsum);
+    if (q) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        float* dst = stage + warp * d + c * V;
+#pragma unroll
+        for (int j = 0; j < V; j += 4) {
+          const float* a = q == 0 ? &accg[i][j] : (q == 1 ? &accb[i][j] : &accx[DXSUM ? i : 0][j]);
+          *reinterpret_cast<float4*>(dst + j) = make_float4(a[0], a[1], a[2], a[3]);
+        }
+      }
+    }
+    __syncthreads();
+    if (out)
+      for (int c = threadIdx.x; c < d; c += LNB_WARPS * 32) {
+        float t = 0.f;
+#pragma unroll
+        for (int w2 = 0; w2 < LNB_WARPS; ++w2) t += stage[w2 * d + c];
+        atomicAdd(out + c, t);
+      }
+  }
+  if (dgate && gate && threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < LNB_WARPS; ++w2) t += dgs[w2];
+    atomicAdd(dgate, t);
+  }
+}
+
 // dgamma / dbeta: CTA = (64 columns, strip of rows); lane owns 2 adjacent columns
 template <typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32)
@@ -410,7 +536,8 @@ template <typename T>
 int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void* x, int64_t ldx,
         const float* gate, const float* gamma, const void* y, int64_t ldy, const float* mean,
         const float* rstd, void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgate,
-        float* dgamma, float* dbeta, int64_t M, int64_t d, int relu, cudaStream_t st) {
+        float* dgamma, float* dbeta, float* dxsum, int64_t M, int64_t d, int relu,
+        cudaStream_t st) {
   if (M <= 0) return MMEMO_OK;
   MM_REQUIRE(dy && x && gamma && mean && rstd && dx && d > 0 && (!relu || y));
   if (d > 1024) return MMEMO_ERR_SHAPE;
@@ -429,6 +556,31 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
                    (!relu || ldy % V == 0) && al16(dy) && al16(x) && al16(dx) &&
                    (!res || al16(res)) && (!dres || al16(dres)) && (!relu || al16(y)) &&
                    al16(gamma) && d / V <= 256;
+  if (vec && (dgamma || dbeta || dxsum) && cdiv(d / V, 32) * V <= 16) {
+    // single pass (<= 16 columns per lane keep the accumulators in registers): one persistent
+    // 16-warp CTA per SM
+    int64_t g1 = cdiv(M, LNB_WARPS);
+    if (g1 > 148) g1 = 148;
+    const int nch = (int)cdiv(d / V, 32);
+    const size_t sm_bytes = (1 + LNB_WARPS) * (size_t)d * sizeof(float);   // <= 34 KB
+#define MM_FUSED(NCH_)                                                                          \
+    do {                                                                                        \
+      if (dxsum)                                                                                \
+        ln_bwd_fused_vec<T, NCH_, true><<<(unsigned)g1, LNB_WARPS * 32, sm_bytes, st>>>(        \
+            dyy, lddy, r, ldres, xx, ldx, gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx,    \
+            lddx, dgate, dgamma, dbeta, dxsum, M, (int)d, relu);                                \
+      else                                                                                      \
+        ln_bwd_fused_vec<T, NCH_, false><<<(unsigned)g1, LNB_WARPS * 32, sm_bytes, st>>>(       \
+            dyy, lddy, r, ldres, xx, ldx, gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx,    \
+            lddx, dgate, dgamma, dbeta, nullptr, M, (int)d, relu);                              \
+    } while (0)
+    if (nch <= 1) MM_FUSED(1);
+    else if (nch <= 2) MM_FUSED(2);
+    else if (V == 4) MM_FUSED(4);
+#undef MM_FUSED
+    MM_LAUNCH_OK();
+    return MMEMO_OK;
+  }
 #define MM_ARGS dyy, lddy, r, ldres, xx, ldx, gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx, \
                 lddx, dgate, M, (int)d, relu
   if (vec) {
@@ -455,6 +607,9 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
         rows_per_cta);
     MM_LAUNCH_OK();
   }
+  if (dxsum)   // shapes the single-pass kernel does not take: separate column sum of dx
+    return sizeof(T) == 2 ? mmemo_rowsum_bf16(dx, lddx, dxsum, M, d, 1, st)
+                          : mmemo_rowsum_f32(dx, lddx, dxsum, M, d, 1, st);
   return MMEMO_OK;
 }
 
@@ -479,18 +634,18 @@ int mmemo_add_ln_bwd_f32(const void* dy, int64_t lddy, const void* res, int64_t 
                          const void* x, int64_t ldx, const float* gate, const float* gamma,
                          const void* y, int64_t ldy, const float* mean, const float* rstd,
                          void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgate,
-                         float* dgamma, float* dbeta, int64_t M, int64_t d, int relu,
-                         mmemo_stream_t s) {
+                         float* dgamma, float* dbeta, float* dxsum, int64_t M, int64_t d,
+                         int relu, mmemo_stream_t s) {
   return bwd<float>(dy, lddy, res, ldres, x, ldx, gate, gamma, y, ldy, mean, rstd, dres, lddres,
-                    dx, lddx, dgate, dgamma, dbeta, M, d, relu, mm_stream(s));
+                    dx, lddx, dgate, dgamma, dbeta, dxsum, M, d, relu, mm_stream(s));
 }
 int mmemo_add_ln_bwd_bf16(const void* dy, int64_t lddy, const void* res, int64_t ldres,
                           const void* x, int64_t ldx, const float* gate, const float* gamma,
                           const void* y, int64_t ldy, const float* mean, const float* rstd,
                           void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgate,
-                          float* dgamma, float* dbeta, int64_t M, int64_t d, int relu,
-                          mmemo_stream_t s) {
+                          float* dgamma, float* dbeta, float* dxsum, int64_t M, int64_t d,
+                          int relu, mmemo_stream_t s) {
   return bwd<bf16>(dy, lddy, res, ldres, x, ldx, gate, gamma, y, ldy, mean, rstd, dres, lddres,
-                   dx, lddx, dgate, dgamma, dbeta, M, d, relu, mm_stream(s));
+                   dx, lddx, dgate, dgamma, dbeta, dxsum, M, d, relu, mm_stream(s));
 }
 }

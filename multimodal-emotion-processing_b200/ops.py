@@ -335,8 +335,10 @@ def _add_ln_fwd(bf16, res, x, gate, gamma, beta, relu=False):
     return y, stat
 
 
-def _add_ln_bwd(bf16, dy, res, x, gate, gamma, y, stat, relu, want_dres, dres_out=None, dpar=None):
-    """Returns (dres, dx, dparams) with dparams = float32 [1 + 2d] = (dgate | dgamma | dbeta)."""
+def _add_ln_bwd(bf16, dy, res, x, gate, gamma, y, stat, relu, want_dres, dres_out=None, dpar=None,
+                dxsum=None):
+    """Returns (dres, dx, dparams) with dparams = float32 [1 + 2d] = (dgate | dgamma | dbeta);
+    ``dxsum`` (float32 [d], zero-initialised by the caller) receives the column sums of dx."""
     dy, M, lddy = _rows(dy)
     x2, _, ldx = _rows(x)
     d = x.shape[-1]
@@ -353,7 +355,7 @@ def _add_ln_bwd(bf16, dy, res, x, gate, gamma, y, stat, relu, want_dres, dres_ou
     _call(f"mmemo_add_ln_bwd_{_sfx(bf16)}", dy.data_ptr(), lddy, _p(res), ldres, x2.data_ptr(),
           ldx, _p(gate), gamma.data_ptr(), _p(y) if relu else None, d, stat[0].data_ptr(),
           stat[1].data_ptr(), _p(dres), d, dx.data_ptr(), d, dpar.data_ptr(),
-          dpar[1:].data_ptr(), dpar[1 + d:].data_ptr(), M, d, int(relu), _stream())
+          dpar[1:].data_ptr(), dpar[1 + d:].data_ptr(), _p(dxsum), M, d, int(relu), _stream())
     return dres, dx, dpar
 
 
@@ -636,13 +638,14 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     z_dp2, z_dp1 = zbuf[:1 + 2 * d], zbuf[1 + 2 * d:2 * (1 + 2 * d)]
     zo = 2 * (1 + 2 * d)
     # LN2: h2 = LN(h1 + b*f2)
-    dh1, df2, dp2 = _add_ln_bwd(bf16, dh2, h1, f2, gb, n2w, None, st2, False, True, dpar=z_dp2)
+    # (the column sums of df2 = the bias gradient of the second FFN layer come out of the same pass)
+    db_f2 = zbuf[zo:zo + d]
+    dh1, df2, dp2 = _add_ln_bwd(bf16, dh2, h1, f2, gb, n2w, None, st2, False, True, dpar=z_dp2,
+                                dxsum=db_f2)
     # FFN backward; df1 = (df2 W2) * (f1 > 0) fused in the GEMM epilogue
     df1 = torch.empty(B, Lq, dff, dtype=dt, device=dev)
     _linear_bwd_x(bf16, df2, _weight(bf16, f2w), df1.view(-1, dff), relu_src=f1.view(-1, dff))
     dw_f2, r_f2 = _wgrad(f2w, d, dff)
-    db_f2 = zbuf[zo:zo + d]
-    _rowsum(bf16, df2.view(-1, d), db_f2)
     _linear_bwd_x(bf16, df1, _weight(bf16, f1w), dh1.view(-1, d), accumulate=True)
     dw_f1, r_f1 = _wgrad(f1w, dff, d)
     db_f1 = zbuf[zo + d:zo + d + dff]
