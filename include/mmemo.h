@@ -46,6 +46,10 @@ int mmemo_set_workspace(void* ptr, int64_t bytes);
  * training sets it below the SM count so that the NCCL all-reduce kernels overlapped with backward
  * have SMs of their own instead of delaying the last CTAs of a persistent grid. */
 int mmemo_set_sm_budget(int n_sms);
+/* Programmatic dependent launch for the hot kernels (tcgen05 GEMM / attention, vector LayerNorm,
+ * column sums, weight casts): the next kernel's prologue overlaps the previous kernel's drain.
+ * On by default; 0 launches every kernel fully serialised. */
+int mmemo_set_pdl(int enabled);
 /* 1 if (M,N,K,mode) is served by the tcgen05/TMA tensor-core GEMM, 0 if by the SIMT GEMM */
 int mmemo_gemm_uses_tensor_cores(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                  int64_t ldc, int mode);

@@ -25,6 +25,33 @@ void mmemo_set_error(const char* what, const char* file, int line);
   } while (0)
 
 static inline cudaStream_t mm_stream(mmemo_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch ----------------------------------------------------------
+// The hot kernels are launched with programmaticStreamSerialization: their CTAs may become
+// resident and run their prologue (smem carve-up, mbarrier init, descriptor prefetch) while the
+// previous kernel on the stream drains, and pdl_wait() then blocks until that kernel has
+// completed and its writes are visible.  Every thread of such a kernel calls pdl_wait() before
+// its first global-memory access (reads AND writes: buffers are recycled between kernels) and
+// before any early return, so completion order stays transitive along the stream.
+extern int g_mm_pdl;   // lib.cu; mmemo_set_pdl
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mm_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                    cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_mm_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---- element conversion ---------------------------------------------------------------------

@@ -115,6 +115,8 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup TMS, const __grid_constant__ Gr
     tc::tma_prefetch_desc(&TMS.b[0]);
     tc::tma_prefetch_desc(&TMS.c[0]);
   }
+  pdl_wait();
+  pdl_trigger();
   if (warp == 1) {
     if (CTA2) { tc::tmem_alloc_2sm(tmem_slot, 2 * BN); tc::tmem_relinquish_2sm(); }
     else      { tc::tmem_alloc(tmem_slot, 2 * BN); tc::tmem_relinquish(); }
@@ -591,17 +593,19 @@ int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t 
     cfg.blockDim = dim3(NTHREADS);
     cfg.dynamicSmemBytes = SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_mm_pdl ? 2 : 1;
     MM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tms, G));
   } else {
-    gemm_tc_kernel<false><<<units, NTHREADS, SMEM_BYTES, st>>>(tms, G);
-    MM_LAUNCH_OK();
+    MM_CUDA_OK(mm_launch(gemm_tc_kernel<false>, dim3((unsigned)units), dim3(NTHREADS), SMEM_BYTES,
+                         st, tms, G));
   }
   if (n == 1 && G.p[0].splits > 1 && !G.p[0].reduce_add) {
     const GemmArgs& g = gs[0];

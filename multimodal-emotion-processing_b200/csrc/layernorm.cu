@@ -19,6 +19,10 @@ constexpr int LN_WARPS = 8;
 template <typename T> struct Vec;
 template <> struct Vec<float> {
   static constexpr int N = 4;
+  __device__ static void unpack(const uint4& t, float* v) {
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y);
+    v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  }
   __device__ static void load(const float* p, float* v) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -29,6 +33,14 @@ template <> struct Vec<float> {
 };
 template <> struct Vec<bf16> {
   static constexpr int N = 8;
+  __device__ static void unpack(const uint4& t, float* v) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
   __device__ static void load(const bf16* p, float* v) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -61,6 +73,8 @@ ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, in
            int relu) {
   constexpr int V = Vec<T>::N;
   const int lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_trigger();
   const float g = gate ? gate[0] : 1.f;
   const int nchunk = d / V;
   float gm[NCH][V], bt[NCH][V];
@@ -232,6 +246,8 @@ ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ r
   float* stage = ln_sm + d;
   __shared__ float dgs[LNB_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_trigger();
   for (int i = threadIdx.x; i < d; i += LNB_WARPS * 32) sg[i] = gamma[i];
   __syncthreads();
   const float g = gate ? gate[0] : 1.f;
@@ -246,33 +262,41 @@ ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ r
       accb[i][j] = 0.f;
       if (DXSUM) accx[i][j] = 0.f;
     }
-  for (int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp; row < M;
-       row += (int64_t)gridDim.x * LNB_WARPS) {
+  // the row loop is software-pipelined: the 16-byte vectors of the next row are requested (and
+  // held packed) before the current row is reduced, so every warp keeps two rows of loads in flight
+  const int64_t rstep = (int64_t)gridDim.x * LNB_WARPS;
+  int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp;
+  uint4 cur[NCH][3], nxt[NCH][3];
+  auto fetch = [&](int64_t r, uint4 (&buf)[NCH][3]) {
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nchunk) {
+        buf[i][0] = *reinterpret_cast<const uint4*>(x + r * ldx + c * V);
+        buf[i][1] = *reinterpret_cast<const uint4*>(dy + r * lddy + c * V);
+        if (res) buf[i][2] = *reinterpret_cast<const uint4*>(res + r * ldres + c * V);
+      }
+    }
+  };
+  if (row < M) fetch(row, cur);
+  for (; row < M; row += rstep) {
+    if (row + rstep < M) fetch(row + rstep, nxt);
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[NCH][V], dv[NCH][V], xv[NCH][V];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunk) {
-        float rv[V];
-        Vec<T>::load(x + row * ldx + c * V, xv[i]);
-        Vec<T>::load(dy + row * lddy + c * V, dv[i]);
-        if (res) Vec<T>::load(res + row * ldres + c * V, rv);
-        if (relu) {
-          float yv[V];
-          Vec<T>::load(y + row * ldy + c * V, yv);
-#pragma unroll
-          for (int j = 0; j < V; ++j)
-            if (!(yv[j] > 0.f)) dv[i][j] = 0.f;
-        }
+        float xv[V], dv[V], rv[V];
+        Vec<T>::unpack(cur[i][0], xv);
+        Vec<T>::unpack(cur[i][1], dv);
+        if (res) Vec<T>::unpack(cur[i][2], rv);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          const float zz = g * xv[i][j] + (res ? rv[j] : 0.f);
-          xh[i][j] = (zz - mean) * rstd;
-          const float w = dv[i][j] * sg[c * V + j];
+          const float xh = (g * xv[j] + (res ? rv[j] : 0.f) - mean) * rstd;
+          const float w = dv[j] * sg[c * V + j];
           s1 += w;
-          s2 = fmaf(w, xh[i][j], s2);
+          s2 = fmaf(w, xh, s2);
         }
       }
     }
@@ -282,20 +306,28 @@ ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ r
     for (int i = 0; i < NCH; ++i) {
       const int c = lane + 32 * i;
       if (c < nchunk) {
-        float dz[V], gx[V];
+        float xv[V], dv[V], rv[V], dz[V], gx[V];
+        Vec<T>::unpack(cur[i][0], xv);
+        Vec<T>::unpack(cur[i][1], dv);
+        if (res) Vec<T>::unpack(cur[i][2], rv);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-          dz[j] = rstd * (dv[i][j] * sg[c * V + j] - s1 - xh[i][j] * s2);
+          const float xh = (g * xv[j] + (res ? rv[j] : 0.f) - mean) * rstd;
+          dz[j] = rstd * (dv[j] * sg[c * V + j] - s1 - xh * s2);
           gx[j] = g * dz[j];
-          dg = fmaf(dz[j], xv[i][j], dg);
-          accg[i][j] = fmaf(dv[i][j], xh[i][j], accg[i][j]);
-          accb[i][j] += dv[i][j];
+          dg = fmaf(dz[j], xv[j], dg);
+          accg[i][j] = fmaf(dv[j], xh, accg[i][j]);
+          accb[i][j] += dv[j];
           if (DXSUM) accx[i][j] += gx[j];
         }
         if (dres) Vec<T>::store(dres + row * lddres + c * V, dz);
         Vec<T>::store(dx + row * lddx + c * V, gx);
       }
     }
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cur[i][k] = nxt[i][k];
   }
   // column partials: registers -> shared [warp][column] -> one sum per column -> one global atomic
   // per column per CTA; the three quantities take turns in the same staging buffer
@@ -518,10 +550,10 @@ int fwd(const void* res, int64_t ldres, const void* x, int64_t ldx, const float*
 #define MM_ARGS r, ldres, xx, ldx, gate, gamma, beta, yy, ldy, mean, rstd, M, (int)d, eps, relu
   if (vec) {
     const int nch = (int)cdiv(d / V, 32);
-    if (nch <= 1) ln_fwd_vec<T, 1><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
-    else if (nch <= 2) ln_fwd_vec<T, 2><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
-    else if (nch <= 4) ln_fwd_vec<T, 4><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
-    else ln_fwd_vec<T, 8><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
+    if (nch <= 1) MM_CUDA_OK(mm_launch(ln_fwd_vec<T, 1>, dim3(grid), dim3(LN_WARPS * 32), 0, st, MM_ARGS));
+    else if (nch <= 2) MM_CUDA_OK(mm_launch(ln_fwd_vec<T, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, st, MM_ARGS));
+    else if (nch <= 4) MM_CUDA_OK(mm_launch(ln_fwd_vec<T, 4>, dim3(grid), dim3(LN_WARPS * 32), 0, st, MM_ARGS));
+    else MM_CUDA_OK(mm_launch(ln_fwd_vec<T, 8>, dim3(grid), dim3(LN_WARPS * 32), 0, st, MM_ARGS));
   } else {
     if (d <= 128) ln_fwd_scalar<T, 4><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
     else if (d <= 512) ln_fwd_scalar<T, 16><<<grid, LN_WARPS * 32, 0, st>>>(MM_ARGS);
@@ -556,7 +588,7 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
                    (!relu || ldy % V == 0) && al16(dy) && al16(x) && al16(dx) &&
                    (!res || al16(res)) && (!dres || al16(dres)) && (!relu || al16(y)) &&
                    al16(gamma) && d / V <= 256;
-  if (vec && (dgamma || dbeta || dxsum) && cdiv(d / V, 32) * V <= 16) {
+  if (vec && !relu && (dgamma || dbeta || dxsum) && cdiv(d / V, 32) * V <= 16) {
     // single pass (<= 16 columns per lane keep the accumulators in registers): one persistent
     // 16-warp CTA per SM
     int64_t g1 = cdiv(M, LNB_WARPS);
@@ -566,13 +598,15 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
 #define MM_FUSED(NCH_)                                                                          \
     do {                                                                                        \
       if (dxsum)                                                                                \
-        ln_bwd_fused_vec<T, NCH_, true><<<(unsigned)g1, LNB_WARPS * 32, sm_bytes, st>>>(        \
-            dyy, lddy, r, ldres, xx, ldx, gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx,    \
-            lddx, dgate, dgamma, dbeta, dxsum, M, (int)d, relu);                                \
+        MM_CUDA_OK(mm_launch(ln_bwd_fused_vec<T, NCH_, true>, dim3((unsigned)g1),                \
+                             dim3(LNB_WARPS * 32), sm_bytes, st, dyy, lddy, r, ldres, xx, ldx,  \
+                             gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx, lddx, dgate,    \
+                             dgamma, dbeta, dxsum, M, (int)d, relu));                           \
       else                                                                                      \
-        ln_bwd_fused_vec<T, NCH_, false><<<(unsigned)g1, LNB_WARPS * 32, sm_bytes, st>>>(       \
-            dyy, lddy, r, ldres, xx, ldx, gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx,    \
-            lddx, dgate, dgamma, dbeta, nullptr, M, (int)d, relu);                              \
+        MM_CUDA_OK(mm_launch(ln_bwd_fused_vec<T, NCH_, false>, dim3((unsigned)g1),               \
+                             dim3(LNB_WARPS * 32), sm_bytes, st, dyy, lddy, r, ldres, xx, ldx,  \
+                             gate, gamma, yy, ldy, mean, rstd, dr, lddres, dxx, lddx, dgate,    \
+                             dgamma, dbeta, (float*)nullptr, M, (int)d, relu));                 \
     } while (0)
     if (nch <= 1) MM_FUSED(1);
     else if (nch <= 2) MM_FUSED(2);

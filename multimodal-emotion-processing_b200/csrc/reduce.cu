@@ -12,6 +12,8 @@ rowsum_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out, int
               int64_t period, int64_t rows_per_cta) {
   __shared__ float red[8][2][33];
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_trigger();
   const int64_t n = (int64_t)blockIdx.x * 64 + lane * 2;     // lane owns two adjacent columns
   const int64_t p = blockIdx.z;                       // residue class handled by this CTA
   const int64_t r_beg = (int64_t)blockIdx.y * rows_per_cta;  // in units of periods
@@ -80,6 +82,8 @@ struct CastTable {
 };
 __global__ void __launch_bounds__(256) cast_multi_kernel(CastTable t) {
   const int which = blockIdx.y;
+  pdl_wait();
+  pdl_trigger();
   if (which >= t.count) return;
   const float* __restrict__ s = t.src[which];
   bf16* __restrict__ d = t.dst[which];
@@ -114,9 +118,8 @@ int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t
   if (strips > 65535) strips = 65535;
   const int64_t rows_per_cta = cdiv(n_per, strips);
   dim3 grid((unsigned)cdiv(N, 64), (unsigned)strips, (unsigned)period);
-  rowsum_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ldx, out, M, N, period,
-                                         rows_per_cta);
-  MM_LAUNCH_OK();
+  MM_CUDA_OK(mm_launch(rowsum_kernel<T>, grid, dim3(256), 0, st, static_cast<const T*>(x), ldx, out,
+                       M, N, period, rows_per_cta));
   return MMEMO_OK;
 }
 
@@ -169,8 +172,8 @@ int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const
   int64_t bx = cdiv(cdiv(nmax, 4), 256);
   if (bx > 148) bx = 148;
   if (bx < 1) bx = 1;
-  cast_multi_kernel<<<dim3((unsigned)bx, (unsigned)count), 256, 0, mm_stream(s)>>>(t);
-  MM_LAUNCH_OK();
+  MM_CUDA_OK(mm_launch(cast_multi_kernel, dim3((unsigned)bx, (unsigned)count), dim3(256), 0,
+                       mm_stream(s), t));
   return MMEMO_OK;
 }
 int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_t s) {

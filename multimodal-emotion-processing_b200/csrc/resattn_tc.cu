@@ -82,6 +82,8 @@ resattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc::mbar_init(bar_o, 1);
     tc::fence_barrier_init();
   }
+  pdl_wait();
+  pdl_trigger();
   if (warp == 1) {
     tc::tmem_alloc(base + OFF_BAR + 64, 256);
     tc::tmem_relinquish();
@@ -305,8 +307,8 @@ int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const
   a.idesc_qk = tc::idesc_bf16(L, L, 0, 0);
   a.idesc_pv = tc::idesc_bf16(L, HD, 0, 1);
   dim3 grid((unsigned)H, (unsigned)B);
-  resattn_fwd_tc_kernel<<<grid, NTHREADS, SMEM_FWD, st>>>(tmQ, tmK, tmV, tmSp, tmSo, tmO, a);
-  MM_LAUNCH_OK();
+  MM_CUDA_OK(mm_launch(resattn_fwd_tc_kernel, grid, dim3(NTHREADS), SMEM_FWD, st, tmQ, tmK, tmV,
+                       tmSp, tmSo, tmO, a));
   return MMEMO_OK;
 }
 
@@ -387,6 +389,8 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc::mbar_init(bar_mm2, 1);
     tc::fence_barrier_init();
   }
+  pdl_wait();
+  pdl_trigger();
   if (warp == 1) {
     tc::tmem_alloc(base + B_OFF_BAR + 64, 512);
     tc::tmem_relinquish();
@@ -650,8 +654,7 @@ int resattn_bwd_tc(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
   a.idesc_tt64 = tc::idesc_bf16(L, HD, 1, 1);
   a.idesc_nt64 = tc::idesc_bf16(L, HD, 0, 1);
   dim3 grid((unsigned)H, (unsigned)B);
-  resattn_bwd_tc_kernel<<<grid, NTHREADS, SMEM_BWD, st>>>(tmQ, tmK, tmV, tmDO, tmS, tmSp, tmDSn,
-                                                          tmDSp, tmDQ, tmDK, tmDV, a);
-  MM_LAUNCH_OK();
+  MM_CUDA_OK(mm_launch(resattn_bwd_tc_kernel, grid, dim3(NTHREADS), SMEM_BWD, st, tmQ, tmK, tmV,
+                       tmDO, tmS, tmSp, tmDSn, tmDSp, tmDQ, tmDK, tmDV, a));
   return MMEMO_OK;
 }
