@@ -147,6 +147,9 @@ def _algorithmic(name: str, a: tuple):
     if name.startswith("mmemo_add_ln_bwd"):
         M, d = a[20], a[21]
         return 16 * M * d, e * M * d * (3 + (2 if a[2] else 0)), f"{M}x{d}"
+    if name.startswith("mmemo_rowsum"):
+        M, N = a[3], a[4]
+        return M * N, e * M * N, f"{M}x{N}"
     if name.startswith("mmemo_cast"):
         return 0, 6 * a[2], f"{a[2]}"
     return 0, 0, ""

@@ -396,7 +396,8 @@ def _attn_fwd(bf16, q, k, v, mask, s_prev, c, H, want_s):
     return o, s, stat
 
 
-def _attn_bwd(bf16, do, q, k, v, mask, s, s_prev, c, ds_next, o, stat, H, dq, dk, dv, want_dsprev):
+def _attn_bwd(bf16, do, q, k, v, mask, s, s_prev, c, ds_next, o, stat, H, dq, dk, dv, want_dsprev,
+              dc_out=None):
     B, Lq, d = q.shape
     Lk = k.shape[1]
     hd = d // H
@@ -404,7 +405,8 @@ def _attn_bwd(bf16, do, q, k, v, mask, s, s_prev, c, ds_next, o, stat, H, dq, dk
     ds_prev = None
     dc = None
     if s_prev is not None:
-        dc = torch.zeros(1, dtype=F32, device=q.device)
+        # "+=" scalar: a zero-initialised slot of the caller, or our own
+        dc = dc_out if dc_out is not None else torch.zeros(1, dtype=F32, device=q.device)
         if want_dsprev:
             ds_prev = torch.empty(B, H, Lq, Lk, dtype=dt, device=q.device)
     ws = None
@@ -659,8 +661,9 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     # attention core
     dqp = torch.empty(B, Lq, d, dtype=dt, device=dev)
     dkvp = torch.empty(B, Lk, 2 * d, dtype=dt, device=dev)
-    ds_prev, dc = _attn_bwd(bf16, do, qp, kvp[..., :d], kvp[..., d:], mask, s, s_prev, gc, ds_next,
-                            o, stat, n_heads, dqp, dkvp[..., :d], dkvp[..., d:], need_dsprev)
+    ds_prev, _ = _attn_bwd(bf16, do, qp, kvp[..., :d], kvp[..., d:], mask, s, s_prev, gc, ds_next,
+                           o, stat, n_heads, dqp, dkvp[..., :d], dkvp[..., d:], need_dsprev,
+                           dc_out=zbuf[zo + d + dff:zo + d + dff + 1])
     # projections: dq += dqp Wq ; dkv = dkvp [Wk;Wv]
     dw_q, r_q = _wgrad(wq, d, d)
     dw_kv = _dest_pair(wk, wv)
@@ -681,9 +684,9 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
                                (dx.view(-1, d), o.view(-1, d), dw_o),
                                (dqp.view(-1, d), q.view(-1, d), dw_q),
                                (dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)])
+    # (dc lives in zbuf; its output slot stays an empty placeholder)
     return [dq, dkv, ds_prev if ds_prev is not None else torch.empty(0, device=dev),
-            dc if dc is not None else torch.empty(0, device=dev),
-            r_q, r_kv, r_o, zbuf, r_f1, r_f2]
+            torch.empty(0, device=dev), r_q, r_kv, r_o, zbuf, r_f1, r_f2]
 
 
 def _block_full_setup(ctx, inputs, output):
@@ -707,11 +710,12 @@ def _block_full_backward(ctx, grads):
     (dq, dkv, ds_prev, dc, dw_q, dw_kv, dw_o, zbuf, dw_f1,
      dw_f2) = block_full_bwd_op(dh2, ds_next, q, kv, mask, s_prev, s, saved, params, H, bf16,
                                 same_qkv, need_dsprev)
-    # the small "+=" outputs share one zero-initialised buffer: [dp2 | dp1 | db_f2 | db_f1]
+    # the small "+=" outputs share one zero-initialised buffer: [dp2 | dp1 | db_f2 | db_f1 | dc]
     dff = params[8].shape[0]
     dp2, dp1 = zbuf[:1 + 2 * d], zbuf[1 + 2 * d:2 * (1 + 2 * d)]
     zo = 2 * (1 + 2 * d)
     db_f2, db_f1 = zbuf[zo:zo + d], zbuf[zo + d:zo + d + dff]
+    dc = zbuf[zo + d + dff:zo + d + dff + 1]
     has_prev = s_prev is not None
     # weight gradients written straight into DP bucket slots come back as empty placeholders
     wq, wk, wv, wo, f1w, f2w = params[0], params[1], params[2], params[3], params[8], params[10]
