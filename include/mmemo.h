@@ -262,6 +262,28 @@ int mmemo_allreduce_sum_f32(void* multicast_ptr, void* const* buffer_ptrs_dev,
                             int64_t offset_elems, int64_t n_elems, int rank, int world, int blocks,
                             mmemo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused gradient clipping + Adam / AdamW over a list of float32 tensors (host arrays of device
+ * pointers and element counts).  Replaces nn.utils.clip_grad_norm_(params, CLIP) +
+ * optimizer.step(): others/realformer.py:314-315,342 (Adam), cmu-mosei/run.py:368-369,398,
+ * Ren-MME/run.py:336-337,379, rencecps/run.py:175-176,202, robot_demo.py:471-472,502 (AdamW).
+ *   grad_sqnorm : *sqnorm_out = sum_i |g_i|^2 (device scalar; zeroed by the call)
+ *   clip_grads  : g_i *= min(1, max_norm / (sqrt(*sqnorm) + 1e-6))       [torch's formula]
+ *   adam_step   : torch.optim.Adam (decoupled=0: g += wd*p) / AdamW (decoupled=1: p *= 1-lr*wd),
+ *                 no amsgrad; `step` is the 1-based step count of this update.  With sqnorm != NULL
+ *                 the clip coefficient above is applied to the gradients on the fly (grads are
+ *                 not modified), so clip + step cost one pass.
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_grad_sqnorm_f32(int count, const float* const* grads, const int64_t* numel,
+                          float* sqnorm_out, mmemo_stream_t stream);
+int mmemo_clip_grads_f32(int count, float* const* grads, const int64_t* numel, const float* sqnorm,
+                         float max_norm, mmemo_stream_t stream);
+int mmemo_adam_step_f32(int count, float* const* params, const float* const* grads,
+                        float* const* exp_avg, float* const* exp_avg_sq, const int64_t* numel,
+                        float lr, float beta1, float beta2, float eps, float weight_decay,
+                        int decoupled, int64_t step, const float* sqnorm, float max_norm,
+                        mmemo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -136,3 +136,43 @@ def test_grad_reducer_on_encoder_skips_undefined_grads(stub):
                 assert p.grad.untyped_storage().data_ptr() in flat_ptrs, n
     finally:
         dist.destroy_process_group()
+
+
+def test_fused_adamw_host_logic(monkeypatch):
+    """optim.AdamW: torch.optim-compatible param_groups / state layout, one launch per step-count
+    group, global norm over all groups, empty groups skipped (Ren-MME/run.py:376-379)."""
+    from mmemo_b200 import optim as mo
+    calls = []
+    monkeypatch.setattr(ops, "_call", lambda name, *a: calls.append((name, a)))
+    monkeypatch.setattr(ops, "_stream", lambda: 0)
+    monkeypatch.setattr(mo, "_check", lambda ts, what: None)
+    w1, w2 = torch.nn.Parameter(torch.ones(5, 3)), torch.nn.Parameter(torch.ones(7))
+    frozen = torch.nn.Parameter(torch.ones(2))
+    opt = mo.AdamW([{"params": [w1, w2, frozen], "lr": 1e-3}, {"params": [], "lr": 1e-3}],
+                   max_grad_norm=1.0)
+    ref = torch.optim.AdamW([torch.nn.Parameter(torch.ones(1))])
+    assert set(opt.param_groups[0]) >= {"lr", "betas", "eps", "weight_decay"}
+    assert opt.param_groups[0]["weight_decay"] == ref.param_groups[0]["weight_decay"] == 1e-2
+    w1.grad, w2.grad = torch.ones_like(w1), torch.ones_like(w2)
+    opt.step()
+    names = [n for n, _ in calls]
+    assert names == ["mmemo_grad_sqnorm_f32", "mmemo_adam_step_f32"]
+    a = calls[1][1]
+    assert a[0] == 2 and a[11] == 1 and a[12] == 1        # two tensors, decoupled, step 1
+    assert a[13] is not None and a[14] == 1.0             # fused clipping
+    assert set(opt.state[w1]) == {"step", "exp_avg", "exp_avg_sq"} and frozen not in opt.state
+    # a parameter that starts receiving gradients later gets its own bias-correction step
+    calls.clear()
+    frozen.grad = torch.ones_like(frozen)
+    opt.step()
+    steps = sorted(a[12] for n, a in calls if n == "mmemo_adam_step_f32")
+    assert steps == [1, 2]
+    assert float(opt.state[w1]["step"]) == 2 and float(opt.state[frozen]["step"]) == 1
+    # ReduceLROnPlateau-style lr edits are picked up
+    opt.param_groups[0]["lr"] = 5e-4
+    calls.clear()
+    opt.step()
+    assert all(abs(a[6] - 5e-4) < 1e-12 for n, a in calls if n == "mmemo_adam_step_f32")
+    with pytest.raises(ValueError):
+        mo.Adam([w1], amsgrad=True)
+    assert mo.Adam([w1]).param_groups[0]["weight_decay"] == 0.0
