@@ -91,3 +91,90 @@ def multi_circle_loss(y_pred, y_true):
 def sigmoids(pred, offset):
     """robot_demo.py:594-595 helper of demo_output: sigmoid with per-class logit offsets."""
     return torch.sigmoid(pred - offset)
+
+
+class Ensemble:
+    """Ensemble-of-models inference of ``demo_output`` / ``f1_calculation`` (robot_demo.py:526-581,
+    597-622): ``pred = (model_1(x) + ... + model_n(x)) / n`` under ``eval()`` and
+    ``no_grad()``.
+
+    The reference runs the members one after the other and moves every prediction to the host.  At
+    batch 1 each member is ~350 launches of microsecond kernels, so the request is launch-bound.
+    Here the members run on their own CUDA streams (forked from and joined into the caller's
+    stream) and the whole request — input staging, all members, the average — is captured once per
+    input shape into a CUDA graph and replayed.  Weights are read at replay time from the members'
+    parameters (float32 mode); in bf16 mode the captured graph uses the bf16 weight shadows that
+    existed at capture time, so call ``refresh()`` after loading new weights.
+    """
+
+    NAMES = ("l", "v_256", "v_512", "v_1024", "a", "l_mask", "v_mask", "a_mask")
+    # logit offsets of the six printed emotions (robot_demo.py:609)
+    OFFSETS = {"happy": 0.1, "sad": 0.1, "angry": -0.1, "disgust": 0.0, "surprise": 0.1, "fear": 0.0}
+
+    def __init__(self, models, use_graph: bool = True):
+        self.models = list(models)
+        if not self.models:
+            raise ValueError("Ensemble needs at least one model")
+        for m in self.models:
+            m.eval()
+        self.use_graph = use_graph
+        self._graphs = {}      # input-shape key -> (graph, static inputs, static output)
+        self._streams = None
+
+    def refresh(self) -> None:
+        """Drop the captured graphs (after load_state_dict / precision changes)."""
+        self._graphs.clear()
+
+    def _forward(self, args):
+        """All members concurrently: one side stream per member, joined before the average."""
+        cur = torch.cuda.current_stream()
+        if self._streams is None or len(self._streams) != len(self.models):
+            self._streams = [torch.cuda.Stream() for _ in self.models]
+        preds = []
+        for m, s in zip(self.models, self._streams):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                preds.append(m(*args))
+        for s in self._streams:
+            cur.wait_stream(s)
+        pred = preds[0]
+        for p in preds[1:]:            # same summation order as robot_demo.py:614
+            pred = pred + p
+        return pred / len(preds)
+
+    @torch.no_grad()
+    def __call__(self, l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask):
+        args = (l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask)
+        if not all(t.is_cuda for t in args):
+            raise RuntimeError("mmemo_b200 runs on CUDA tensors only (no CPU fallback)")
+        if not self.use_graph:
+            return self._forward(args)
+        from .blocks import get_precision
+        key = (get_precision(),) + tuple((tuple(t.shape), t.dtype) for t in args)
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = [torch.empty_like(t) for t in args]
+            for s, t in zip(static_in, args):
+                s.copy_(t)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up off the capture: allocator, shadows
+                for _ in range(2):
+                    self._forward(static_in)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_out = self._forward(static_in)
+            entry = (graph, static_in, static_out)
+            self._graphs[key] = entry
+        graph, static_in, static_out = entry
+        torch._foreach_copy_(static_in, list(args))
+        graph.replay()
+        return static_out.clone()
+
+    def emotions(self, pred: torch.Tensor) -> dict:
+        """The scores ``demo_output`` prints for sample 0: sigmoid(logit - offset), rounded to 2
+        places (robot_demo.py:594-595, 615-622)."""
+        p = pred[0].detach().float().cpu()
+        return {k: round(float(torch.sigmoid(p[i] - off)), 2)
+                for i, (k, off) in enumerate(self.OFFSETS.items())}

@@ -293,3 +293,32 @@ def test_scores_returned_by_block_match_reference_semantics():
     assert rel_err(s2, t2) < 1e-6   # relative to 1.5e8: masked columns must carry c*(-1e8) - 1e8
     valid = mask[:, None, None, :].expand_as(t2) > 0
     assert rel_err(s2.cpu()[valid], t2[valid]) < TOL32
+
+
+@pytest.mark.parametrize("B", [1, 32])
+def test_robot_demo_graphed_ensemble_equals_sequential_members(B):
+    """robot_demo.py:610-614: pred = (pred_1 + pred_2 + pred_3 + pred_4) / 4 — the CUDA-graph,
+    multi-stream ensemble must return exactly what the members return one by one, also when it is
+    replayed on new inputs."""
+    kw = dict(dim=192, l_len=25, v_len=100, a_len=100, n_heads=6, n_layers=2, ffn=2)
+    models = []
+    for i in range(4):
+        torch.manual_seed(i)
+        m = mmemo_b200.robot_demo.Multi_class(**kw)
+        m.load_state_dict(synth.randomize_gates(m.state_dict(), seed=10 + i))
+        models.append(m.to(DEV).eval())
+    ens = mmemo_b200.robot_demo.Ensemble(models)
+    for seed in (1, 2, 3):          # first call captures, later calls replay
+        b = to_dev(synth.robot_batch(seed=seed, B=B))
+        args = [b[k] for k in mmemo_b200.robot_demo.Ensemble.NAMES]
+        with torch.no_grad():
+            ref = models[0](*args)
+            for m in models[1:]:
+                ref = ref + m(*args)
+            ref = ref / 4
+        out = ens(*args)
+        assert rel_err(out, ref) < 1e-6      # (split-K atomics may reorder fp32 sums)
+    assert len(ens._graphs) == 1
+    emo = ens.emotions(out)
+    assert list(emo) == ["happy", "sad", "angry", "disgust", "surprise", "fear"]
+    assert all(0.0 <= v <= 1.0 for v in emo.values())
