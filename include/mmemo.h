@@ -284,6 +284,19 @@ int mmemo_adam_step_f32(int count, float* const* params, const float* const* gra
                         int decoupled, int64_t step, const float* sqnorm, float max_norm,
                         mmemo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Device-side batch assembly: ragged float32 sequences (rows of D features, concatenated in
+ * `flat`; sample n owns rows [row_start[n], row_start[n] + n_rows[n])) -> padded batch
+ * out (N, m_len, D) + mask (N, m_len; nullable).  mode 0 "tail": the last min(T, m_len) rows
+ * (others/realformer.py:72-82,100-102); mode 1 "head": the first ones; mode 2 "stride": T < m_len
+ * -> all rows, else rows 0, gap, 2 gap, ... with gap = T / m_len (robot_demo.py:86-99,115-150).
+ * Remaining rows are 0 and masked out; do_scrub replaces NaN / +-Inf by scrub_value (-71 in the
+ * reference).  n_rows[n] == 0 gives an all-zero, fully masked sample ('no_name' slots).
+ * ------------------------------------------------------------------------------------------- */
+int mmemo_assemble_batch_f32(const float* flat, const int64_t* row_start, const int64_t* n_rows,
+                             float* out, float* mask, int64_t N, int64_t m_len, int64_t D,
+                             int mode, int do_scrub, float scrub_value, mmemo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

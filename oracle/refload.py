@@ -22,7 +22,8 @@ FILES = {
     "rencecps": "rencecps/run.py",
     "robot": "robot_demo.py",
 }
-_LOSS_FUNCS = {"multi_circle_loss", "multi_loss"}
+# loss functions + the pure host-side batch-assembly helpers (oracle/batching_oracle.py is pinned to them)
+_LOSS_FUNCS = {"multi_circle_loss", "multi_loss", "masking", "audio_features", "text_features"}
 
 
 def ref_root() -> str:

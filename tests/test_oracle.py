@@ -8,6 +8,7 @@
 Tolerance: fp32 reference-vs-restatement noise; the reference's own fp32-vs-fp64 floor is 3e-7 on
 logits / 7e-6 on the worst gradient tensor, so 2e-5 relative leaves margin.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -123,3 +124,76 @@ def test_circle_loss_closed_form():
     y = torch.tensor([[1, 0, 0]])
     want = torch.log1p(torch.exp(s[0, 1]) + torch.exp(s[0, 2])) + torch.log1p(torch.exp(-s[0, 0]))
     assert torch.allclose(O.multi_circle_loss(s, y)[0], want, atol=1e-6)
+
+
+# ---- batch assembly: oracle/batching_oracle.py vs the reference's own helpers -----
+def _ragged(seed, D, lens):
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for T in lens:
+        a = rng.standard_normal((T, D)).astype(np.float32)
+        if T:
+            bad = rng.random((T, D)) < 0.02
+            a[bad] = rng.choice(np.array([np.nan, np.inf, -np.inf], dtype=np.float32), bad.sum())
+        seqs.append(a)
+    return seqs
+
+
+@needs_ref
+def test_batching_oracle_tail_matches_reference_masking():
+    from oracle import batching_oracle as BO
+    ns = refload.load("realformer")
+    for a in _ragged(3, 35, [1, 7, 49, 50, 51, 180]):
+        ref_m, ref_mask = ns.masking(a.copy()[-50:], 50)      # call site others/realformer.py:100-102
+        m, mask = BO.masking_tail(a.copy(), 50)
+        assert np.array_equal(m, ref_m) and np.array_equal(mask, ref_mask)
+
+
+@needs_ref
+def test_batching_oracle_stride_matches_reference_features(tmp_path):
+    from oracle import batching_oracle as BO
+    ns = refload.load("robot")
+    for i, a in enumerate(_ragged(4, 40, [0, 3, 99, 100, 101, 250, 1000])):
+        a = np.nan_to_num(a, nan=0.5, posinf=1.5, neginf=-1.5)    # the demo does not scrub
+        np.save(tmp_path / f"u{i}.npy", a)
+        ref_f, ref_mask = ns.audio_features(str(tmp_path) + "/", f"u{i}", 100)
+        f, mask = BO.features_stride(a, 100)
+        assert np.array_equal(f, ref_f) and np.array_equal(mask, ref_mask)
+    b = _ragged(5, 768, [30])[0]
+    b = np.nan_to_num(b, nan=0.0, posinf=0.0, neginf=0.0)
+    np.save(tmp_path / "t.npy", b)
+    ref_f, ref_mask = ns.text_features(str(tmp_path) + "/", "t", 25)
+    f, mask = BO.features_stride(b, 25)
+    assert np.array_equal(f, ref_f) and np.array_equal(mask, ref_mask)
+
+
+def test_batching_oracle_literal_cases():
+    """Runs everywhere (no reference tree needed): hand-checked small cases."""
+    from oracle import batching_oracle as BO
+    a = np.arange(10, dtype=np.float32).reshape(5, 2)
+    a[4, 1] = np.inf
+    m, mask = BO.masking_tail(a, 3)
+    assert m.tolist() == [[4, 5], [6, 7], [8, -71]] and mask.tolist() == [1, 1, 1]
+    m, mask = BO.masking_tail(a[:2], 3)
+    assert m.tolist() == [[0, 1], [2, 3], [0, 0]] and mask.tolist() == [1, 1, 0]
+    f, mask = BO.features_stride(np.arange(14, dtype=np.float32).reshape(7, 2), 3)   # gap 2
+    assert f.tolist() == [[0, 1], [4, 5], [8, 9]] and mask.tolist() == [1, 1, 1]
+    f, mask = BO.features_stride(np.zeros((0, 2), np.float32), 2)
+    assert f.tolist() == [[0, 0], [0, 0]] and mask.tolist() == [0, 0]
+    f, mask = BO.head(np.arange(8, dtype=np.float32).reshape(4, 2), 3)
+    assert f.tolist() == [[0, 1], [2, 3], [4, 5]] and mask.tolist() == [1, 1, 1]
+
+
+def test_ragged_batch_pack_host_side():
+    from mmemo_b200.batching import RaggedBatch
+    seqs = [np.ones((3, 4)), None, np.zeros((0, 4)), 2 * np.ones((2, 4), dtype=np.float64)]
+    rb = RaggedBatch.pack(seqs, pin=False)
+    assert rb.n_rows.tolist() == [3, 0, 0, 2] and rb.row_start.tolist() == [0, 3, 3, 3]
+    assert rb.flat.dtype == torch.float32 and rb.flat.shape == (5, 4) and float(rb.flat[4, 0]) == 2.0
+    with pytest.raises(ValueError):
+        RaggedBatch.pack([np.ones((1, 3)), np.ones((1, 4))], pin=False)
+    with pytest.raises(ValueError):
+        RaggedBatch.pack([None, None], pin=False)
+    assert len(RaggedBatch.pack([None, None], dim=7, pin=False)) == 2
+    with pytest.raises(RuntimeError):           # no CPU fallback
+        rb.assemble(5)
