@@ -28,9 +28,9 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4;
+constexpr int BM = 128, BK = 64, STAGES = 5;
 constexpr uint32_t A_TILE = BM * BK * 2, B_TILE = 128 * BK * 2;   // per CTA per stage: 16 KB + 16 KB
-constexpr uint32_t RING = STAGES * (A_TILE + B_TILE);             // 128 KB
+constexpr uint32_t RING = STAGES * (A_TILE + B_TILE);             // 160 KB
 constexpr uint32_t OUT_BYTES = 64 * 1024;    // fp32 staging (128x128), or bf16 staging + aux tile
 constexpr int NTHREADS = 192;
 constexpr uint32_t SMEM_BYTES = RING + OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;

@@ -100,9 +100,11 @@ class GradReducer:
             raise ValueError(f"unknown transport {transport!r}")
         # "auto": libmmemo's symmetric-memory all-reduce on CUDA, the process group's otherwise
         self.transport = "nccl" if (transport == "nccl" or not on_cuda) else "symm"
+        self._requested_transport = transport
         self.comm_blocks = comm_blocks
         self._symm = None           # (handle, comm stream) once the buckets are built
-        self.sm_reserve = sm_reserve if (on_cuda and self.transport == "nccl") else 0
+        self._nccl_sm_reserve = sm_reserve if on_cuda else 0
+        self.sm_reserve = self._nccl_sm_reserve if self.transport == "nccl" else 0
         self.reserve_launches = reserve_launches
         self._slot: Dict[torch.nn.Parameter, tuple] = {}
         self._order: List[torch.nn.Parameter] = []
@@ -124,8 +126,8 @@ class GradReducer:
             groups.append(cur)
         flat, bases = None, [0] * len(groups)
         if self.transport == "symm" and groups:
-            flat, bases = self._alloc_symmetric([_Bucket.layout(g)[1] for g in groups],
-                                                groups[0][0].device)
+            flat, bases = self._try_symmetric([_Bucket.layout(g)[1] for g in groups],
+                                              groups[0][0].device)
         self.buckets = [_Bucket(g, flat, base) for g, base in zip(groups, bases)]
         for bi, b in enumerate(self.buckets):
             for p, off in zip(b.params, b.offsets):
@@ -135,6 +137,30 @@ class GradReducer:
                     from . import ops
                     ops.register_grad_dest(p, b.flat, off)
         self._built = True
+
+    def _try_symmetric(self, sizes: List[int], device):
+        """Symmetric buckets when every rank can set them up; otherwise ALL ranks switch to the
+        process group's all-reduce (a transport choice between two GPU paths, agreed collectively —
+        e.g. GPUs without peer access, or a torch build without symmetric memory)."""
+        import sys
+        flat, bases, err = None, [0] * len(sizes), None
+        try:
+            flat, bases = self._alloc_symmetric(sizes, device)
+        except Exception as ex:      # noqa: BLE001 - any setup failure means "not available here"
+            err = ex
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if float(ok.item()) == 1.0:
+            return flat, bases
+        if self._requested_transport == "symm":
+            raise RuntimeError(f"symmetric-memory gradient transport unavailable: {err!r}")
+        if dist.get_rank(self.group) == 0:
+            print(f"[mmemo_b200.dp] symmetric memory unavailable ({err!r}); using the process "
+                  "group's all-reduce", file=sys.stderr)
+        self._symm = None
+        self.transport = "nccl"
+        self.sm_reserve = self._nccl_sm_reserve
+        return None, [0] * len(sizes)
 
     def _alloc_symmetric(self, sizes: List[int], device):
         """One symmetric allocation for all buckets + rendezvous (collective, first step only)."""
