@@ -18,6 +18,7 @@ struct GemmArgs {
   int relu_src_bf16;
   int relu;                // C = max(C, 0)
   int accumulate;          // C += result
+  int c_zeroed;            // C is known to be all zero: the split-K reduce-add path skips its own fill
 };
 
 int gemm_simt(const GemmArgs& g, int a_bf16, int b_bf16, int c_bf16, cudaStream_t st);

@@ -578,7 +578,7 @@ int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t 
     a.tiles_m = tiles_m; a.tiles_n = tiles_n;
     G.item_start[i] = items;
     items += tiles * sp;
-    if (reduce_add && !g.accumulate)   // the slices accumulate into C: start from zero
+    if (reduce_add && !g.accumulate && !g.c_zeroed)   // the slices accumulate into C: start from zero
       MM_CUDA_OK(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
   }
   G.item_start[n] = items;

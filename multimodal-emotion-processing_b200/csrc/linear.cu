@@ -152,7 +152,8 @@ int mmemo_linear_bwd_w_grouped_bf16(int n, const void* const* dy, const int64_t*
     g[i].C = dw[i]; g[i].ldc = lddw[i];
     g[i].M = N[i]; g[i].N = K[i]; g[i].K = M[i];
     g[i].pos_period = 1;
-    g[i].accumulate = accumulate;
+    g[i].accumulate = accumulate == 1;
+    g[i].c_zeroed = accumulate == 2;      // either overwrite or add is correct
     cb[i] = 0;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 0);
   }

@@ -303,8 +303,9 @@ def _linear_bwd_x_group(bf16, items):
           _arr(C.c_int, [int(it[3]) for it in items]), _stream())
 
 
-def _linear_bwd_w_group(bf16, items):
-    """items: [(dy, x, dw)] -> dw = dy^T x (float32), all in one grouped launch in bf16 mode."""
+def _linear_bwd_w_group(bf16, items, zeroed=False):
+    """items: [(dy, x, dw)] -> dw = dy^T x (float32), all in one grouped launch in bf16 mode.
+    ``zeroed``: every dw is already all zero (saves the split-K path its own zero fills)."""
     if not bf16 or len(items) == 1:
         for dy, x, dw in items:
             _linear_bwd_w(bf16, dy, x, dw)
@@ -317,7 +318,7 @@ def _linear_bwd_w_group(bf16, items):
           _arr(C.c_void_p, [it[2].data_ptr() for it in items]),
           _arr(C.c_int64, [it[2].stride(0) for it in items]),
           _arr(C.c_int64, [M for _, M, _ in dys]), _arr(C.c_int64, [d.shape[-1] for d, _, _ in dys]),
-          _arr(C.c_int64, [x.shape[-1] for x, _, _ in xs]), 0, _stream())
+          _arr(C.c_int64, [x.shape[-1] for x, _, _ in xs]), 2 if zeroed else 0, _stream())
 
 
 def _add_ln_fwd(bf16, res, x, gate, gamma, beta, relu=False):
@@ -621,6 +622,22 @@ def block_full_op(q: Tensor, kv: Tensor, mask: Optional[Tensor], s_prev: Optiona
     return [h2, s if s is not None else e, qp, kvp, o, stat, x, h1, st1, f1, f2, st2]
 
 
+def _zbuf_layout(d: int, dff: int):
+    """(floats of the small "+=" outputs rounded to 256 B, [sizes of dWq, dWkv, dWo, dWf1, dWf2])."""
+    n_small = (2 * (1 + 2 * d) + d + dff + 32 + 63) // 64 * 64
+    return n_small, [d * d, 2 * d * d, d * d, dff * d, d * dff]
+
+
+def _zbuf_weights(zbuf: Tensor, d: int, dff: int):
+    n_small, sizes = _zbuf_layout(d, dff)
+    shapes = [(d, d), (2 * d, d), (d, d), (dff, d), (d, dff)]
+    out, o = [], n_small
+    for n, sh in zip(sizes, shapes):
+        out.append(zbuf[o:o + n].view(sh))
+        o += n
+    return out
+
+
 @torch.library.custom_op("mmemo::block_full_bwd", mutates_args=())
 def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Tensor,
                       mask: Optional[Tensor], s_prev: Optional[Tensor], s: Optional[Tensor],
@@ -636,7 +653,10 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     kv = q if same_qkv else kv.contiguous()
     dh2 = dh2.contiguous()
     # one zero-filled buffer for every "+=" output of the block (LN params, biases, dc)
-    zbuf = torch.zeros(2 * (1 + 2 * d) + d + dff + 32, dtype=F32, device=dev)
+    # ... and, unless they have a data-parallel bucket slot, for the five weight gradients
+    in_z = _dest(wq) is None
+    n_small, w_sizes = _zbuf_layout(d, dff)
+    zbuf = torch.zeros(n_small + (sum(w_sizes) if in_z else 0), dtype=F32, device=dev)
     z_dp2, z_dp1 = zbuf[:1 + 2 * d], zbuf[1 + 2 * d:2 * (1 + 2 * d)]
     zo = 2 * (1 + 2 * d)
     # LN2: h2 = LN(h1 + b*f2)
@@ -647,9 +667,14 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     # FFN backward; df1 = (df2 W2) * (f1 > 0) fused in the GEMM epilogue
     df1 = torch.empty(B, Lq, dff, dtype=dt, device=dev)
     _linear_bwd_x(bf16, df2, _weight(bf16, f2w), df1.view(-1, dff), relu_src=f1.view(-1, dff))
-    dw_f2, r_f2 = _wgrad(f2w, d, dff)
+    if in_z:
+        dw_q, dw_kv, dw_o, dw_f1, dw_f2 = _zbuf_weights(zbuf, d, dff)
+        r_q = r_kv = r_o = r_f1 = r_f2 = None       # returned through zbuf
+    else:
+        dw_f2, r_f2 = _wgrad(f2w, d, dff)
     _linear_bwd_x(bf16, df1, _weight(bf16, f1w), dh1.view(-1, d), accumulate=True)
-    dw_f1, r_f1 = _wgrad(f1w, dff, d)
+    if not in_z:
+        dw_f1, r_f1 = _wgrad(f1w, dff, d)
     db_f1 = zbuf[zo + d:zo + d + dff]
     _rowsum(bf16, df1.view(-1, dff), db_f1)
     # LN1: h1 = LN(q + a*x)
@@ -657,7 +682,8 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     # output projection
     do = torch.empty(B, Lq, d, dtype=dt, device=dev)
     _linear_bwd_x(bf16, dx, _weight(bf16, wo), do.view(-1, d))
-    dw_o, r_o = _wgrad(wo, d, d)
+    if not in_z:
+        dw_o, r_o = _wgrad(wo, d, d)
     # attention core
     dqp = torch.empty(B, Lq, d, dtype=dt, device=dev)
     dkvp = torch.empty(B, Lk, 2 * d, dtype=dt, device=dev)
@@ -665,11 +691,12 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
                            o, stat, n_heads, dqp, dkvp[..., :d], dkvp[..., d:], need_dsprev,
                            dc_out=zbuf[zo + d + dff:zo + d + dff + 1])
     # projections: dq += dqp Wq ; dkv = dkvp [Wk;Wv]
-    dw_q, r_q = _wgrad(wq, d, d)
-    dw_kv = _dest_pair(wk, wv)
-    r_kv = torch.empty(0, device=dev)
-    if dw_kv is None:
-        dw_kv = r_kv = torch.empty(2 * d, d, dtype=F32, device=dev)
+    if not in_z:
+        dw_q, r_q = _wgrad(wq, d, d)
+        dw_kv = _dest_pair(wk, wv)
+        r_kv = torch.empty(0, device=dev)
+        if dw_kv is None:
+            dw_kv = r_kv = torch.empty(2 * d, d, dtype=F32, device=dev)
     if same_qkv:   # both input gradients accumulate into dq: keep them ordered
         _linear_bwd_x(bf16, dqp, _weight(bf16, wq), dq.view(-1, d), accumulate=True)
         _linear_bwd_x(bf16, dkvp, _weight(bf16, wk, wv), dq.view(-1, d), accumulate=True)
@@ -683,10 +710,12 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
                                (df1.view(-1, dff), h1.view(-1, d), dw_f1),
                                (dx.view(-1, d), o.view(-1, d), dw_o),
                                (dqp.view(-1, d), q.view(-1, d), dw_q),
-                               (dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)])
-    # (dc lives in zbuf; its output slot stays an empty placeholder)
+                               (dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)], zeroed=in_z)
+    # (dc lives in zbuf; its output slot stays an empty placeholder — like the weight gradients
+    # when they live in zbuf or in a bucket slot)
+    ph = [torch.empty(0, device=dev) if r is None else r for r in (r_q, r_kv, r_o, r_f1, r_f2)]
     return [dq, dkv, ds_prev if ds_prev is not None else torch.empty(0, device=dev),
-            torch.empty(0, device=dev), r_q, r_kv, r_o, zbuf, r_f1, r_f2]
+            torch.empty(0, device=dev), ph[0], ph[1], ph[2], zbuf, ph[3], ph[4]]
 
 
 def _block_full_setup(ctx, inputs, output):
@@ -719,12 +748,15 @@ def _block_full_backward(ctx, grads):
     has_prev = s_prev is not None
     # weight gradients written straight into DP bucket slots come back as empty placeholders
     wq, wk, wv, wo, f1w, f2w = params[0], params[1], params[2], params[3], params[8], params[10]
-    dw_q = dw_q if dw_q.numel() else _dest(wq)
-    dw_o = dw_o if dw_o.numel() else _dest(wo)
-    dw_f1 = dw_f1 if dw_f1.numel() else _dest(f1w)
-    dw_f2 = dw_f2 if dw_f2.numel() else _dest(f2w)
-    if not dw_kv.numel():
-        dw_kv = _dest_pair(wk, wv)
+    if zbuf.numel() > _zbuf_layout(d, dff)[0]:        # weight gradients inside the zero buffer
+        dw_q, dw_kv, dw_o, dw_f1, dw_f2 = _zbuf_weights(zbuf, d, dff)
+    else:
+        dw_q = dw_q if dw_q.numel() else _dest(wq)
+        dw_o = dw_o if dw_o.numel() else _dest(wo)
+        dw_f1 = dw_f1 if dw_f1.numel() else _dest(f1w)
+        dw_f2 = dw_f2 if dw_f2.numel() else _dest(f2w)
+        if not dw_kv.numel():
+            dw_kv = _dest_pair(wk, wv)
     pgrads = [dw_q, dw_kv[:d], dw_kv[d:], dw_o, dp1[1:1 + d], dp1[1 + d:], dp2[1:1 + d],
               dp2[1 + d:], dw_f1, db_f1, dw_f2, db_f2, dp1[0:1], dp2[0:1],
               dc if has_prev else None]

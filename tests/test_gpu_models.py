@@ -317,7 +317,7 @@ def test_robot_demo_graphed_ensemble_equals_sequential_members(B):
                 ref = ref + m(*args)
             ref = ref / 4
         out = ens(*args)
-        assert rel_err(out, ref) < 1e-6      # (split-K atomics may reorder fp32 sums)
+        assert rel_err(out, ref) < 1e-5      # (split-K atomics may reorder fp32 sums)
     assert len(ens._graphs) == 1
     emo = ens.emotions(out)
     assert list(emo) == ["happy", "sad", "angry", "disgust", "surprise", "fear"]

@@ -116,4 +116,6 @@ def test_training_loop_with_fused_optimizer_tracks_torch():
             ls.append(float(loss.detach()))
     assert l1s[-1] < l1s[0]
     for a, b in zip(l1s, l2s):
-        assert abs(a - b) <= 1e-3 * max(1.0, abs(b)), (l1s, l2s)
+        # (atomics reorder fp32 sums, so the two runs are not bit-identical; SURVEY's bar for a
+        # loss curve is 1 %)
+        assert abs(a - b) <= 5e-3 * max(1.0, abs(b)), (l1s, l2s)
