@@ -103,6 +103,7 @@ class GradReducer:
         self._requested_transport = transport
         self.comm_blocks = comm_blocks
         self._symm = None           # (handle, comm stream) once the buckets are built
+        self._flat_all = None       # the one symmetric buffer all buckets are views of
         self._nccl_sm_reserve = sm_reserve if on_cuda else 0
         self.sm_reserve = self._nccl_sm_reserve if self.transport == "nccl" else 0
         self.reserve_launches = reserve_launches
@@ -128,6 +129,7 @@ class GradReducer:
         if self.transport == "symm" and groups:
             flat, bases = self._try_symmetric([_Bucket.layout(g)[1] for g in groups],
                                               groups[0][0].device)
+        self._flat_all = flat
         self.buckets = [_Bucket(g, flat, base) for g, base in zip(groups, bases)]
         for bi, b in enumerate(self.buckets):
             for p, off in zip(b.params, b.offsets):
@@ -254,7 +256,21 @@ class GradReducer:
         if self.zero_copy:
             from . import ops
             ops.grad_dest_enabled = in_place_ok
-        (loss / self.world).backward()
+            ops.grad_dest_zeroed = False
+            if in_place_ok and self._built and self.buckets and self.buckets[0].flat.is_cuda:
+                # one fill for all buckets (they are views of one symmetric buffer) instead of one
+                # per weight gradient inside the split-K GEMM launches
+                if self._flat_all is not None:
+                    self._flat_all.zero_()
+                else:
+                    for b in self.buckets:
+                        b.flat.zero_()
+                ops.grad_dest_zeroed = True
+        try:
+            (loss / self.world).backward()
+        finally:
+            if self.zero_copy:
+                ops.grad_dest_zeroed = False
         self.finish()
 
     def finish(self) -> None:

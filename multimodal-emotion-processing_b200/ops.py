@@ -193,6 +193,9 @@ def _rows(x: Tensor) -> Tuple[Tensor, int, int]:
 # ------------------------------------------------------------------------------------------------
 _grad_dest: dict = {}
 grad_dest_enabled = True
+# set by dp.GradReducer.backward(): the bucket slots were zero-filled before this backward, so
+# kernels that accumulate into them (split-K reduce-add) need no fill of their own
+grad_dest_zeroed = False
 
 
 def register_grad_dest(param: Tensor, flat: Tensor, offset: int) -> None:
@@ -691,10 +694,12 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
                            o, stat, n_heads, dqp, dkvp[..., :d], dkvp[..., d:], need_dsprev,
                            dc_out=zbuf[zo + d + dff:zo + d + dff + 1])
     # projections: dq += dqp Wq ; dkv = dkvp [Wk;Wv]
+    all_dest = False
     if not in_z:
         dw_q, r_q = _wgrad(wq, d, d)
         dw_kv = _dest_pair(wk, wv)
         r_kv = torch.empty(0, device=dev)
+        all_dest = dw_kv is not None and all(_dest(w) is not None for w in (wq, wo, f1w, f2w))
         if dw_kv is None:
             dw_kv = r_kv = torch.empty(2 * d, d, dtype=F32, device=dev)
     if same_qkv:   # both input gradients accumulate into dq: keep them ordered
@@ -710,7 +715,8 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
                                (df1.view(-1, dff), h1.view(-1, d), dw_f1),
                                (dx.view(-1, d), o.view(-1, d), dw_o),
                                (dqp.view(-1, d), q.view(-1, d), dw_q),
-                               (dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)], zeroed=in_z)
+                               (dkvp.view(-1, 2 * d), kv.view(-1, d), dw_kv)],
+                        zeroed=in_z or (grad_dest_zeroed and all_dest))
     # (dc lives in zbuf; its output slot stays an empty placeholder — like the weight gradients
     # when they live in zbuf or in a bucket slot)
     ph = [torch.empty(0, device=dev) if r is None else r for r in (r_q, r_kv, r_o, r_f1, r_f2)]
