@@ -257,6 +257,7 @@ class GradReducer:
             from . import ops
             ops.grad_dest_enabled = in_place_ok
             ops.grad_dest_zeroed = False
+            ops.begin_backward()
             if in_place_ok and self._built and self.buckets and self.buckets[0].flat.is_cuda:
                 # one fill for all buckets (they are views of one symmetric buffer) instead of one
                 # per weight gradient inside the split-K GEMM launches

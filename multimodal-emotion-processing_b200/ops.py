@@ -198,8 +198,26 @@ grad_dest_enabled = True
 grad_dest_zeroed = False
 
 
+# A slot can be WRITTEN by one op per backward: a parameter that is used twice (shared weights)
+# gets a fresh buffer for its second gradient and autograd sums the two as usual.
+_dest_claimed: set = set()
+
+
 def register_grad_dest(param: Tensor, flat: Tensor, offset: int) -> None:
     _grad_dest[param.data_ptr()] = (flat, offset, param.numel())
+
+
+def begin_backward() -> None:
+    """Called by dp.GradReducer.backward(): every slot is writable again."""
+    _dest_claimed.clear()
+
+
+def _claim(*ws: Tensor) -> bool:
+    keys = [w.data_ptr() for w in ws]
+    if any(k in _dest_claimed for k in keys):
+        return False
+    _dest_claimed.update(keys)
+    return True
 
 
 def clear_grad_dest() -> None:
@@ -226,7 +244,7 @@ def _dest_pair(wa: Tensor, wb: Tensor) -> Optional[Tensor]:
 def _wgrad(w: Tensor, rows: int, cols: int):
     """(buffer to write dW into, tensor to return from the custom op)."""
     d = _dest(w)
-    if d is not None:
+    if d is not None and _claim(w):
         return d.view(rows, cols), torch.empty(0, device=w.device)
     buf = torch.empty(rows, cols, dtype=F32, device=w.device)
     return buf, buf
@@ -698,10 +716,13 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     if not in_z:
         dw_q, r_q = _wgrad(wq, d, d)
         dw_kv = _dest_pair(wk, wv)
+        if dw_kv is not None and not _claim(wk, wv):
+            dw_kv = None
         r_kv = torch.empty(0, device=dev)
-        all_dest = dw_kv is not None and all(_dest(w) is not None for w in (wq, wo, f1w, f2w))
         if dw_kv is None:
             dw_kv = r_kv = torch.empty(2 * d, d, dtype=F32, device=dev)
+        # every gradient of the group goes to a (zero-filled) bucket slot?
+        all_dest = not any(r.numel() for r in (r_q, r_kv, r_o, r_f1, r_f2))
     if same_qkv:   # both input gradients accumulate into dq: keep them ordered
         _linear_bwd_x(bf16, dqp, _weight(bf16, wq), dq.view(-1, d), accumulate=True)
         _linear_bwd_x(bf16, dkvp, _weight(bf16, wk, wv), dq.view(-1, d), accumulate=True)

@@ -176,3 +176,26 @@ def test_fused_adamw_host_logic(monkeypatch):
     with pytest.raises(ValueError):
         mo.Adam([w1], amsgrad=True)
     assert mo.Adam([w1]).param_groups[0]["weight_decay"] == 0.0
+
+
+def test_bucket_slot_is_written_once_per_backward():
+    """A weight that is used twice in one forward (shared module) must not have both gradients
+    written into the same data-parallel bucket slot: the second use gets a fresh buffer and
+    autograd sums the two."""
+    w = torch.nn.Parameter(torch.zeros(4, 3))
+    flat = torch.zeros(64)
+    ops.clear_grad_dest()
+    ops.register_grad_dest(w, flat, 16)
+    ops.grad_dest_enabled = True
+    try:
+        ops.begin_backward()
+        buf1, ret1 = ops._wgrad(w, 4, 3)
+        buf2, ret2 = ops._wgrad(w, 4, 3)
+        assert ret1.numel() == 0 and buf1.data_ptr() == flat[16:].data_ptr()      # the slot itself
+        assert ret2.numel() == 12 and buf2.data_ptr() != buf1.data_ptr()          # a fresh buffer
+        ops.begin_backward()                                                        # next step
+        buf3, ret3 = ops._wgrad(w, 4, 3)
+        assert ret3.numel() == 0 and buf3.data_ptr() == buf1.data_ptr()
+    finally:
+        ops.clear_grad_dest()
+        ops.begin_backward()
