@@ -9,10 +9,13 @@ per-rank gradients reproduces the single-process full-batch gradient up to fp32 
 Mechanics: parameters are packed into flat float32 buckets in the order their gradients become
 ready (observed during the first backward, like DDP's bucket rebuild; parameters that never
 receive a gradient, e.g. the first-layer ``c`` of each chain, are left out identically on all
-ranks).  A post-accumulate hook copies each gradient into its bucket slot and re-points
-``p.grad`` at the slot; when a bucket is full its all-reduce is issued asynchronously (NCCL runs
-it on its own stream, so it overlaps the rest of backward, also under CUDA-graph capture).
-``finish()`` joins the collectives.  The loss is pre-scaled by 1/world so a SUM reduction yields
+ranks).  The fused block backward writes its weight gradients straight into their slots
+(``ops.register_grad_dest``; the buckets are zero-filled once per backward so the split-K
+reduce-add needs no fills of its own; one writer per slot and backward — a shared weight's second
+gradient goes through autograd's normal accumulation); a post-accumulate hook copies every other
+gradient into its slot and re-points ``p.grad`` at it.  When a bucket is full its all-reduce is
+issued asynchronously on a side stream, so it overlaps the rest of backward, also under CUDA-graph
+capture.  ``finish()`` joins the collectives.  The loss is pre-scaled by 1/world so a SUM reduction yields
 the average (gloo has no AVG).
 
 Transport: on CUDA the buckets are carved out of ONE symmetric-memory allocation
