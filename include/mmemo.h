@@ -10,8 +10,10 @@
  *
  * Conventions
  *   - every pointer is a DEVICE pointer unless the comment says "host"; buffers are owned by the
- *     caller; nothing here allocates, synchronises or keeps global state; all work is enqueued on
- *     `stream` (a cudaStream_t passed as void*).
+ *     caller; nothing here allocates or synchronises; all work is enqueued on `stream` (a
+ *     cudaStream_t passed as void*).  The only process-wide state are the three settings of the
+ *     "library / device info" block (split-K workspace, SM budget, programmatic dependent launch);
+ *     one process drives one GPU.
  *   - return 0 on success, <0 on error (MMEMO_ERR_*).  No CPU fallback exists.
  *   - suffix _f32 / _bf16 = dtype of ACTIVATIONS and GEMM weights (T).  Small parameter vectors
  *     (bias, LayerNorm gamma/beta, gates a/b/c, position tables) and ALL parameter gradients are
