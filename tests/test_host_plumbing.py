@@ -199,3 +199,22 @@ def test_bucket_slot_is_written_once_per_backward():
     finally:
         ops.clear_grad_dest()
         ops.begin_backward()
+
+
+def test_ensemble_emotion_scores_follow_demo_output():
+    """robot_demo.py:594-595,609,615-622: score = 1 / (1 + exp(-x + t)) with the per-emotion
+    offsets happy .1, sad .1, angry -.1, disgust 0, surprise .1, fear 0, rounded to 2 places."""
+    import math
+
+    from mmemo_b200.robot_demo import Ensemble
+    ens = Ensemble([torch.nn.Linear(2, 2)])
+    pred = torch.tensor([[0.3, -1.2, 2.0, 0.0, -0.1, 5.0, 9.9]])
+    offs = [0.1, 0.1, -0.1, 0.0, 0.1, 0.0]
+    exp = [round(1 / (1 + math.exp(-float(pred[0][i]) + offs[i])), 2) for i in range(6)]
+    got = ens.emotions(pred)
+    assert list(got) == ["happy", "sad", "angry", "disgust", "surprise", "fear"]
+    assert all(abs(g - e) <= 0.011 for g, e in zip(got.values(), exp)), (got, exp)
+    with pytest.raises(ValueError):
+        Ensemble([])
+    with pytest.raises(RuntimeError):          # no CPU fallback
+        ens(*[torch.zeros(1, 2)] * 8)
