@@ -61,20 +61,25 @@ def shard_batch(batch, rank: int, world: int, align: int = 1):
 class _Bucket:
     __slots__ = ("flat", "params", "offsets", "pending", "work", "todo", "base")
 
-    ALIGN = 1024        # bucket length granularity: 4 floats x up to 16 ranks x 16
+    ALIGN = 1024        # bucket length granularity (floats)
 
     @classmethod
-    def layout(cls, params: Sequence[torch.nn.Parameter]):
+    def layout(cls, params: Sequence[torch.nn.Parameter], world: int = 1):
+        """Slot offsets and padded length.  The length is a multiple of 4 floats x world (the
+        all-reduce kernel gives every rank a 16-byte-aligned 1/world slice): 1024 for the usual
+        power-of-two worlds, lcm(1024, 4*world) otherwise."""
+        import math
+        align = math.lcm(cls.ALIGN, 4 * max(world, 1))
         offsets, n = [], 0
         for p in params:
             offsets.append(n)
             n += (p.numel() + 31) // 32 * 32          # 128-byte aligned slots
-        return offsets, (n + cls.ALIGN - 1) // cls.ALIGN * cls.ALIGN
+        return offsets, (n + align - 1) // align * align
 
     def __init__(self, params: Sequence[torch.nn.Parameter], flat: Optional[torch.Tensor] = None,
-                 base: int = 0):
+                 base: int = 0, world: int = 1):
         self.params = list(params)
-        self.offsets, n = self.layout(self.params)
+        self.offsets, n = self.layout(self.params, world)
         p0 = self.params[0]
         self.flat = (torch.zeros(n, dtype=torch.float32, device=p0.device) if flat is None
                      else flat[base:base + n])
@@ -130,10 +135,10 @@ class GradReducer:
             groups.append(cur)
         flat, bases = None, [0] * len(groups)
         if self.transport == "symm" and groups:
-            flat, bases = self._try_symmetric([_Bucket.layout(g)[1] for g in groups],
+            flat, bases = self._try_symmetric([_Bucket.layout(g, self.world)[1] for g in groups],
                                               groups[0][0].device)
         self._flat_all = flat
-        self.buckets = [_Bucket(g, flat, base) for g, base in zip(groups, bases)]
+        self.buckets = [_Bucket(g, flat, base, self.world) for g, base in zip(groups, bases)]
         for bi, b in enumerate(self.buckets):
             for p, off in zip(b.params, b.offsets):
                 self._slot[p] = (bi, off)

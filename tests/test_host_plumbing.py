@@ -218,3 +218,14 @@ def test_ensemble_emotion_scores_follow_demo_output():
         Ensemble([])
     with pytest.raises(RuntimeError):          # no CPU fallback
         ens(*[torch.zeros(1, 2)] * 8)
+
+
+def test_bucket_length_is_sliceable_for_any_world():
+    """The all-reduce kernel needs bucket_len % (4 * world) == 0; layouts of the tested worlds
+    (2, 4, 8) keep the 1024-float granularity."""
+    ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 96 * 96, 1, 33)]
+    for world in range(1, 17):
+        offs, n = dp._Bucket.layout(ps, world)
+        assert n % (4 * world) == 0 and n >= offs[-1] + 33 and all(o % 32 == 0 for o in offs)
+        if world in (1, 2, 4, 8, 16):
+            assert n == dp._Bucket.layout(ps)[1] and n % 1024 == 0
