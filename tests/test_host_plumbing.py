@@ -223,6 +223,7 @@ def test_ensemble_emotion_scores_follow_demo_output():
 def test_bucket_length_is_sliceable_for_any_world():
     """The all-reduce kernel needs bucket_len % (4 * world) == 0; layouts of the tested worlds
     (2, 4, 8) keep the 1024-float granularity."""
+    from mmemo_b200 import dp
     ps = [torch.nn.Parameter(torch.zeros(n)) for n in (5, 96 * 96, 1, 33)]
     for world in range(1, 17):
         offs, n = dp._Bucket.layout(ps, world)
