@@ -9,7 +9,7 @@
 //       128 x 128 version was L2-bandwidth-bound (profiles/).
 //   CTA2 = false: one CTA per 128 x 128 tile (small N, and the ragged shapes).
 //
-//   warp 0   TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) into a 4-stage shared-memory ring
+//   warp 0   TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) into a 5-stage shared-memory ring
 //   warp 1   MMA issuer   : one thread (of the leader CTA) issues the UMMAs into one of TWO TMEM
 //                           accumulators; tcgen05.commit frees ring slots (in both CTAs) and hands
 //                           the finished accumulator to the epilogue warps (of both CTAs)
@@ -21,7 +21,12 @@
 // Operand "majors" are encoded in the UMMA descriptors, so y = x w^T (K-major A, B), dx = dy w
 // (B MN-major) and dw = dy^T x (A and B MN-major) run without transposes in HBM.
 // Split-K (weight gradients: tiny output, K = B*L rows): fp32 slices are summed into C by TMA
-// reduce-add; bf16 outputs use a caller-provided workspace + a fixed-order reduce kernel.
+// reduce-add (C zero-filled here unless the caller says it already is); bf16 outputs use a
+// caller-provided workspace + a fixed-order reduce kernel.
+// Grouped launches: up to MAXG independent problems (own tensor maps and epilogue flags) share one
+// persistent grid; work items are numbered problem by problem.  The kernel is launched with
+// programmatic stream serialization: its prologue runs while the previous kernel drains
+// (griddepcontrol.wait before the first global access).
 #include "common.cuh"
 #include "gemm.h"
 #include "tc_common.cuh"
