@@ -78,7 +78,6 @@ class FullAttentionBlock(nn.Module):
         self.a = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
         self.b = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
         self.c = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
-        self.emit_scores = True  # set False when nothing consumes the returned scores
 
     def _params(self) -> List[torch.Tensor]:
         return [self.w_qkv[0].weight, self.w_qkv[1].weight, self.w_qkv[2].weight, self.proj.weight,
@@ -97,7 +96,10 @@ class FullAttentionBlock(nn.Module):
         x = ops.linear(o, self.proj.weight, bf16=bf)
         return ops.dropout(x, self.drop.p, self.training), s
 
-    def forward(self, q, k, v, mask, scores=None):
+    def forward(self, q, k, v, mask, scores=None, emit_scores: bool = True):
+        """``emit_scores=False`` (not a reference argument; used by the fusion trunk for the last
+        layer of a chain, whose scores feed nothing) skips writing the score tensor and returns
+        ``(q, None)``; the default returns the scores like the reference."""
         bf = is_bf16()
         fused = (k is v) and not (self.training and self.drop.p > 0)
         if fused:  # one autograd node for the whole block
@@ -105,7 +107,7 @@ class FullAttentionBlock(nn.Module):
             q = as_act(q)
             k = q if same else as_act(k)
             out = ops.block_full_op(q, k, as_mask(mask), scores, self._params(), self.n_heads, bf,
-                                    self.emit_scores, q is k)
+                                    emit_scores, q is k)
             s = out[1]
             return out[0], (s if s.numel() else None)
         x, s = self.multi_head_attention(q, k, v, mask, scores)
@@ -133,7 +135,6 @@ class LiteAttentionBlock(nn.Module):
         setattr(self, norm_name, nn.LayerNorm(dim))
         self._norm_name = norm_name
         self.c = nn.Parameter(torch.FloatTensor([0]), requires_grad=True)
-        self.emit_scores = True
 
     @property
     def _norm(self) -> nn.LayerNorm:
@@ -146,7 +147,7 @@ class LiteAttentionBlock(nn.Module):
         x = ops.linear(o, self.proj.weight, bf16=bf)
         return ops.dropout(x, self.drop.p, self.training), s
 
-    def forward(self, q, k, v, mask, scores=None):
+    def forward(self, q, k, v, mask, scores=None, emit_scores: bool = True):
         bf = is_bf16()
         n = self._norm
         fused = (k is v) and not (self.training and self.drop.p > 0)
@@ -156,7 +157,7 @@ class LiteAttentionBlock(nn.Module):
             k = q if same else as_act(k)
             out = ops.block_lite_op(q, k, as_mask(mask), scores,
                                     [self.proj.weight, self.minus.weight, n.weight, n.bias, self.c],
-                                    self.n_heads, bf, self.emit_scores)
+                                    self.n_heads, bf, emit_scores)
             s = out[1]
             return out[0], (s if s.numel() else None)
         x, s = self.multi_head_attention(q, k, v, mask, scores)
@@ -182,8 +183,8 @@ def fusion_trunk(blocks: Sequence[nn.Module], n_layers: int, feats: Dict[str, to
         src, m = feats[sm], masks[sm]
         for i in range(n_layers):
             blk = blocks[n_layers * ci + i]
-            blk.emit_scores = i + 1 < n_layers      # the last layer's scores feed nothing
-            q, s = blk(q, src, src, m, s)
+            # the last layer's scores feed nothing: do not write them
+            q, s = blk(q, src, src, m, s, emit_scores=i + 1 < n_layers)
             if keep_all:
                 outs[qm].append(q)
         if not keep_all:

@@ -154,14 +154,30 @@ class GradReducer:
         e.g. GPUs without peer access, or a torch build without symmetric memory)."""
         import sys
         flat, bases, err = None, [0] * len(sizes), None
+        # vote on what every rank can check locally (import, device, peer access) BEFORE entering
+        # the collective rendezvous: a rank that failed here would otherwise leave the others
+        # hanging inside symm_mem.rendezvous
         try:
-            flat, bases = self._alloc_symmetric(sizes, device)
-        except Exception as ex:      # noqa: BLE001 - any setup failure means "not available here"
+            import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+            if device.type != "cuda":
+                raise RuntimeError("symmetric memory needs CUDA tensors")
+            me = device.index if device.index is not None else torch.cuda.current_device()
+            for peer in range(torch.cuda.device_count()):
+                if peer != me and not torch.cuda.can_device_access_peer(me, peer):
+                    raise RuntimeError(f"no peer access between GPU {me} and GPU {peer}")
+        except Exception as ex:      # noqa: BLE001
             err = ex
         ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
         if float(ok.item()) == 1.0:
-            return flat, bases
+            try:
+                flat, bases = self._alloc_symmetric(sizes, device)
+            except Exception as ex:  # noqa: BLE001 - any setup failure means "not available here"
+                err = ex
+            ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            if float(ok.item()) == 1.0:
+                return flat, bases
         if self._requested_transport == "symm":
             raise RuntimeError(f"symmetric-memory gradient transport unavailable: {err!r}")
         if dist.get_rank(self.group) == 0:
@@ -258,9 +274,17 @@ class GradReducer:
             b.pending = len(b.params)
             b.work = None
             b.todo = []
-            # writing gradients straight into the bucket is only sound when autograd will ASSIGN
-            # (p.grad is None), not accumulate into the very same memory
-            in_place_ok = in_place_ok and all(p.grad is None for p in b.params)
+            # After a step p.grad is a view of its all-reduce bucket and holds the AVERAGED gradient.
+            # A second backward() without zero_grad(set_to_none=True) would make autograd accumulate
+            # the new local gradient into that view and the whole bucket would be SUM-reduced again
+            # (the old contribution multiplied by the world size) - refuse instead of training on
+            # silently wrong gradients.  The reference loops call optimizer.zero_grad() before every
+            # backward (others/realformer.py:305), whose default is set_to_none=True.
+            if any(p.grad is not None for p in b.params):
+                raise RuntimeError(
+                    "GradReducer.backward(): parameters still hold gradients from the previous "
+                    "step; call optimizer.zero_grad() / model.zero_grad(set_to_none=True) first "
+                    "(gradient accumulation across backward() calls is not supported)")
         if self.zero_copy:
             from . import ops
             ops.grad_dest_enabled = in_place_ok

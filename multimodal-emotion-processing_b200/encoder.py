@@ -22,6 +22,6 @@ class ResidualEncoder(nn.Module):
         q, s = x, None
         n = len(self.blocks)
         for i, blk in enumerate(self.blocks):
-            blk.emit_scores = i + 1 < n      # the last layer's scores feed nothing
-            q, s = blk(q, x, x, mask, s)
+            # the last layer's scores feed nothing: do not write them
+            q, s = blk(q, x, x, mask, s, emit_scores=i + 1 < n)
         return q

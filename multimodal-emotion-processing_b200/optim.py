@@ -128,6 +128,10 @@ class _FusedAdam(torch.optim.Optimizer):
                           float(self.max_grad_norm or 0.0), ops._stream())
                 for p in pp:
                     self.state[p]["step"] += 1
+                # the launch wrote the parameters through raw pointers: bump their version counters
+                # so that everything keyed on them (the bf16 weight shadows of ops.shadow_bf16,
+                # autograd's saved-tensor checks) sees the update like after an in-place torch op
+                torch._C._increment_version(pp)
         return loss
 
 

@@ -89,12 +89,19 @@ def test_state_dict_round_trip_with_torch_optim():
     assert float(back.state[back.param_groups[0]["params"][0]]["step"]) == 2
 
 
-def test_training_loop_with_fused_optimizer_tracks_torch():
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_training_loop_with_fused_optimizer_tracks_torch(prec):
     """cmu-mosei Concat_Trans, 20 steps of the reference loop's  backward -> clip -> AdamW  with the
-    fused optimizer vs torch.optim on an identical model copy: same loss curve."""
-    from mmemo_b200 import cmu_mosei, synth
+    fused optimizer vs torch.optim on an identical model copy: same loss curve.  In bf16 mode the
+    GEMMs read bf16 shadows of the float32 masters, keyed on the parameters' version counters: the
+    fused step (which writes through raw pointers) must invalidate them, or training would keep
+    running on the initial weights while the masters move on."""
+    import mmemo_b200
+    from mmemo_b200 import cmu_mosei, ops, synth
     from mmemo_b200.cmu_mosei import multi_circle_loss
 
+    mmemo_b200.set_precision(prec)
+    ops.clear_shadow_cache()
     torch.manual_seed(0)
     model = cmu_mosei.Concat_Trans(96, 50, 50, 50, 6, 2, 1)
     model.load_state_dict(synth.randomize_gates(model.state_dict(), seed=2))
@@ -114,8 +121,11 @@ def test_training_loop_with_fused_optimizer_tracks_torch():
                 torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
             o.step()
             ls.append(float(loss.detach()))
+    mmemo_b200.set_precision("fp32")
     assert l1s[-1] < l1s[0]
     for a, b in zip(l1s, l2s):
         # (atomics reorder fp32 sums, so the two runs are not bit-identical; SURVEY's bar for a
         # loss curve is 1 %)
         assert abs(a - b) <= 5e-3 * max(1.0, abs(b)), (l1s, l2s)
+    # the fused step bumped the version counters like torch.optim's in-place update does
+    assert all(p._version > 0 for p in m1.parameters() if p.grad is not None)

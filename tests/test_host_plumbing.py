@@ -79,12 +79,26 @@ def test_unfused_paths_when_k_is_not_v(stub):
     assert out.shape == (2, 5, 16)
 
 
-def test_trunk_skips_unused_score_writes(stub):
+def test_trunk_skips_unused_score_writes(stub, monkeypatch):
+    """The last layer of a chain must not write its scores (nothing consumes them), and the drop-in
+    blocks themselves keep returning scores afterwards (emit_scores is a per-call argument, not
+    module state)."""
+    emitted = []
+    real = ops.block_lite_op
+
+    def spy(q, kv, mask, s_prev, params, H, bf16, emit_s):
+        emitted.append(emit_s)
+        return real(q, kv, mask, s_prev, params, H, bf16, emit_s)
+
+    monkeypatch.setattr(ops, "block_lite_op", spy)
     m = mmemo_b200.cmu_mosei.Multi_ATTN(16, 4, 5, 6, 2, 2, 1, l_dim=8, v_dim=6, a_dim=7)
     m(torch.randn(2, 4, 8), torch.randn(2, 5, 6), torch.randn(2, 6, 7), torch.ones(2, 4),
       torch.ones(2, 5), torch.ones(2, 6))
-    flags = [b.emit_scores for b in m.multimodal_blocks]
-    assert flags == [True, False] * 9
+    assert emitted == [True, False] * 9
+    blk = m.multimodal_blocks[1]                  # a last-layer block, called directly
+    x = torch.randn(2, 4, 16)
+    out, s = blk(x, x, x, torch.ones(2, 4))
+    assert s is not None and s.shape == (2, 2, 4, 4)
 
 
 def test_shadow_cache_tracks_parameter_version(stub):
