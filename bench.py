@@ -15,9 +15,15 @@ their 0 init every attention/FFN gradient is exactly zero).
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events around K
 CUDA-graph replays, max over ranks); `e2e` = the same step driven from pinned HOST buffers through
 the public module API with the H2D copy of the inputs and the D2H read of the loss inside the
-timed region; `roofline` = the dominant kernel family timed live with CUDA events in an
-instrumented eager step; `cpu_baseline` = the oracle (CPU port of the reference algorithm) timed on
-this box's host cores on a bounded sample.
+timed region; `roofline` = the dominant kernel family timed live with CUDA events (L2 flushed
+before every launch for HBM-bound families; the L2-warm time is reported next to it);
+`cpu_baseline` = the oracle (CPU port of the reference algorithm) timed on this box's host cores
+on a bounded sample; `gpu_eager_baseline` = the same oracle (= the reference's eager PyTorch op
+sequence) run on this GPU; `configs` = the other BASELINE.json configurations (the reference's
+real models: State_Transfer, Concat_Trans, Concat_Linear, Base_model at global batch 256 sharded
+over the ranks = the strong-scaling curve, robot_demo ensemble p50 latency), each with its own
+device-timed value, e2e, launch count, kernel table and baselines; `dp` (N > 1) = which gradient
+transport ran, the exposed communication time and a check of the reduced gradients.
 """
 from __future__ import annotations
 
@@ -198,28 +204,46 @@ def _algorithmic(name: str, a: tuple):
     return 0, 0, ""
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the bench workload's kernels, from the
-# one `ncu --set full` capture committed under profiles/ (cold caches; a profiler number, constant
-# for a given shape -- it is reported next to the live timing, never measured inside bench.py)
-NCU_DRAM_SOURCE = "profiles/r01_ncu_full_backward_kernels.csv"
-NCU_DRAM_BYTES = {
-    "linear_bwd_w_grouped_bf16:8192x512x1024+8192x1024x512+8192x512x512+8192x512x512+8192x1024x512":
-        117.48e6 + 4.55e6,
-    "resattn_bwd_bf16:B64H8L128x128hd64+S+prev+dSnext": 84.53e6 + 12.28e6,
-    "add_ln_bwd_bf16:8192x512": 25.28e6 + 0.03e6,
-}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the bench workload's kernels: read
+# from profiles/ncu_traffic.json, which tools/ncu_traffic.py writes from the `ncu --set full`
+# capture committed under profiles/ (a profiler number for a given shape, reported next to the live
+# timing; it is never measured inside bench.py and never hard-coded here)
+NCU_TRAFFIC_FILE = os.path.join(ROOT, "profiles", "ncu_traffic.json")
 
 
-def instrumented_step(step_fn, reps: int = 10):
+def ncu_traffic():
+    try:
+        with open(NCU_TRAFFIC_FILE) as fh:
+            d = json.load(fh)
+        return d.get("families", {}), d.get("source")
+    except Exception:
+        return {}, None
+
+
+_FLUSH = {}
+
+
+def flush_l2():
+    """Evict the L2 (126 MB) by READING a 256 MB buffer (leaves clean lines, unlike a fill)."""
+    dev = torch.cuda.current_device()
+    buf = _FLUSH.get(dev)
+    if buf is None:
+        buf = _FLUSH[dev] = torch.zeros(64 << 20, dtype=torch.int32, device=f"cuda:{dev}")
+    return buf.amax()
+
+
+def instrumented_step(step_fn, reps: int = 10, cold: bool = True):
     """Per-kernel device time, measured live with CUDA events.
 
     One eager step is run with a hook on every libmmemo launch.  Timing a launch in place with an
     event pair would mostly measure the host (an eager step is launch-bound: the GPU idles between
-    kernels), so the FIRST launch of every kernel family (entry point + shape) is re-issued `reps`
-    times from a small CUDA graph while its argument buffers are still alive, and the graph replay
-    is timed with events on its stream.  Inputs are L2-warm, as in the real step where the
-    producer kernel has just written them.  Returns {family: dict(n, ms, flops, bytes)} with ms =
-    launches-per-step x measured time per launch."""
+    kernels), so the FIRST launch of every kernel family (entry point + shape) is re-issued while
+    its argument buffers are still alive:
+      * warm: `reps` times back to back from a small CUDA graph (inputs L2-resident, as for a
+        consumer that runs right after its producer inside the real step);
+      * cold: 5 times, each after the L2 was evicted by reading a 256 MB buffer, timed by an event
+        pair around the single launch (includes ~1-2 us of launch gap) - the honest HBM number.
+    Returns {family: dict(n, ms_each (warm), ms_cold, flops, bytes)}."""
     from mmemo_b200 import ops
     real = ops._call
     fam = {}
@@ -250,6 +274,19 @@ def instrumented_step(step_fn, reps: int = 10):
             torch.cuda.synchronize()
             return s.elapsed_time(e) / reps
 
+    def measure_cold(name, args):
+        ts = []
+        for _ in range(5):
+            flush_l2()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            real(name, *args)
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ts.sort()
+        return ts[len(ts) // 2]
+
     def hooked(name, *args):
         real(name, *args)
         fl, by, tag = _algorithmic(name, args)
@@ -257,6 +294,7 @@ def instrumented_step(step_fn, reps: int = 10):
         r = fam.get(key)
         if r is None:
             r = fam[key] = dict(n=0, ms_each=measure(name, args), flops=0, bytes=0)
+            r["ms_cold"] = measure_cold(name, args) if cold else None
         r["n"] += 1
         r["flops"] += fl
         r["bytes"] += by
@@ -270,6 +308,38 @@ def instrumented_step(step_fn, reps: int = 10):
     for r in fam.values():
         r["ms"] = r["ms_each"] * r["n"]
     return fam, sum(r["ms"] for r in fam.values())
+
+
+def kernel_table(fam, pk, top: int = 12):
+    """Rows of the per-kernel roofline table.  Bound = tensor when the arithmetic intensity is
+    above the ridge, else hbm.  `frac` is computed from the COLD time for hbm-bound families and
+    from the in-step-like warm time for tensor-bound ones; both fractions are listed."""
+    ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
+    ksum = sum(r["ms"] for r in fam.values())
+    rows = []
+    for key, r in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        ai = r["flops"] / r["bytes"] if r["bytes"] else 0.0
+        bound = "tensor" if ai > ridge else "hbm"
+        work = (r["flops"] / 1e12) if bound == "tensor" else (r["bytes"] / 1e9)
+        peak = pk["tf_sust"] if bound == "tensor" else pk["hbm"]
+        warm_s = r["ms"] * 1e-3
+        cold_s = (r["ms_cold"] * r["n"] * 1e-3) if r.get("ms_cold") else None
+        ach_warm = work / warm_s if warm_s else 0.0
+        ach_cold = work / cold_s if cold_s else None
+        use_cold = bound == "hbm" and ach_cold is not None
+        ach = ach_cold if use_cold else ach_warm
+        row = {"kernel": key, "launches": r["n"], "us_per_launch": 1e3 * r["ms"] / r["n"],
+               "us_per_launch_cold": None if r.get("ms_cold") is None else 1e3 * r["ms_cold"],
+               "share": r["ms"] / ksum if ksum else 0.0, "bound": bound, "achieved": ach,
+               "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+               "frac": ach / peak if peak else None,
+               "frac_l2_warm": ach_warm / peak if peak else None,
+               "frac_cold": None if ach_cold is None else ach_cold / peak,
+               "timing": "cold (L2 flushed)" if use_cold else "L2-warm graph replay"}
+        if bound == "tensor":
+            row["frac_of_burst_peak"] = ach / pk["tf_burst"]
+        rows.append(row)
+    return rows[:top], ksum
 
 
 # ------------------------------------------------------------------------------------------------
@@ -313,10 +383,12 @@ def time_cpu(steps: int, warmup: int, batch_size: int):
 
 def run_reference(args, rank):
     """--impl reference: the reference algorithm's CPU path (oracle port; the reference scripts are
-    not importable and /root/reference does not exist on the GPU box) on all host cores."""
+    not importable and /root/reference does not exist on the GPU box) on all host cores, for
+    exactly --steps timed steps after --warmup warm-ups (one step = fwd+bwd of one B=64 batch,
+    ~0.2-0.5 s on 16-32 cores)."""
     if rank != 0:
         return
-    steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    steps, warm = max(1, args.steps), max(0, args.warmup)
     B = CFG["batch_per_gpu"]
     v, ms = time_cpu(steps, warm, B)
     cores = torch.get_num_threads()
@@ -346,6 +418,176 @@ def workload_config(n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (the reference's real models)
+# ------------------------------------------------------------------------------------------------
+def _median(ts):
+    ts = sorted(ts)
+    return ts[len(ts) // 2]
+
+
+def oracle_baselines(wl, want_cpu: bool, want_gpu: bool, dev):
+    """(cpu_baseline, gpu_eager_baseline) of a training workload: the oracle = the reference's
+    eager PyTorch op sequence, on the host cores and on this GPU (fp32 with TF32 off = the
+    reference as written; bf16 = the same modules cast with .bfloat16())."""
+    import benchlib
+    from oracle import mmemo_oracle as O
+    cpu = gpu = None
+    n = wl.batch * wl.samples_per_item
+    if want_cpu:
+        torch.set_num_threads(os.cpu_count() or 1)
+        step = benchlib.oracle_train_step(O, wl, "cpu")
+        ts = benchlib.time_wall(step, 2, 1)
+        med = _median(ts)
+        cpu = {"value": n / med, "unit": "samples/s", "cores": torch.get_num_threads(),
+               "kind": "port", "sample": f"2 fwd+bwd steps of one B={wl.batch} batch after 1 warm-up, "
+                                         f"fp32 oracle, {med * 1e3:.0f} ms/step"}
+    if want_gpu:
+        gpu = {"what": "reference op sequence (oracle) as eager PyTorch on this GPU, fwd+bwd, "
+                       "device-resident inputs; TF32 off", "unit": "samples/s"}
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        for tag, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+            try:
+                step = benchlib.oracle_train_step(O, wl, dev, dt)
+
+                def run():
+                    step()
+                    torch.cuda.synchronize()
+                ts = benchlib.time_wall(run, 5, 2)
+                gpu[tag] = n / _median(ts)
+                gpu[tag + "_ms_per_step"] = _median(ts) * 1e3
+            except Exception as ex:  # e.g. out of memory for the eager score tensors
+                gpu[tag] = None
+                gpu[tag + "_error"] = f"{type(ex).__name__}: {str(ex)[:120]}"
+            torch.cuda.empty_cache()
+    return cpu, gpu
+
+
+def measure_train_config(key, batch, dev, rank, world, K, W, barrier, allreduce_max, pk,
+                         reducer_factory=None, shard=None, baselines=True, scaling=None,
+                         instrument=True):
+    """Device-timed value, e2e, launch count, per-kernel table and baselines of one training
+    workload.  With `shard` = (rank, world) the batch is the GLOBAL batch and every rank runs its
+    contiguous 1/world slice (strong scaling)."""
+    import benchlib
+    wl = benchlib.WORKLOADS[key](batch)
+    local = wl
+    if shard is not None:
+        from mmemo_b200 import dp as mdp
+
+        class _Sharded(type(wl)):
+            def host_batch(self_inner, seed):
+                return mdp.shard_batch(wl.host_batch(seed), shard[0], shard[1], align=2)
+        local = _Sharded(batch)
+    gs = benchlib.GraphedStep(local, dev, seed=1234, reducer_factory=reducer_factory)
+    ms = allreduce_max(benchlib.time_events(gs.run, K, W, barrier))
+    n_global = batch * wl.samples_per_item * (1 if shard is not None else world)
+    value = n_global * K / (ms * 1e-3)
+    # e2e: pinned host inputs -> H2D -> step -> loss D2H, synchronous every step
+    for _ in range(2):
+        gs.run_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        last = gs.run_e2e()
+    e2e_ms = allreduce_max((time.perf_counter() - t0) * 1e3)
+    out = {"name": wl.name, "baseline_config": wl.cfg, "workload": wl.description,
+           "metric": wl.metric, "unit": "samples/s", "value": value, "ms_per_step": ms / K,
+           "global_batch": n_global,
+           "batch_per_gpu": batch * wl.samples_per_item // (shard[1] if shard is not None else 1),
+           "scaling": scaling, "n_gpus": world, "steps": K, "warmup": W,
+           "launches_per_step": gs.launches, "cuda_graph": gs.graph is not None, "loss": last,
+           "e2e": {"value": n_global * K / (e2e_ms * 1e-3), "unit": "samples/s",
+                   "ms_per_step": e2e_ms / K, "h2d_bytes_per_step": gs.h2d_bytes(),
+                   "d2h_bytes_per_step": 4,
+                   "how": "pinned host batch -> cudaMemcpyAsync -> graph replay -> loss D2H, "
+                          "stream synchronised every step (no pipelining)"}}
+    if rank == 0 and instrument:
+        red = gs.reducer
+        if red is not None:
+            red.enabled = False
+        fam, _ = instrumented_step(gs._step, reps=5)
+        if red is not None:
+            red.enabled = True
+        rows, ksum = kernel_table(fam, pk, top=8)
+        out["kernels"] = rows
+        out["kernel_time_sum_ms"] = ksum
+        out["kernel_families"] = len(fam)
+    del gs
+    torch.cuda.empty_cache()
+    if rank == 0 and baselines:
+        cpu, gpu = oracle_baselines(wl, world == 1, world == 1, dev)
+        out["cpu_baseline"], out["gpu_eager_baseline"] = cpu, gpu
+    return out
+
+
+def measure_robot_ensemble(dev, n_requests: int = 200, baselines: bool = True):
+    """BASELINE configs[4]: p50 request latency of the 4-model robot_demo ensemble at B=1 and
+    B=32.  One request = pinned host inputs -> H2D -> Ensemble (one CUDA-graph replay) -> D2H of the
+    (B,7) prediction, wall clock per request after a stream synchronise."""
+    import benchlib
+    import mmemo_b200
+    from mmemo_b200 import ops
+    res = {"name": benchlib.Cfg5.name, "baseline_config": benchlib.Cfg5.cfg,
+           "workload": benchlib.Cfg5.description, "metric": benchlib.Cfg5.metric, "unit": "ms",
+           "higher_is_better": False, "requests": n_requests, "batches": {}}
+    for B in (1, 32):
+        wl = benchlib.Cfg5(B)
+        models, sds = wl.models()
+        models = [m.to(dev) for m in models]
+        ens = mmemo_b200.robot_demo.Ensemble(models)
+        hb = wl.host_batch(77)
+        host = [hb[k].pin_memory() for k in wl.NAMES]
+        stat = [t.to(dev) for t in host]
+        out_host = torch.zeros(B, 7, pin_memory=True)
+
+        def request():
+            for s_, h_ in zip(stat, host):
+                s_.copy_(h_, non_blocking=True)
+            pred = ens(*stat)
+            out_host.copy_(pred, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        n0 = ops.launch_count
+        request()
+        launches = ops.launch_count - n0          # launches captured into the request graph
+        ts = sorted(benchlib.time_wall(request, n_requests, 10))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(50):
+            ens(*stat)
+        e1.record()
+        torch.cuda.synchronize()
+        r = {"p50_ms": ts[len(ts) // 2] * 1e3, "p90_ms": ts[int(len(ts) * 0.9)] * 1e3,
+             "min_ms": ts[0] * 1e3, "device_ms": e0.elapsed_time(e1) / 50,
+             "samples_per_s": B / ts[len(ts) // 2], "launches_per_request": launches,
+             "h2d_bytes_per_request": sum(t.numel() * 4 for t in host),
+             "d2h_bytes_per_request": B * 7 * 4}
+        if baselines:
+            from oracle import mmemo_oracle as O
+            torch.set_num_threads(os.cpu_count() or 1)
+            with torch.no_grad():
+                cpu_ts = benchlib.time_wall(lambda: wl.oracle_pred(O, sds, hb), 5, 1)
+                r["cpu_baseline_ms"] = _median(cpu_ts) * 1e3
+                r["cpu_cores"] = torch.get_num_threads()
+                sdg = [{k: v.to(dev) for k, v in sd.items()} for sd in sds]
+                hbg = {k: v.to(dev) for k, v in hb.items()}
+
+                def eager():
+                    p_ = wl.oracle_pred(O, sdg, hbg).cpu()
+                    return p_
+                r["gpu_eager_baseline_ms"] = _median(benchlib.time_wall(eager, 20, 3)) * 1e3
+                ref = wl.oracle_pred(O, sds, hb)
+            request()
+            r["max_abs_diff_vs_oracle"] = float((out_host - ref).abs().max())
+        res["batches"][f"B{B}"] = r
+        del ens, models
+        torch.cuda.empty_cache()
+    res["value"] = res["batches"]["B1"]["p50_ms"]
+    return res
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -355,6 +597,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="all",
+                    help="comma list of the extra BASELINE configs to measure "
+                         "(cfg1a,cfg1b,cfg3,cfg3c,cfg4,cfg5), 'all' or 'none'")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -446,6 +691,7 @@ def main():
         step()
         launches_per_step = ops.launch_count - n0
     run = graph.replay if graph is not None else step
+    cuda_graph = graph is not None
 
     def barrier():
         if world > 1:
@@ -532,44 +778,150 @@ def main():
 
     # ---- per-kernel roofline (rank 0, eager instrumented step) ------------------------------------
     roof, kernels = None, []
+    pk = peaks()
     if rank == 0:
         if reducer is not None:
             reducer.enabled = False
         fam, total_ms = instrumented_step(step)
         if reducer is not None:
             reducer.enabled = True
-        pk = peaks()
-        ridge = pk["tf_sust"] * 1e12 / (pk["hbm"] * 1e9)
-        ksum = sum(r["ms"] for r in fam.values())
-        for key, r in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
-            ai = r["flops"] / r["bytes"] if r["bytes"] else 0.0
-            bound = "tensor" if ai > ridge else "hbm"
-            t_s = r["ms"] * 1e-3
-            ach = (r["flops"] / t_s / 1e12) if bound == "tensor" else (r["bytes"] / t_s / 1e9)
-            peak = pk["tf_sust"] if bound == "tensor" else pk["hbm"]
-            kernels.append({"kernel": key, "launches": r["n"], "us_per_launch": 1e3 * r["ms"] / r["n"],
-                            "share": r["ms"] / ksum if ksum else 0.0, "bound": bound,
-                            "achieved": ach, "peak": peak,
-                            "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
-                            "frac": ach / peak if peak else None})
+        kernels, ksum = kernel_table(fam, pk)
         top = kernels[0]
-        traffic = next((v for k, v in NCU_DRAM_BYTES.items() if top["kernel"].startswith(k)), None)
+        traffic_tab, traffic_src = ncu_traffic()
+        traffic = traffic_tab.get(top["kernel"])
         roof = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"],
-                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
-                "traffic_source": NCU_DRAM_SOURCE if traffic else None,
+                "peak": top["peak"], "unit": top["unit"], "frac": top["frac"],
+                "frac_l2_warm": top["frac_l2_warm"], "frac_cold": top["frac_cold"],
+                "frac_of_burst_peak": top.get("frac_of_burst_peak"),
+                "traffic": traffic, "traffic_source": traffic_src if traffic else None,
                 "share_of_step": top["share"], "peak_source": pk["src"],
-                "how": "first launch of each kernel family re-issued 10x from a CUDA graph inside "
-                       "an eager step (buffers alive, L2-warm), graph replay timed with CUDA events; "
-                       "achieved = algorithmic bytes|flops per launch / time per launch",
+                "how": "first launch of each kernel family re-issued inside an eager step while its "
+                       "buffers are alive: 10x from a CUDA graph (L2-warm) and 5x each after an L2 "
+                       "flush (cold, event pair around the launch); achieved = algorithmic "
+                       "bytes|flops per launch / time per launch; hbm-bound families use the cold "
+                       "time, tensor-bound ones the warm (in-step-like) time",
                 "kernel_time_sum_ms": total_ms}
 
-    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------------
-    cpu = None
+    # ---- data-parallel evidence (N > 1): transport, exposed communication, reduced-gradient check --
+    dp_info = None
+    if reducer is not None:
+        # (a) step without the collectives (same bucket plumbing) -> exposed communication time
+        reducer.no_comm = True
+        g2 = None
+        try:
+            model.zero_grad(set_to_none=True)
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2):
+                step()
+        except Exception:
+            g2 = None
+            torch.cuda.synchronize()
+        run2 = g2.replay if g2 is not None else step
+        for _ in range(W):
+            run2()
+        barrier()
+        e0.record()
+        for _ in range(K):
+            run2()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_nocomm = float(t.item()) / K
+        reducer.no_comm = False
+        g2 = None
+        # (b) reduced gradients of a probe (first parameter of every bucket) vs an NCCL all-reduce
+        # of the ranks' local gradients
+        probes = [b.params[0] for b in reducer.buckets]
+        reducer.enabled = False
+        step()
+        ref = [p.grad.detach().clone() for p in probes]
+        for r_ in ref:
+            dist.all_reduce(r_, op=dist.ReduceOp.SUM)
+            r_.div_(world)
+        reducer.enabled = True
+        step()
+        torch.cuda.synchronize()
+        err = max(float((p.grad - r_).abs().max() / r_.abs().max().clamp_min(1e-30))
+                  for p, r_ in zip(probes, ref))
+        dp_info = {"transport": reducer.transport, "uses_multicast": reducer.uses_multicast,
+                   "kernel": "libmmemo allreduce_kernel (multimem.ld_reduce/st)"
+                             if reducer.transport == "symm" else "NCCL all_reduce",
+                   "buckets": len(reducer.buckets),
+                   "bucket_bytes": [int(b.flat.numel()) * 4 for b in reducer.buckets],
+                   "ms_per_step_without_comm": ms_nocomm,
+                   "exposed_comm_us": (ms_per_step - ms_nocomm) * 1e3,
+                   "grad_check": {"probe_tensors": len(probes), "max_rel_err": err,
+                                  "what": "max |reduced - allreduce(local)/N| / max |ref| over the "
+                                          "first parameter of every bucket"}}
+
+    # ---- CPU baseline + eager-PyTorch-on-this-GPU baseline (rank 0, N=1 only) -----------------------
+    cpu, gpu_eager = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cms = time_cpu(3, 1, B)
         cpu = {"value": v, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"3 fwd+bwd steps of one B={B} batch (same shapes/seeds), fp32 oracle, "
                          f"median, {cms:.0f} ms/step"}
+        gpu_eager = {"what": "reference op sequence (oracle) as eager PyTorch on this GPU, fwd+bwd, "
+                             "device-resident inputs, TF32 off", "unit": "samples/s"}
+        for tag, dt in (("fp32", torch.float32), ("bf16", torch.bfloat16)):
+            sd_g = {k: v_.to(dev, dt).requires_grad_(True) for k, v_ in sd.items()}
+            from oracle import mmemo_oracle as O
+            pres = [f"blocks.{i}." for i in range(CFG["n_layers"])]
+            xg, mg = x_dev.to(dt), m_dev.to(dt)
+
+            def eager_step():
+                for v_ in sd_g.values():
+                    v_.grad = None
+                out = O.encoder_chain(sd_g, pres, xg, mg, CFG["n_heads"])[0]
+                (out.float() ** 2).mean().backward()
+                torch.cuda.synchronize()
+            import benchlib
+            ts = sorted(benchlib.time_wall(eager_step, 5, 2))
+            gpu_eager[tag] = B / ts[len(ts) // 2]
+            gpu_eager[tag + "_ms_per_step"] = ts[len(ts) // 2] * 1e3
+            del sd_g
+            torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs ------------------------------------------------------------------
+    graph = None
+    run = None
+    want = ["cfg1a", "cfg1b", "cfg3", "cfg3c", "cfg4", "cfg5"] if args.configs == "all" else \
+        ([] if args.configs == "none" else args.configs.split(","))
+    configs = []
+
+    def allreduce_max(ms_):
+        if world == 1:
+            return ms_
+        t_ = torch.tensor([ms_], device=dev)
+        dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    Kc = min(K, 20)
+    base = not args.no_cpu_baseline
+    for key in want:
+        try:
+            if key == "cfg4":
+                # global batch 256 sharded over the ranks (R-Drop pairs stay together): strong scaling
+                mk = None
+                if world > 1:
+                    mk = lambda m: mdp.GradReducer(m, world, bucket_bytes=4 << 20)   # noqa: E731
+                configs.append(measure_train_config(
+                    "cfg4", 256, dev, rank, world, Kc, W, barrier, allreduce_max, pk,
+                    reducer_factory=mk, shard=(rank, world), baselines=base, scaling="strong"))
+            elif world > 1:
+                continue        # single-GPU legs: reported by the N=1 run only
+            elif key == "cfg5":
+                configs.append(measure_robot_ensemble(dev, baselines=base))
+            else:
+                bsz = {"cfg1a": 32, "cfg1b": 32, "cfg3": 128, "cfg3c": 64}[key]
+                configs.append(measure_train_config(key, bsz, dev, rank, world, Kc, W, barrier,
+                                                    allreduce_max, pk, baselines=base))
+        except Exception as ex:   # a failed leg must not take the headline line down with it
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            configs.append({"name": key, "error": f"{type(ex).__name__}: {str(ex)[:200]}"})
+            torch.cuda.synchronize()
 
     if rank == 0:
         out = {
@@ -585,17 +937,16 @@ def main():
                            "one step later; all inside the timed region"},
             "gpu_launches": launches_per_step * K,
             "launches_per_step": launches_per_step,
-            "cuda_graph": graph is not None,
+            "cuda_graph": cuda_graph,
             "loss": last_loss,
-            "roofline": roof, "cpu_baseline": cpu, "kernels": kernels[:12],
+            "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "dp": dp_info,
+            "kernels": kernels[:12], "configs": configs,
         }
         print(json.dumps(out), flush=True)
     if world > 1:
-        # Tear down in a fixed order: drop the captured graph (it references NCCL kernels), drain
-        # the device, meet the other ranks, then leave without waiting on communicator teardown
-        # (destroy_process_group() was observed to block here after a captured all-reduce).
-        graph = None
-        run = None
+        # Tear down in a fixed order: drain the device, meet the other ranks, then leave without
+        # waiting on communicator teardown (destroy_process_group() was observed to block here
+        # after a captured all-reduce).
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()

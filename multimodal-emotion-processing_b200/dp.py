@@ -99,6 +99,7 @@ class GradReducer:
         self.world = world_size if world_size is not None else dist.get_world_size(group)
         self.bucket_bytes = bucket_bytes
         self.enabled = True
+        self.no_comm = _NO_COMM
         self.zero_copy = zero_copy
         self.buckets: List[_Bucket] = []
         # SMs left to the NCCL kernel of a bucket for the next `reserve_launches` GEMM launches after
@@ -251,7 +252,7 @@ class GradReducer:
                 for q, v in b.todo:
                     q.grad = v
                 b.todo = []
-            if _NO_COMM:
+            if self.no_comm:      # measurement knob: bucket plumbing without the collectives
                 return
             if self._symm is not None:
                 self._launch_symm(b)

@@ -9,7 +9,7 @@ product never imports it.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``be
 Pinning: the reference ships no tests or golden vectors for this path ("parity unpinned" by the
 reference itself).  The oracle is therefore pinned against *outputs of the reference's own classes*
 executed in the build container (``oracle/refload.py`` extracts them from ``/root/reference`` with
-``ast``; ``tests/test_oracle_vs_reference.py`` compares, ``tests/golden/make_golden.py`` freezes the
+``ast``; ``tests/test_oracle.py`` compares, ``tests/golden/make_golden.py`` freezes the
 reference outputs into ``tests/golden/*.pt`` so the comparison travels to boxes without
 ``/root/reference``).
 

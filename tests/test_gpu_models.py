@@ -194,32 +194,95 @@ def test_cfg2_encoder_chain_full_size_fp32_and_bf16():
         assert cos > 0.98, (k, cos.item())
 
 
-def test_cfg1b_mosei_native_lengths_forward():
-    """cmu-mosei/run.py native lengths 20/100/200 (9 (Lq,Lk) combinations), 1 layer."""
+def test_cfg1b_mosei_native_lengths_full_batch_with_gradients():
+    """cmu-mosei/run.py at its native lengths 20/100/200 (9 (Lq,Lk) combinations, Lk up to 200),
+    1 layer, FULL batch 32: logits, loss and every parameter gradient in float32; bf16 logits."""
     kw = dict(dim=96, l_len=20, v_len=100, a_len=200, n_heads=6, n_layers=1, ffn=1)
     m, sd = _model_and_state(lambda: mmemo_b200.cmu_mosei.Concat_Trans(**kw))
-    b = synth.mosei_batch(seed=1234, B=8)
+    b = synth.mosei_batch(seed=1234, B=32)
+    c = cases.CASES["mosei_concat_trans"]
+    nog = cases.Case(**{**c.__dict__, "grad_inputs": []})
+    fn = lambda s, bb: O.mosei_concat_trans(s, bb["l"], bb["v"], bb["a"], bb["l_mask"],
+                                            bb["v_mask"], bb["a_mask"], 6, 1)
+    ref_logits, ref_loss, ref_grads, _ = cases.run_with_grads(fn, sd, b, c.loss, O, [])
+    _, _, ref_grads64, _ = cases.run_with_grads(fn, f64(sd), f64(b), c.loss, O, [])
+    logits, loss, grads, _ = cases.run_module_with_grads(m, nog, to_dev(b), Loss)
+    assert rel_err(logits, ref_logits) < TOL32
+    assert abs(loss.item() - ref_loss.item()) < TOL32 * abs(ref_loss.item())
+    assert set(grads) == set(ref_grads)
+    assert_grads_close(grads, ref_grads, ref_grads64)
+    with mmemo_b200.precision("bf16"), torch.no_grad():
+        out_bf = cases._rf_call(m, to_dev(b))
+    assert rel_err(out_bf.float(), ref_logits) < TOLBF
+
+
+def test_cfg1a_realformer_full_size_bf16_logits():
+    kw = dict(l_dim=300, v_dim=35, a_dim=74, dim=96, l_len=50, v_len=50, a_len=50, n_heads=6,
+              n_layers=2, ffn=2)
+    m, sd = _model_and_state(lambda: mmemo_b200.realformer.State_Transfer(**kw))
+    b = synth.realformer_batch(seed=1234, B=32, P=6)
     with torch.no_grad():
-        ref = O.mosei_concat_trans(sd, b["l"], b["v"], b["a"], b["l_mask"], b["v_mask"], b["a_mask"],
-                                   6, 1)
-        out = cases._rf_call(m, to_dev(b))
-    assert rel_err(out, ref) < TOL32
+        ref = O.realformer_state_transfer(sd, b["l"], b["v"], b["a"], b["l_mask"], b["v_mask"],
+                                          b["a_mask"], 6, 2)
+        with mmemo_b200.precision("bf16"):
+            out = cases._rf_call(m, to_dev(b))
+    assert rel_err(out.float(), ref) < TOLBF
 
 
-def test_cfg4_renmme_native_shapes_with_rdrop_loss():
-    """Ren-MME/run.py defaults at a reduced batch (16): seq 40/76/275, dims 768/640/205, d=128."""
+def test_cfg4_renmme_full_batch_256_with_rdrop_loss():
+    """Ren-MME/run.py defaults at the FULL batch BASELINE names (256 = 128 R-Drop pairs): seq
+    40/76/275, dims 768/640/205, d=128, 8 heads: logits, loss (multi_loss + symmetric KL) and
+    every parameter gradient in float32; bf16 logits; bf16 training step runs (tiled Lk=275
+    backward) and its gradients point the same way."""
     m, sd = _model_and_state(lambda: mmemo_b200.ren_mme.Base_model())
-    b = synth.renmme_batch(seed=1234, B=16)
+    b = synth.renmme_batch(seed=1234, B=256)
     c = cases.CASES["renmme_base_model"]
-    ref_logits, ref_loss, ref_grads, _ = cases.run_with_grads(
-        lambda s, bb: O.renmme_base_model(s, *bb["inputs"]), sd, b, c.loss, O, [])
+    fn = lambda s, bb: O.renmme_base_model(s, *bb["inputs"])
+    ref_logits, ref_loss, ref_grads, _ = cases.run_with_grads(fn, sd, b, c.loss, O, [])
     logits, loss, grads, _ = cases.run_module_with_grads(m, c, to_dev(b), Loss)
     assert rel_err(logits, ref_logits) < TOL32
     assert abs(loss.item() - ref_loss.item()) < TOL32 * abs(ref_loss.item())
+    assert set(grads) == set(ref_grads)
     worst = max((rel_err(grads[k], v), k) for k, v in ref_grads.items())
     assert worst[0] < TOL32, worst
     # R-Drop pairs carry identical inputs and dropout is off -> identical logits
     assert torch.equal(logits[0::2], logits[1::2])
+    with mmemo_b200.precision("bf16"):
+        logits_bf, _, grads_bf, _ = cases.run_module_with_grads(m, c, to_dev(b), Loss)
+    assert rel_err(logits_bf.float(), ref_logits) < TOLBF
+    for k in ("intensity.multimodal_blocks.6.proj.weight", "stimulation.multimodal_blocks.8.minus.weight",
+              "intensity.unify_dimension.acoustic.weight", "stimulation.classifier.weight"):
+        a, r = grads_bf[k].flatten().double().cpu(), ref_grads[k].flatten().double()
+        cos = torch.dot(a, r) / (a.norm() * r.norm())
+        assert cos > 0.98, (k, cos.item())
+
+
+def test_cfg3_composite_text_encoder_full_size():
+    """BASELINE configs[2] as worded (seq 256, batch 128, RealFormer encoder): 6 x
+    Attention_Block(512, 8) on 64 (previous, current) sentence pairs = 128 sequences of 256 tokens
+    -> cls|max|mean pooling -> Concat_Linear(1536).  Oracle = composition of the reference
+    classes' restatements (benchlib.composite_oracle)."""
+    import benchlib
+    wl = benchlib.Cfg3Composite(64)
+    m, sd = _model_and_state(wl.model)
+    b = wl.host_batch(1234)
+    fn = lambda s, bb: benchlib.composite_oracle(O, s, bb["x"], bb["mask"])
+    loss_fn = lambda lg, bb, L: L.multi_circle_loss(lg, bb["label"]).mean()
+    ref_logits, ref_loss, ref_grads, _ = cases.run_with_grads(fn, sd, b, loss_fn, O, [])
+    _, _, ref_grads64, _ = cases.run_with_grads(fn, f64(sd), f64(b), loss_fn, O, [])
+    bd = to_dev(b)
+    m.zero_grad(set_to_none=True)
+    logits = m(bd["x"], bd["mask"])
+    loss = ops.circle_loss_op(logits, bd["label"]).mean()
+    loss.backward()
+    grads = {k: p.grad.detach() for k, p in m.named_parameters() if p.grad is not None}
+    assert rel_err(logits, ref_logits) < TOL32
+    assert abs(loss.item() - ref_loss.item()) < TOL32 * abs(ref_loss.item())
+    assert set(grads) == set(ref_grads)
+    assert_grads_close(grads, ref_grads, ref_grads64)
+    with mmemo_b200.precision("bf16"), torch.no_grad():
+        out_bf = m(bd["x"], bd["mask"])
+    assert rel_err(out_bf.float(), ref_logits) < TOLBF
 
 
 def test_cfg5_robot_demo_native_shapes_batch1_and_32():

@@ -163,7 +163,15 @@ def test_resattn_3d_mask_fp32():
     assert rel_err(od, o) < TOL32
 
 
-@pytest.mark.parametrize("shape", [(2, 6, 50, 50, 16), (2, 8, 128, 128, 64), (2, 8, 40, 275, 16)])
+# the shapes the reference's real models run in bf16 mode: cfg 1a (50,50,16), cfg 1b (20..200, 16),
+# cfg 4 (40/76/275, 16; Lk > 128 = the tiled backward), cfg 5 (25/100, 32), cfg 2 (128,128,64),
+# cfg 3 composite (256,256,64), plus ragged lengths
+BF16_SHAPES = [(2, 6, 50, 50, 16), (2, 8, 128, 128, 64), (2, 8, 40, 275, 16), (2, 8, 275, 275, 16),
+               (2, 6, 200, 100, 16), (2, 6, 20, 200, 16), (2, 8, 76, 40, 16), (2, 6, 25, 100, 32),
+               (2, 6, 100, 100, 32), (2, 8, 256, 256, 64), (1, 3, 7, 9, 16), (1, 2, 33, 65, 64)]
+
+
+@pytest.mark.parametrize("shape", BF16_SHAPES)
 @pytest.mark.parametrize("prev", [False, True])
 def test_resattn_bf16(shape, prev):
     B, H, Lq, Lk, hd = shape
@@ -179,7 +187,7 @@ def test_resattn_bf16(shape, prev):
     assert rel_err(sd.float().cpu()[valid], s[valid]) < TOLBF
 
 
-@pytest.mark.parametrize("shape", [(2, 6, 50, 50, 16), (3, 8, 128, 128, 64)])
+@pytest.mark.parametrize("shape", BF16_SHAPES + [(3, 8, 128, 128, 64)])
 @pytest.mark.parametrize("prev", [False, True])
 def test_resattn_bf16_backward(shape, prev):
     """bf16 backward (tcgen05 kernel for hd=64/L=128, SIMT otherwise) against the fp32 oracle run
