@@ -151,6 +151,46 @@ int mmemo_resattn_bwd_bf16(const void* d_o, int64_t lddo, const void* q, int64_t
 /* 1 if the tcgen05/TMA attention kernels serve this shape in the _bf16 build */
 int mmemo_resattn_uses_tensor_cores(int64_t Lq, int64_t Lk, int64_t hd, int64_t ld);
 
+/* Grouped residual attention (bf16): n <= 40 independent problems in ONE launch - the nine chains
+ * of a fusion-trunk layer (others/realformer.py:232-257, cmu-mosei/run.py:278-313,
+ * Ren-MME/run.py:230-265, robot_demo.py:399-434), both towers of Concat_Trans / Base_model
+ * (cmu-mosei/run.py:330-331, Ren-MME/run.py:283-284), the members of an ensemble
+ * (robot_demo.py:610-614).  Same math and argument meaning as mmemo_resattn_{fwd,bwd}_bf16, one
+ * struct per problem (HOST array; pointers inside are device pointers).  (B, Lk) masks only.
+ * `lds` is the row stride (elements) of all score-shaped tensors of the problem (s_prev, s_out,
+ * s, ds_next, ds_prev: (B, H, Lq, lds) with lds >= Lk; a multiple of 8 enables 16-byte accesses).
+ * All problems of a call share hd in {16, 32, 64}.  Runs on the warp-level tensor-core path
+ * (mma.sync m16n8k16).  Returns MMEMO_ERR_SHAPE when a problem is outside that kernel's limits
+ * (the caller then issues the problems one by one through the ungrouped entry points). */
+typedef struct mmemo_attn_problem {
+  const void *q, *k, *v;                 /* (B,Lq,H*hd), (B,Lk,H*hd) x2 */
+  int64_t ldq, ldk, ldv;
+  const float* mask;                     /* (B, Lk) float 0/1 or NULL */
+  int64_t mask_bs;
+  const void* s_prev;                    /* previous layer's scores or NULL */
+  const float* c;
+  void* s_out;                           /* fwd: scores out (nullable) */
+  int64_t lds;
+  void* o;                               /* fwd: out; bwd: the saved forward output */
+  int64_t ldo;
+  float* lse;                            /* (B,H,Lq,2): fwd out / bwd in */
+  int64_t B, H, Lq, Lk, hd;
+  /* backward only */
+  const void* d_o;
+  int64_t lddo;
+  const void* s;                         /* stored scores, or NULL -> recomputed */
+  const void* ds_next;                   /* gradient arriving at the returned scores or NULL */
+  void *dq, *dk, *dv;
+  int64_t lddq, lddk, lddv;
+  void* ds_prev;                         /* nullable */
+  float* dc;                             /* "+=" scalar, nullable */
+} mmemo_attn_problem;
+int mmemo_resattn_fwd_grouped_bf16(int n, const mmemo_attn_problem* problems, mmemo_stream_t stream);
+int mmemo_resattn_bwd_grouped_bf16(int n, const mmemo_attn_problem* problems, mmemo_stream_t stream);
+/* 1 if the problem shape (pointers may be dummy non-null, 16-byte aligned) is served by the
+ * mma.sync kernels; bwd != 0 asks about the backward */
+int mmemo_resattn_uses_mma(int64_t Lq, int64_t Lk, int64_t hd, int64_t ld, int same_kv, int bwd);
+
 /* ---------------------------------------------------------------------------------------------
  * Gated residual + LayerNorm (+ReLU).  y = act( LN( res + gate * x ) * gamma + beta ), eps 1e-5.
  * Replaces others/realformer.py:207-208,263  cmu-mosei/run.py:261  Ren-MME/run.py:166,213

@@ -30,6 +30,17 @@ _POOL_FWD = [_vp, _vp, _i32, _i32, _i64, _i64, _vp, _vp, _vp]
 _POOL_BWD = [_vp, _vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp]
 _DROPOUT = [_vp, _vp, _i64, _f32, _u64, _vp]
 
+class AttnProblem(C.Structure):
+    """mmemo_attn_problem of include/mmemo.h (field order and types must match)."""
+    _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("ldq", _i64), ("ldk", _i64), ("ldv", _i64),
+                ("mask", _vp), ("mask_bs", _i64), ("s_prev", _vp), ("c", _vp), ("s_out", _vp),
+                ("lds", _i64), ("o", _vp), ("ldo", _i64), ("lse", _vp),
+                ("B", _i64), ("H", _i64), ("Lq", _i64), ("Lk", _i64), ("hd", _i64),
+                ("d_o", _vp), ("lddo", _i64), ("s", _vp), ("ds_next", _vp),
+                ("dq", _vp), ("dk", _vp), ("dv", _vp), ("lddq", _i64), ("lddk", _i64),
+                ("lddv", _i64), ("ds_prev", _vp), ("dc", _vp)]
+
+
 SIGNATURES = {
     "mmemo_version": [],
     "mmemo_set_workspace": [_vp, _i64],
@@ -45,6 +56,9 @@ SIGNATURES = {
     "mmemo_linear_bwd_w_grouped_bf16": [_i32] + [_vp] * 9 + [_i32, _vp],
     "mmemo_resattn_fwd_f32": _ATTN_FWD, "mmemo_resattn_fwd_bf16": _ATTN_FWD,
     "mmemo_resattn_bwd_f32": _ATTN_BWD, "mmemo_resattn_bwd_bf16": _ATTN_BWD,
+    "mmemo_resattn_fwd_grouped_bf16": [_i32, _vp, _vp],
+    "mmemo_resattn_bwd_grouped_bf16": [_i32, _vp, _vp],
+    "mmemo_resattn_uses_mma": [_i64, _i64, _i64, _i64, _i32, _i32],
     "mmemo_add_ln_fwd_f32": _LN_FWD, "mmemo_add_ln_fwd_bf16": _LN_FWD,
     "mmemo_add_ln_bwd_f32": _LN_BWD, "mmemo_add_ln_bwd_bf16": _LN_BWD,
     "mmemo_rowsum_f32": _ROWSUM, "mmemo_rowsum_bf16": _ROWSUM,

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mmemo.h"
+
 int resattn_fwd_simt(int bf16_mode, const void* q, int64_t ldq, const void* k, int64_t ldk,
                      const void* v, int64_t ldv, const float* mask, int64_t mask_bs,
                      int64_t mask_rs, const void* s_prev, const float* c, void* s_out, void* o,
@@ -28,3 +30,8 @@ int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const
                    int64_t ldv, const float* mask, int64_t mask_bs, const void* s_prev,
                    const float* c, void* s_out, void* o, int64_t ldo, float* lse, int64_t B,
                    int64_t H, int64_t Lq, int64_t Lk, int64_t hd, cudaStream_t st);
+
+// mma.sync (m16n8k16 bf16) path: hd in {16, 32, 64}, any L that fits shared memory; grouped
+bool resattn_mma_supported(const mmemo_attn_problem& a, bool bwd);
+int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st);
+int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st);

@@ -1,0 +1,744 @@
+// Fused residual-attention core on the warp-level tensor-core path (mma.sync.m16n8k16, bf16
+// operands, fp32 accumulation) for the head sizes / lengths of the reference's real models:
+// hd = 16 (others/realformer.py, cmu-mosei/run.py, Ren-MME/run.py), hd = 32 (robot_demo.py),
+// hd = 64 with ragged lengths; any Lq, Lk (20 ... 275 in the reference configs).  tcgen05 tiles
+// (128 x N x 16, one head per CTA) do not fit 16-wide heads and 20..275-long sequences, so these
+// shapes run as 16-row warp tiles; the tcgen05 kernel (resattn_tc.cu) keeps hd = 64, L = 128.
+//
+// GROUPED: one launch serves up to MAXP independent problems (the nine chains of a fusion-trunk
+// layer, both towers of Concat_Trans / Base_model, the members of an ensemble) - the problem
+// table travels as a kernel parameter and blockIdx.x is mapped to (problem, batch, head, tile).
+//
+// Forward  (replaces others/realformer.py:189-203 and its twins): CTA = (b, h, 64 query rows),
+//   4 warps x 16 rows.  K_h, V_h (and the Q tile) are staged in shared memory by cp.async in an
+//   XOR-swizzled layout read back with ldmatrix; keys are walked in blocks of 64:
+//   S = Q K^T (mma) -> scale, + c*S_prev, - 1e8*(1-mask) in the reference's fp32 op order, bf16
+//   round -> S written -> online softmax (running max / sum, fp32) -> O += P V (mma, P from
+//   registers).  The n index of each 8-wide MMA tile is PERMUTED over the keys of a 32-key group
+//   (tile i, column n  <->  key 8*(n/2) + 2*i + n%2) so that a lane ends up owning 8 CONTIGUOUS
+//   keys of a row: S_prev / S / dS move as 16-byte vectors although the accumulator layout gives a
+//   lane only 2 adjacent columns per tile.  The permutation costs nothing: ldmatrix takes one row
+//   address per lane.
+// Backward (autograd of the above): CTA = (b, h), 8 warps, keys in blocks of KB (64 or 32).
+//   phase A (warp = 16 query rows): S (re-read, or recomputed by mma when it was not stored),
+//     P = exp(S - max)/sum, dP = dO V^T (mma), dS = P*(dP - D) + dS_next, dc += dS*S_prev,
+//     dS_prev = c*dS (16-byte stores), dQ += dS K (mma, fp32 tile in shared memory); P and dS of
+//     the block go to shared memory as bf16;
+//   phase B (warp = 16 keys x {dV, dK}): dV = P^T dO, dK = dS^T Q over ALL query rows (mma with
+//     ldmatrix.trans operands) - complete for the block, written straight to HBM.
+#include <math.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "resattn.h"
+
+namespace {
+
+constexpr int MAXP = 40;          // problems per launch
+constexpr int FWD_WARPS = 4, FWD_ROWS = 64;
+constexpr int BWD_WARPS = 8;
+constexpr size_t SMEM_MAX = 227 * 1024;
+
+struct Prob {
+  const bf16 *q, *k, *v;
+  const float* mask;
+  const bf16* s_prev;
+  const float* c;
+  bf16* s_out;
+  bf16* o;
+  float* lse;
+  // backward
+  const bf16 *d_o, *s, *ds_next, *o_in;
+  bf16 *dq, *dk, *dv, *ds_prev;
+  float* dc;
+  int ldq, ldk, ldv, ldo, lds, lddo, lddq, lddk, lddv, mask_bs;
+  int B, H, Lq, Lk;
+  int vec_s;        // score tensors may be accessed with 16-byte vectors
+  int cta_start;
+};
+
+struct Table {
+  int n, total;
+  float inv_sqrt;
+  Prob p[MAXP];
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;     // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_commit_wait() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+      "{%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ float round_bf(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// Shared-memory tile [rows][HD] of bf16, 16-byte chunks XOR-swizzled so that the 8 row addresses
+// of an ldmatrix fall into distinct bank groups for every HD (32 / 64 / 128-byte rows).
+template <int HD>
+__device__ __forceinline__ uint32_t sw(int row, int chunk) {
+  constexpr int RB = HD * 2, CPR = HD / 8, RP = 128 / RB;
+  return (uint32_t)(row * RB + ((chunk ^ ((row / RP) % CPR)) << 4));
+}
+// [rows][64] bf16 tiles (P, dS): 128-byte rows; [rows][32]: 64-byte rows
+template <int KB>
+__device__ __forceinline__ uint32_t swp(int row, int chunk) {
+  return sw<KB>(row, chunk);
+}
+
+// key of (tile i of a 32-key group, n index of the MMA tile): lanes end up with 8 contiguous keys
+__device__ __forceinline__ int perm_key(int i, int n) { return 8 * (n >> 1) + 2 * i + (n & 1); }
+
+// 8 consecutive bf16 of a score-shaped tensor -> fp32 (vector path when the row stride allows)
+__device__ __forceinline__ void load8(const bf16* p, int n_valid, bool vec, float (&v)[8]) {
+  if (vec && n_valid >= 8) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = bf_lo(w[i]); v[2 * i + 1] = bf_hi(w[i]); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (i < n_valid) ? __bfloat162float(p[i]) : 0.f;
+  }
+}
+__device__ __forceinline__ void store8(bf16* p, int n_valid, bool vec, const float (&v)[8]) {
+  if (vec && n_valid >= 8) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]),
+                                              pack2(v[4], v[5]), pack2(v[6], v[7]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (i < n_valid) p[i] = __float2bfloat16_rn(v[i]);
+  }
+}
+
+__device__ __forceinline__ const Prob& locate(const Table& T, int& local) {
+  int p = 0;
+  while (p + 1 < T.n && (int)blockIdx.x >= T.p[p + 1].cta_start) ++p;
+  local = (int)blockIdx.x - T.p[p].cta_start;
+  return T.p[p];
+}
+
+// stage `rows` rows of a (.., ld) bf16 matrix (head slice: HD columns starting at col0) into a
+// swizzled tile; rows >= n_rows are zero-filled
+template <int HD, int NT>
+__device__ __forceinline__ void stage(uint32_t dst, const bf16* src, int ld, int n_rows,
+                                      int rows_padded) {
+  constexpr int CPR = HD / 8;
+  for (int i = threadIdx.x; i < rows_padded * CPR; i += NT) {
+    const int r = i / CPR, ch = i - r * CPR;
+    const bool ok = r < n_rows;
+    cp16(dst + sw<HD>(r, ch), src + (size_t)(ok ? r : 0) * ld + ch * 8, ok);
+  }
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+template <int HD>
+__global__ void __launch_bounds__(FWD_WARPS * 32)
+resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  int local;
+  const Prob& P = locate(T, local);
+  const int Lq = P.Lq, Lk = P.Lk, H = P.H;
+  const int qtiles = (Lq + FWD_ROWS - 1) / FWD_ROWS;
+  const int qt = local % qtiles, bh = local / qtiles, h = bh % H, b = bh / H;
+  const int q0 = qt * FWD_ROWS;
+  const int LkP = (Lk + 63) & ~63;
+  const bool same_kv = (P.k == P.v) && (P.ldk == P.ldv);
+  const uint32_t sQ = s_u32(smem);
+  const uint32_t sK = sQ + FWD_ROWS * HD * 2;
+  const uint32_t sV = same_kv ? sK : sK + LkP * HD * 2;
+  float* sbias = reinterpret_cast<float*>(smem + FWD_ROWS * HD * 2 + (same_kv ? 1 : 2) * LkP * HD * 2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  pdl_wait();
+  pdl_trigger();
+  stage<HD, FWD_WARPS * 32>(sQ, P.q + ((size_t)b * Lq + q0) * P.ldq + h * HD, P.ldq,
+                            min(FWD_ROWS, Lq - q0), FWD_ROWS);
+  stage<HD, FWD_WARPS * 32>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
+  if (!same_kv) stage<HD, FWD_WARPS * 32>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
+  for (int j = threadIdx.x; j < LkP; j += FWD_WARPS * 32)
+    sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
+  cp_commit_wait();
+  __syncthreads();
+
+  const int r0 = q0 + warp * 16;          // first query row of this warp
+  if (r0 >= Lq) return;
+  const bool has_prev = P.s_prev != nullptr;
+  const float cval = (has_prev && P.c) ? P.c[0] : 0.f;
+  const float inv_sqrt = T.inv_sqrt;
+  const bool vec = P.vec_s != 0;
+  const int rowA = r0 + g, rowB = r0 + g + 8;
+  const bool okA = rowA < Lq, okB = rowB < Lq;
+  const size_t sbase = ((size_t)b * H + h) * Lq;
+
+  // Q fragments (A operand), all k-tiles
+  uint32_t qa[HD / 16][4];
+#pragma unroll
+  for (int kt = 0; kt < HD / 16; ++kt)
+    ldsm4(sQ + sw<HD>(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * kt + (lane >> 4)), qa[kt]);
+
+  float o[HD / 8][4];
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[n][e] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+
+  for (int kb = 0; kb < Lk; kb += 64) {
+    float sc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sc[i][e] = 0.f;
+    // ---- S = Q K^T : 2 groups of 32 keys x 4 permuted tiles ------------------------------------
+#pragma unroll
+    for (int G = 0; G < 2; ++G)
+#pragma unroll
+      for (int ip = 0; ip < 2; ++ip)
+#pragma unroll
+        for (int kt = 0; kt < HD / 16; ++kt) {
+          const int mi = lane >> 3, r = lane & 7;
+          const int tile = ip * 2 + (mi >> 1);
+          const int key = kb + 32 * G + perm_key(tile, r);
+          uint32_t kf[4];
+          ldsm4(sK + sw<HD>(key, 2 * kt + (mi & 1)), kf);
+          mma16816(sc[G * 4 + ip * 2], qa[kt], kf[0], kf[1]);
+          mma16816(sc[G * 4 + ip * 2 + 1], qa[kt], kf[2], kf[3]);
+        }
+    // ---- scale, + c*S_prev, - 1e8*(1-mask), bf16 round, store S; block max ----------------------
+    float bmax[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int G = 0; G < 2; ++G) {
+      const int k0 = kb + 32 * G + 8 * t;             // this lane's 8 contiguous keys
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = half ? rowB : rowA;
+        const bool row_ok = half ? okB : okA;
+        float pv[8];
+        if (has_prev && row_ok && k0 < Lk)
+          load8(P.s_prev + (sbase + row) * P.lds + k0, P.lds - k0, vec, pv);
+        float sv[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * i + e, key = k0 + j;
+            float s = sc[G * 4 + i][half * 2 + e] * inv_sqrt;
+            if (has_prev && row_ok && k0 < Lk) s = __fadd_rn(s, __fmul_rn(cval, pv[j]));
+            if (P.mask) s = __fsub_rn(s, sbias[min(key, LkP - 1)]);
+            s = round_bf(s);
+            sv[j] = key < Lk ? s : 0.f;
+            s = key < Lk ? s : -INFINITY;
+            sc[G * 4 + i][half * 2 + e] = s;
+            bmax[half] = fmaxf(bmax[half], s);
+          }
+        if (P.s_out && row_ok && k0 < P.lds)
+          store8(P.s_out + (sbase + row) * P.lds + k0, P.lds - k0, vec, sv);
+      }
+    }
+    // ---- online softmax ----------------------------------------------------------------------
+    float scale[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const float m_new = fmaxf(m_run[half], quad_max(bmax[half]));
+      scale[half] = __expf(m_run[half] - m_new);       // first block: exp(-inf) = 0
+      m_run[half] = m_new;
+      l_run[half] *= scale[half];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float p = __expf(sc[i][e] - m_run[e >> 1]);
+        sc[i][e] = p;
+        l_run[e >> 1] += p;
+      }
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n) {
+      o[n][0] *= scale[0]; o[n][1] *= scale[0];
+      o[n][2] *= scale[1]; o[n][3] *= scale[1];
+    }
+    // ---- O += P V : P from registers (A operand), V via ldmatrix.trans ---------------------------
+#pragma unroll
+    for (int G = 0; G < 2; ++G)
+#pragma unroll
+      for (int pp = 0; pp < 2; ++pp) {
+        if (kb + 32 * G >= Lk) continue;               // whole group beyond the keys (warp-uniform)
+        const int i0 = G * 4 + 2 * pp, i1 = i0 + 1;
+        uint32_t pa[4] = {pack2(sc[i0][0], sc[i0][1]), pack2(sc[i0][2], sc[i0][3]),
+                          pack2(sc[i1][0], sc[i1][1]), pack2(sc[i1][2], sc[i1][3])};
+#pragma unroll
+        for (int c2 = 0; c2 < HD / 8; c2 += 2) {
+          const int mi = lane >> 3, r = lane & 7;
+          const int key = kb + 32 * G + perm_key(2 * pp + (mi & 1), r);
+          uint32_t vf[4];
+          ldsm4t(sV + sw<HD>(key, c2 + (mi >> 1)), vf);
+          mma16816(o[c2], pa, vf[0], vf[1]);
+          mma16816(o[c2 + 1], pa, vf[2], vf[3]);
+        }
+      }
+  }
+  // ---- epilogue: normalise, write O (merged-head layout) and the (max, sum) pair ----------------
+  const float lA = quad_sum(l_run[0]), lB = quad_sum(l_run[1]);
+  const float iA = 1.f / lA, iB = 1.f / lB;
+#pragma unroll
+  for (int n = 0; n < HD / 8; ++n) {
+    if (okA)
+      *reinterpret_cast<uint32_t*>(P.o + ((size_t)b * Lq + rowA) * P.ldo + h * HD + 8 * n + 2 * t) =
+          pack2(o[n][0] * iA, o[n][1] * iA);
+    if (okB)
+      *reinterpret_cast<uint32_t*>(P.o + ((size_t)b * Lq + rowB) * P.ldo + h * HD + 8 * n + 2 * t) =
+          pack2(o[n][2] * iB, o[n][3] * iB);
+  }
+  if (t == 0 && P.lse) {
+    if (okA) { P.lse[2 * (sbase + rowA)] = m_run[0]; P.lse[2 * (sbase + rowA) + 1] = lA; }
+    if (okB) { P.lse[2 * (sbase + rowB)] = m_run[1]; P.lse[2 * (sbase + rowB) + 1] = lB; }
+  }
+}
+
+// =============================================================================================
+// backward
+// =============================================================================================
+template <int HD, int KB>
+__global__ void __launch_bounds__(BWD_WARPS * 32)
+resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
+  constexpr int NT = BWD_WARPS * 32;
+  constexpr int NG = KB / 32;              // 32-key groups per block
+  extern __shared__ __align__(128) uint8_t smem[];
+  int local;
+  const Prob& P = locate(T, local);
+  const int Lq = P.Lq, Lk = P.Lk, H = P.H;
+  const int h = local % H, b = local / H;
+  const int LqP = (Lq + 15) & ~15, LkP = (Lk + KB - 1) / KB * KB;
+  const bool same_kv = (P.k == P.v) && (P.ldk == P.ldv);
+  // carve-up: Q | dO | K | (V) | P | dS | dQ(fp32) | stat(m, 1/l, D) | bias
+  uint32_t off = 0;
+  const uint32_t sQ = s_u32(smem) + off;   off += LqP * HD * 2;
+  const uint32_t sdO = s_u32(smem) + off;  off += LqP * HD * 2;
+  const uint32_t sK = s_u32(smem) + off;   off += LkP * HD * 2;
+  uint32_t sV = sK;
+  if (!same_kv) { sV = s_u32(smem) + off;  off += LkP * HD * 2; }
+  const uint32_t sP = s_u32(smem) + off;   off += LqP * KB * 2;
+  const uint32_t sdS = s_u32(smem) + off;  off += LqP * KB * 2;
+  float* sdQ = reinterpret_cast<float*>(smem + off);    off += LqP * HD * 4;
+  float* sstat = reinterpret_cast<float*>(smem + off);  off += LqP * 3 * 4;
+  float* sbias = reinterpret_cast<float*>(smem + off);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+
+  pdl_wait();
+  pdl_trigger();
+  stage<HD, NT>(sQ, P.q + (size_t)b * Lq * P.ldq + h * HD, P.ldq, Lq, LqP);
+  stage<HD, NT>(sdO, P.d_o + (size_t)b * Lq * P.lddo + h * HD, P.lddo, Lq, LqP);
+  stage<HD, NT>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
+  if (!same_kv) stage<HD, NT>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
+  for (int j = threadIdx.x; j < LkP; j += NT)
+    sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
+  for (int i = threadIdx.x; i < LqP * HD; i += NT) sdQ[i] = 0.f;
+  const size_t sbase = ((size_t)b * H + h) * Lq;
+  // per-row statistics: max, 1/sum (saved by the forward), D = rowsum(dO * O)
+  for (int r = threadIdx.x; r < LqP; r += NT) {
+    float mx = 0.f, inv = 0.f, D = 0.f;
+    if (r < Lq) {
+      mx = P.lse[2 * (sbase + r)];
+      inv = 1.f / P.lse[2 * (sbase + r) + 1];
+      const bf16* dop = P.d_o + ((size_t)b * Lq + r) * P.lddo + h * HD;
+      const bf16* op = P.o_in + ((size_t)b * Lq + r) * P.ldo + h * HD;
+#pragma unroll
+      for (int c8 = 0; c8 < HD / 8; ++c8) {
+        const uint4 a = *reinterpret_cast<const uint4*>(dop + c8 * 8);
+        const uint4 o4 = *reinterpret_cast<const uint4*>(op + c8 * 8);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, ow[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          D = fmaf(bf_lo(aw[i]), bf_lo(ow[i]), fmaf(bf_hi(aw[i]), bf_hi(ow[i]), D));
+      }
+    }
+    sstat[3 * r] = mx; sstat[3 * r + 1] = inv; sstat[3 * r + 2] = D;
+  }
+  cp_commit_wait();
+  __syncthreads();
+
+  const bool has_prev = P.s_prev != nullptr;
+  const bool recompute = P.s == nullptr;
+  const float cval = (has_prev && P.c) ? P.c[0] : 0.f;
+  const float inv_sqrt = T.inv_sqrt;
+  const bool vec = P.vec_s != 0;
+  const int n_rt = LqP / 16;
+  float dc_part = 0.f;
+
+  for (int kb = 0; kb < Lk; kb += KB) {
+    // ================= phase A: one warp per 16-row tile ========================================
+    for (int rt = warp; rt < n_rt; rt += BWD_WARPS) {
+      const int rowA = rt * 16 + g, rowB = rowA + 8;
+      const bool okA = rowA < Lq, okB = rowB < Lq;
+      uint32_t doa[HD / 16][4];
+#pragma unroll
+      for (int kt = 0; kt < HD / 16; ++kt)
+        ldsm4(sdO + sw<HD>(rt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * kt + (lane >> 4)),
+              doa[kt]);
+      float sc[NG * 4][4], dp[NG * 4][4];
+#pragma unroll
+      for (int i = 0; i < NG * 4; ++i)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sc[i][e] = 0.f; dp[i][e] = 0.f; }
+      if (recompute) {
+        uint32_t qa[HD / 16][4];
+#pragma unroll
+        for (int kt = 0; kt < HD / 16; ++kt)
+          ldsm4(sQ + sw<HD>(rt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * kt + (lane >> 4)),
+                qa[kt]);
+#pragma unroll
+        for (int G = 0; G < NG; ++G)
+#pragma unroll
+          for (int ip = 0; ip < 2; ++ip)
+#pragma unroll
+            for (int kt = 0; kt < HD / 16; ++kt) {
+              const int mi = lane >> 3, r = lane & 7;
+              const int key = kb + 32 * G + perm_key(ip * 2 + (mi >> 1), r);
+              uint32_t kf[4];
+              ldsm4(sK + sw<HD>(key, 2 * kt + (mi & 1)), kf);
+              mma16816(sc[G * 4 + ip * 2], qa[kt], kf[0], kf[1]);
+              mma16816(sc[G * 4 + ip * 2 + 1], qa[kt], kf[2], kf[3]);
+            }
+      }
+      // dP = dO V^T
+#pragma unroll
+      for (int G = 0; G < NG; ++G)
+#pragma unroll
+        for (int ip = 0; ip < 2; ++ip)
+#pragma unroll
+          for (int kt = 0; kt < HD / 16; ++kt) {
+            const int mi = lane >> 3, r = lane & 7;
+            const int key = kb + 32 * G + perm_key(ip * 2 + (mi >> 1), r);
+            uint32_t vf[4];
+            ldsm4(sV + sw<HD>(key, 2 * kt + (mi & 1)), vf);
+            mma16816(dp[G * 4 + ip * 2], doa[kt], vf[0], vf[1]);
+            mma16816(dp[G * 4 + ip * 2 + 1], doa[kt], vf[2], vf[3]);
+          }
+      // elementwise: P, dS, dc, dS_prev; P / dS -> shared memory (bf16, natural key order)
+#pragma unroll
+      for (int G = 0; G < NG; ++G) {
+        const int k0 = kb + 32 * G + 8 * t;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int row = half ? rowB : rowA;
+          const bool row_ok = half ? okB : okA;
+          const bool in = row_ok && k0 < Lk;
+          const float mx = sstat[3 * row], inv = sstat[3 * row + 1], D = sstat[3 * row + 2];
+          float sv[8], pv[8], nv[8], pb[8], dsb[8];
+          if (!recompute && in) load8(P.s + (sbase + row) * P.lds + k0, P.lds - k0, vec, sv);
+          if (has_prev && in) load8(P.s_prev + (sbase + row) * P.lds + k0, P.lds - k0, vec, pv);
+          if (P.ds_next && in) load8(P.ds_next + (sbase + row) * P.lds + k0, P.lds - k0, vec, nv);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int j = 2 * i + e, key = k0 + j;
+              float p = 0.f, ds = 0.f;
+              if (in && key < Lk) {
+                float s;
+                if (recompute) {
+                  s = sc[G * 4 + i][half * 2 + e] * inv_sqrt;
+                  if (has_prev) s = __fadd_rn(s, __fmul_rn(cval, pv[j]));
+                  if (P.mask) s = __fsub_rn(s, sbias[key]);
+                  s = round_bf(s);
+                } else {
+                  s = sv[j];
+                }
+                p = __expf(s - mx) * inv;
+                ds = p * (dp[G * 4 + i][half * 2 + e] - D);
+                if (P.ds_next) ds += nv[j];
+                if (has_prev) dc_part = fmaf(ds, pv[j], dc_part);
+              }
+              pb[j] = p;
+              dsb[j] = ds;
+              sc[G * 4 + i][half * 2 + e] = ds;        // reused as the A operand of dQ += dS K
+            }
+          if (has_prev && P.ds_prev && in) {
+            float o8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o8[j] = cval * dsb[j];
+            store8(P.ds_prev + (sbase + row) * P.lds + k0, P.lds - k0, vec, o8);
+          }
+          const uint32_t ch = (uint32_t)(4 * G + t);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sP + swp<KB>(row, ch)),
+                       "r"(pack2(pb[0], pb[1])), "r"(pack2(pb[2], pb[3])), "r"(pack2(pb[4], pb[5])),
+                       "r"(pack2(pb[6], pb[7])) : "memory");
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sdS + swp<KB>(row, ch)),
+                       "r"(pack2(dsb[0], dsb[1])), "r"(pack2(dsb[2], dsb[3])),
+                       "r"(pack2(dsb[4], dsb[5])), "r"(pack2(dsb[6], dsb[7])) : "memory");
+        }
+      }
+      // dQ tile += dS K  (A = dS from registers, B = K via ldmatrix.trans), fp32 in shared memory
+      float dq[HD / 8][4];
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dq[n][e] = 0.f;
+#pragma unroll
+      for (int G = 0; G < NG; ++G)
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {
+          if (kb + 32 * G >= Lk) continue;
+          const int i0 = G * 4 + 2 * pp, i1 = i0 + 1;
+          uint32_t da[4] = {pack2(sc[i0][0], sc[i0][1]), pack2(sc[i0][2], sc[i0][3]),
+                            pack2(sc[i1][0], sc[i1][1]), pack2(sc[i1][2], sc[i1][3])};
+#pragma unroll
+          for (int c2 = 0; c2 < HD / 8; c2 += 2) {
+            const int mi = lane >> 3, r = lane & 7;
+            const int key = kb + 32 * G + perm_key(2 * pp + (mi & 1), r);
+            uint32_t kf[4];
+            ldsm4t(sK + sw<HD>(key, c2 + (mi >> 1)), kf);
+            mma16816(dq[c2], da, kf[0], kf[1]);
+            mma16816(dq[c2 + 1], da, kf[2], kf[3]);
+          }
+        }
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n) {
+        float2* pa = reinterpret_cast<float2*>(sdQ + rowA * HD + 8 * n + 2 * t);
+        float2* pb2 = reinterpret_cast<float2*>(sdQ + rowB * HD + 8 * n + 2 * t);
+        float2 a = *pa, b2 = *pb2;
+        a.x += dq[n][0]; a.y += dq[n][1]; b2.x += dq[n][2]; b2.y += dq[n][3];
+        *pa = a; *pb2 = b2;
+      }
+    }
+    __syncthreads();
+    // ================= phase B: dV = P^T dO, dK = dS^T Q for the KB keys of this block ===========
+    for (int task = warp; task < (KB / 16) * 2; task += BWD_WARPS) {
+      const int ks = task >> 1, kind = task & 1;          // kind 0: dV (P, dO); 1: dK (dS, Q)
+      if (kb + 16 * ks >= Lk) continue;
+      const uint32_t sA = kind ? sdS : sP, sB = kind ? sQ : sdO;
+      float acc[HD / 8][4];
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
+      for (int kt = 0; kt < n_rt; ++kt) {
+        const int mi = lane >> 3, r = lane & 7;
+        uint32_t af[4];
+        ldsm4t(sA + swp<KB>(kt * 16 + r + 8 * (mi >> 1), 2 * ks + (mi & 1)), af);
+#pragma unroll
+        for (int c2 = 0; c2 < HD / 8; c2 += 2) {
+          uint32_t bf[4];
+          ldsm4t(sB + sw<HD>(kt * 16 + r + 8 * (mi & 1), c2 + (mi >> 1)), bf);
+          mma16816(acc[c2], af, bf[0], bf[1]);
+          mma16816(acc[c2 + 1], af, bf[2], bf[3]);
+        }
+      }
+      bf16* out = kind ? P.dk : P.dv;
+      const int ld = kind ? P.lddk : P.lddv;
+      const float scl = kind ? inv_sqrt : 1.f;
+      const int keyA = kb + 16 * ks + g, keyB = keyA + 8;
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n) {
+        if (keyA < Lk)
+          *reinterpret_cast<uint32_t*>(out + ((size_t)b * Lk + keyA) * ld + h * HD + 8 * n + 2 * t) =
+              pack2(acc[n][0] * scl, acc[n][1] * scl);
+        if (keyB < Lk)
+          *reinterpret_cast<uint32_t*>(out + ((size_t)b * Lk + keyB) * ld + h * HD + 8 * n + 2 * t) =
+              pack2(acc[n][2] * scl, acc[n][3] * scl);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- dQ: fp32 tile -> bf16, 16-byte stores --------------------------------------------------
+  for (int i = threadIdx.x; i < Lq * (HD / 8); i += NT) {
+    const int r = i / (HD / 8), c8 = i - r * (HD / 8);
+    const float* s = sdQ + r * HD + c8 * 8;
+    *reinterpret_cast<uint4*>(P.dq + ((size_t)b * Lq + r) * P.lddq + h * HD + c8 * 8) =
+        make_uint4(pack2(s[0] * inv_sqrt, s[1] * inv_sqrt), pack2(s[2] * inv_sqrt, s[3] * inv_sqrt),
+                   pack2(s[4] * inv_sqrt, s[5] * inv_sqrt), pack2(s[6] * inv_sqrt, s[7] * inv_sqrt));
+  }
+  // ---- dc -------------------------------------------------------------------------------------
+  if (P.dc && has_prev) {
+    __shared__ float red[BWD_WARPS];
+    dc_part = warp_sum(dc_part);
+    if (lane == 0) red[warp] = dc_part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < BWD_WARPS; ++w) s += red[w];
+      atomicAdd(P.dc, s);
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------
+inline bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+size_t fwd_smem(int hd, int Lk, bool same_kv) {
+  const int LkP = (Lk + 63) & ~63;
+  return (size_t)FWD_ROWS * hd * 2 + (size_t)(same_kv ? 1 : 2) * LkP * hd * 2 + (size_t)LkP * 4;
+}
+size_t bwd_smem(int hd, int kbk, int Lq, int Lk, bool same_kv) {
+  const int LqP = (Lq + 15) & ~15, LkP = (Lk + kbk - 1) / kbk * kbk;
+  return (size_t)2 * LqP * hd * 2 + (size_t)(same_kv ? 1 : 2) * LkP * hd * 2 +
+         (size_t)2 * LqP * kbk * 2 + (size_t)LqP * hd * 4 + (size_t)LqP * 12 + (size_t)LkP * 4;
+}
+
+bool operands_ok(const mmemo_attn_problem& a, bool bwd) {
+  if (a.hd != 16 && a.hd != 32 && a.hd != 64) return false;
+  if (a.B <= 0 || a.H <= 0 || a.Lq <= 0 || a.Lk <= 0) return false;
+  if (a.Lq > 4096 || a.Lk > 4096) return false;
+  if (!a.q || !a.k || !a.v || !a.o || !a.lse) return false;
+  if (!a16(a.q) || !a16(a.k) || !a16(a.v) || a.ldq % 8 || a.ldk % 8 || a.ldv % 8 || a.ldo % 2 ||
+      (reinterpret_cast<uintptr_t>(a.o) & 3))
+    return false;
+  if (a.lds < a.Lk) return false;
+  if (bwd) {
+    if (!a.d_o || !a.dq || !a.dk || !a.dv) return false;
+    if (!a16(a.d_o) || !a16(a.o) || !a16(a.dq) || a.lddo % 8 || a.ldo % 8 || a.lddq % 8 ||
+        a.lddk % 2 || a.lddv % 2 || (reinterpret_cast<uintptr_t>(a.dk) & 3) ||
+        (reinterpret_cast<uintptr_t>(a.dv) & 3))
+      return false;
+  }
+  return true;
+}
+
+void fill(Prob& p, const mmemo_attn_problem& a) {
+  p.q = static_cast<const bf16*>(a.q); p.k = static_cast<const bf16*>(a.k);
+  p.v = static_cast<const bf16*>(a.v); p.mask = a.mask;
+  p.s_prev = static_cast<const bf16*>(a.s_prev); p.c = a.c;
+  p.s_out = static_cast<bf16*>(a.s_out); p.o = static_cast<bf16*>(a.o); p.lse = a.lse;
+  p.d_o = static_cast<const bf16*>(a.d_o); p.s = static_cast<const bf16*>(a.s);
+  p.ds_next = static_cast<const bf16*>(a.ds_next); p.o_in = static_cast<const bf16*>(a.o);
+  p.dq = static_cast<bf16*>(a.dq); p.dk = static_cast<bf16*>(a.dk); p.dv = static_cast<bf16*>(a.dv);
+  p.ds_prev = static_cast<bf16*>(a.ds_prev); p.dc = a.dc;
+  p.ldq = (int)a.ldq; p.ldk = (int)a.ldk; p.ldv = (int)a.ldv; p.ldo = (int)a.ldo;
+  p.lds = (int)a.lds; p.lddo = (int)a.lddo; p.lddq = (int)a.lddq; p.lddk = (int)a.lddk;
+  p.lddv = (int)a.lddv; p.mask_bs = (int)a.mask_bs;
+  p.B = (int)a.B; p.H = (int)a.H; p.Lq = (int)a.Lq; p.Lk = (int)a.Lk;
+  const void* sp[5] = {a.s_prev, a.s_out, a.s, a.ds_next, a.ds_prev};
+  bool v = a.lds % 8 == 0;
+  for (const void* x : sp) v = v && (!x || a16(x));
+  p.vec_s = v ? 1 : 0;
+}
+
+}  // namespace
+
+bool resattn_mma_supported(const mmemo_attn_problem& a, bool bwd) {
+  if (!operands_ok(a, bwd)) return false;
+  const bool same = a.k == a.v && a.ldk == a.ldv;
+  if (!bwd) return fwd_smem((int)a.hd, (int)a.Lk, same) <= SMEM_MAX;
+  return bwd_smem((int)a.hd, 32, (int)a.Lq, (int)a.Lk, same) <= SMEM_MAX;
+}
+
+int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
+  if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
+  static Table T;      // host staging (copied by value into the launch)
+  T.n = n;
+  const int hd = (int)ps[0].hd;
+  size_t smem = 0;
+  int ctas = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ps[i].hd != hd || !resattn_mma_supported(ps[i], false)) return MMEMO_ERR_SHAPE;
+    fill(T.p[i], ps[i]);
+    T.p[i].cta_start = ctas;
+    ctas += (int)(ps[i].B * ps[i].H * cdiv(ps[i].Lq, FWD_ROWS));
+    const size_t s = fwd_smem(hd, (int)ps[i].Lk, ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv);
+    smem = s > smem ? s : smem;
+  }
+  T.total = ctas;
+  T.inv_sqrt = (float)(1.0 / sqrt((double)hd));
+#define MM_FWD(HD)                                                                               \
+  {                                                                                              \
+    MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_fwd_kernel<HD>,                                  \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); \
+    MM_CUDA_OK(mm_launch(resattn_mma_fwd_kernel<HD>, dim3((unsigned)ctas), dim3(FWD_WARPS * 32), \
+                         smem, st, T));                                                          \
+  }
+  if (hd == 16) MM_FWD(16) else if (hd == 32) MM_FWD(32) else MM_FWD(64)
+#undef MM_FWD
+  return MMEMO_OK;
+}
+
+int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
+  if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
+  static Table T;
+  T.n = n;
+  const int hd = (int)ps[0].hd;
+  size_t smem64 = 0, smem32 = 0;
+  int ctas = 0;
+  for (int i = 0; i < n; ++i) {
+    if (ps[i].hd != hd || !resattn_mma_supported(ps[i], true)) return MMEMO_ERR_SHAPE;
+    fill(T.p[i], ps[i]);
+    T.p[i].cta_start = ctas;
+    ctas += (int)(ps[i].B * ps[i].H);
+    const bool same = ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv;
+    const size_t s64 = bwd_smem(hd, 64, (int)ps[i].Lq, (int)ps[i].Lk, same);
+    const size_t s32 = bwd_smem(hd, 32, (int)ps[i].Lq, (int)ps[i].Lk, same);
+    smem64 = s64 > smem64 ? s64 : smem64;
+    smem32 = s32 > smem32 ? s32 : smem32;
+  }
+  T.total = ctas;
+  T.inv_sqrt = (float)(1.0 / sqrt((double)hd));
+  // Key block: the 64-key instantiation needs ~155 registers (one 8-warp CTA per SM), the 32-key
+  // one ~100 (two CTAs per SM when shared memory allows): prefer 32 whenever two CTAs fit, 64
+  // when only one CTA fits either way (fewer block iterations), 32 when 64 does not fit at all.
+  // MMEMO_ATTN_KB=32|64 overrides (experiments).
+  bool kb64 = smem32 > 110 * 1024 && smem64 <= SMEM_MAX;
+  if (const char* e = getenv("MMEMO_ATTN_KB")) {
+    if (e[0] == '6' && smem64 <= SMEM_MAX) kb64 = true;
+    if (e[0] == '3') kb64 = false;
+  }
+#define MM_BWD(HD, KBK, SM)                                                                       \
+  {                                                                                               \
+    MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_bwd_kernel<HD, KBK>,                              \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); \
+    MM_CUDA_OK(mm_launch(resattn_mma_bwd_kernel<HD, KBK>, dim3((unsigned)ctas),                   \
+                         dim3(BWD_WARPS * 32), SM, st, T));                                       \
+  }
+  if (kb64) {
+    if (hd == 16) MM_BWD(16, 64, smem64) else if (hd == 32) MM_BWD(32, 64, smem64)
+    else MM_BWD(64, 64, smem64)
+  } else {
+    if (hd == 16) MM_BWD(16, 32, smem32) else if (hd == 32) MM_BWD(32, 32, smem32)
+    else MM_BWD(64, 32, smem32)
+  }
+#undef MM_BWD
+  return MMEMO_OK;
+}

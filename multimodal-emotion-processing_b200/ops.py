@@ -444,6 +444,48 @@ def _attn_bwd(bf16, do, q, k, v, mask, s, s_prev, c, ds_next, o, stat, H, dq, dk
 
 
 # ------------------------------------------------------------------------------------------------
+# grouped residual attention (bf16): the problems of a fusion-trunk layer in ONE launch
+# ------------------------------------------------------------------------------------------------
+def score_stride(Lk: int) -> int:
+    """Row stride of the score tensors the fused trunk allocates: padded to 8 elements so that the
+    kernels move S / S_prev / dS as 16-byte vectors (the returned scores are the [..., :Lk] view)."""
+    return (Lk + 7) // 8 * 8
+
+
+def _attn_problem(q, k, v, mask, s_prev, c, s_out, o, stat, H, lds, d_o=None, s=None, ds_next=None,
+                  dq=None, dk=None, dv=None, ds_prev=None, dc=None) -> "_lib.AttnProblem":
+    B, Lq, d = q.shape
+    Lk = k.shape[1]
+    a = _lib.AttnProblem()
+    a.q, a.k, a.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.ldq, a.ldk, a.ldv = _bld(q, Lq), _bld(k, Lk), _bld(v, Lk)
+    a.mask, a.mask_bs = _p(mask), Lk
+    a.s_prev, a.c = _p(s_prev), (_p(c) if s_prev is not None else None)
+    a.s_out, a.lds = _p(s_out), lds
+    a.o, a.ldo, a.lse = o.data_ptr(), _bld(o, Lq), stat.data_ptr()
+    a.B, a.H, a.Lq, a.Lk, a.hd = B, H, Lq, Lk, d // H
+    if d_o is not None:
+        a.d_o, a.lddo = d_o.data_ptr(), _bld(d_o, Lq)
+        a.s, a.ds_next = _p(s), _p(ds_next)
+        a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+        a.lddq, a.lddk, a.lddv = _bld(dq, Lq), _bld(dk, Lk), _bld(dv, Lk)
+        a.ds_prev, a.dc = _p(ds_prev), _p(dc)
+    return a
+
+
+def _attn_group_call(name: str, probs) -> bool:
+    """One grouped launch; False when the mma kernels do not take one of the shapes."""
+    global launch_count
+    arr = (_lib.AttnProblem * len(probs))(*probs)
+    rc = getattr(_lib.load(), name)(len(probs), C.cast(arr, C.c_void_p), _stream())
+    if rc == -2:
+        return False
+    _lib.check(rc, name)
+    launch_count += 1
+    return True
+
+
+# ------------------------------------------------------------------------------------------------
 # mmemo::linear  (Linear / Conv1d(k=1) with optional bias, fused position table, fused ReLU)
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("mmemo::linear", mutates_args=())
