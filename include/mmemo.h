@@ -87,9 +87,10 @@ int mmemo_linear_bwd_w_bf16(const void* dy, int64_t lddy, const void* x, int x_i
                             float* dw, int64_t lddw, float* dbias, int64_t M, int64_t N, int64_t K,
                             int accumulate, mmemo_stream_t stream);
 
-/* Grouped variants (bf16): n <= 6 independent problems of the kinds above in ONE persistent
- * tensor-core launch (the Q and K|V projections of a block; its five weight gradients), so that
- * GEMMs too small to fill 148 SMs share a wave.  All arrays are HOST arrays of length n.  Falls
+/* Grouped variants (bf16): n <= 48 independent problems of the kinds above in ONE persistent
+ * tensor-core launch (the Q and K|V projections of a block; its five weight gradients; the same
+ * for all nine chains of a fusion-trunk layer at once), so that GEMMs too small to fill 148 SMs
+ * share a wave.  All arrays are HOST arrays of length n.  Falls
  * back to n single launches when a problem does not meet the tensor-core kernel's constraints. */
 int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ldx,
                                   const void* const* w, const int64_t* ldw,
@@ -219,16 +220,50 @@ int mmemo_add_ln_bwd_bf16(const void* dy, int64_t lddy, const void* res, int64_t
                           float* dgamma, float* dbeta, float* dxsum, int64_t M, int64_t d,
                           int relu, mmemo_stream_t stream);
 
+/* Grouped variants (n <= 40 problems, ONE launch; HOST arrays of length n; rows contiguous, i.e.
+ * every leading dimension = d): the LayerNorms of the nine chains of a fusion-trunk layer.  The
+ * backward serves d <= 512 (its single-pass kernel), no ReLU.  MMEMO_ERR_SHAPE when a problem does
+ * not meet the vector kernels' alignment (16-byte pointers, d % 8 == 0 (bf16) / d % 4 == 0). */
+int mmemo_add_ln_fwd_grouped_f32(int n, const void* const* res, const void* const* x,
+                                 const float* const* gate, const float* const* gamma,
+                                 const float* const* beta, void* const* y, float* const* mean,
+                                 float* const* rstd, const int64_t* M, int64_t d, float eps,
+                                 int relu, mmemo_stream_t stream);
+int mmemo_add_ln_fwd_grouped_bf16(int n, const void* const* res, const void* const* x,
+                                  const float* const* gate, const float* const* gamma,
+                                  const float* const* beta, void* const* y, float* const* mean,
+                                  float* const* rstd, const int64_t* M, int64_t d, float eps,
+                                  int relu, mmemo_stream_t stream);
+int mmemo_add_ln_bwd_grouped_f32(int n, const void* const* dy, const void* const* res,
+                                 const void* const* x, const float* const* gate,
+                                 const float* const* gamma, const float* const* mean,
+                                 const float* const* rstd, void* const* dres, void* const* dx,
+                                 float* const* dgate, float* const* dgamma, float* const* dbeta,
+                                 float* const* dxsum, const int64_t* M, int64_t d,
+                                 mmemo_stream_t stream);
+int mmemo_add_ln_bwd_grouped_bf16(int n, const void* const* dy, const void* const* res,
+                                  const void* const* x, const float* const* gate,
+                                  const float* const* gamma, const float* const* mean,
+                                  const float* const* rstd, void* const* dres, void* const* dx,
+                                  float* const* dgate, float* const* dgamma, float* const* dbeta,
+                                  float* const* dxsum, const int64_t* M, int64_t d,
+                                  mmemo_stream_t stream);
+
 /* out[m % period, n] += x[m, n]  (float32 out).  Bias gradients (period 1) and position-table
  * gradients (period L; backward of others/realformer.py:225-227). */
 int mmemo_rowsum_f32(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
                      mmemo_stream_t stream);
 int mmemo_rowsum_bf16(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
                       mmemo_stream_t stream);
+/* out[i][c] += sum_m x[i][m, c] for n <= 40 contiguous (M[i], N) bf16 matrices in one launch (the
+ * FFN-1 bias gradients of a trunk layer); N % 8 == 0 */
+int mmemo_colsum_grouped_bf16(int n, const void* const* x, float* const* out, const int64_t* M,
+                              int64_t N, mmemo_stream_t stream);
 /* dtype conversion of n contiguous elements (bf16 shadow copies of float32 master weights) */
 int mmemo_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mmemo_stream_t stream);
 int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_t stream);
-/* `count` <= 8 tensors in one launch (host arrays): all bf16 weight shadows of one block */
+/* `count` <= 64 tensors in one launch (host arrays): all bf16 weight shadows of a block / of a
+ * whole trunk layer */
 int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const* dst,
                                  const int64_t* n, mmemo_stream_t stream);
 /* y = x * keep/(1-p), keep ~ Bernoulli(1-p) from a counter-based RNG keyed by (seed, element).

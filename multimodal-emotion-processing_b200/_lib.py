@@ -61,6 +61,11 @@ SIGNATURES = {
     "mmemo_resattn_uses_mma": [_i64, _i64, _i64, _i64, _i32, _i32],
     "mmemo_add_ln_fwd_f32": _LN_FWD, "mmemo_add_ln_fwd_bf16": _LN_FWD,
     "mmemo_add_ln_bwd_f32": _LN_BWD, "mmemo_add_ln_bwd_bf16": _LN_BWD,
+    "mmemo_add_ln_fwd_grouped_f32": [_i32] + [_vp] * 9 + [_i64, _f32, _i32, _vp],
+    "mmemo_add_ln_fwd_grouped_bf16": [_i32] + [_vp] * 9 + [_i64, _f32, _i32, _vp],
+    "mmemo_add_ln_bwd_grouped_f32": [_i32] + [_vp] * 14 + [_i64, _vp],
+    "mmemo_add_ln_bwd_grouped_bf16": [_i32] + [_vp] * 14 + [_i64, _vp],
+    "mmemo_colsum_grouped_bf16": [_i32, _vp, _vp, _vp, _i64, _vp],
     "mmemo_rowsum_f32": _ROWSUM, "mmemo_rowsum_bf16": _ROWSUM,
     "mmemo_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mmemo_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],

@@ -58,17 +58,22 @@ struct TcArgs {
 // One launch can serve up to MAXG independent GEMMs ("grouped"): the work items of all problems
 // form one list that the persistent CTAs walk, so small GEMMs that would each leave the machine
 // half empty (the five weight gradients of a block, the Q and K|V projections) share one wave.
-constexpr int MAXG = 6;
-struct TmapGroup { CUtensorMap a[MAXG], b[MAXG], c[MAXG], aux[MAXG]; };
-struct GroupArgs {
+// Two capacities of the same kernel: NG = 6 (the launches of one block: ~3.5 KB of kernel
+// parameters) and NG = 48 (the nine chains x five weight gradients of a fusion-trunk layer, both
+// towers' projections: ~29 KB, within the 32 764-byte parameter limit of CUDA >= 12.1).
+// FAM only names the instantiation after the Linear-layer pass it serves (0 fwd, 1 dX, 2 dW), so
+// that profiler launch lists can be read per family.
+constexpr int MAXG_SMALL = 6, MAXG = 48;
+template <int NG> struct TmapGroup { CUtensorMap a[NG], b[NG], c[NG], aux[NG]; };
+template <int NG> struct GroupArgs {
   int n;
-  int item_start[MAXG + 1];
-  TcArgs p[MAXG];
+  int item_start[NG + 1];
+  TcArgs p[NG];
 };
 
-template <bool CTA2>
+template <bool CTA2, int NG, int FAM>
 __global__ void __launch_bounds__(NTHREADS, 1)
-gemm_tc_kernel(const __grid_constant__ TmapGroup TMS, const __grid_constant__ GroupArgs G) {
+gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant__ GroupArgs<NG> G) {
   constexpr int BN = CTA2 ? 256 : 128;        // accumulator columns per tile
   constexpr int TM = CTA2 ? 256 : 128;        // output rows per work item (pair or CTA)
   constexpr int NHALF = BN / 128;             // epilogue works on 128 columns at a time
@@ -395,7 +400,6 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceArgs a) 
 
 float* g_ws = nullptr;
 size_t g_ws_bytes = 0;
-int g_force_1cta = 0;   // debug / A-B switch (mmemo_debug_gemm_force_1cta)
 int g_sm_budget = 0;    // SMs the persistent kernels may occupy (0 = all); mmemo_set_sm_budget
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -442,11 +446,6 @@ extern "C" int mmemo_set_sm_budget(int n_sms) {
   g_sm_budget = n_sms;
   return MMEMO_OK;
 }
-// debug only (not part of include/mmemo.h): force the one-CTA 128x128 configuration
-extern "C" int mmemo_debug_gemm_force_1cta(int on) {
-  g_force_1cta = on;
-  return MMEMO_OK;
-}
 
 PFN_encodeTiled mm_get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
@@ -485,18 +484,16 @@ bool gemm_tc_supported(const GemmArgs& g, int c_bf16) {
   return true;
 }
 
-int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t st) {
-  if (n < 1 || n > MAXG) return MMEMO_ERR_ARG;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    attr_done = true;
-  }
+namespace {
+template <int NG, int FAM>
+int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t st) {
+  // (idempotent and cheap: no guard variable, so concurrent callers cannot race on one)
+  MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, NG, FAM>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, NG, FAM>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   // CTA pairs (256 x 256 tiles) when every output is wide and tall enough to fill them
-  bool cta2 = !g_force_1cta;
+  bool cta2 = true;
   for (int i = 0; i < n; ++i) cta2 = cta2 && gs[i].N >= 256 && gs[i].M >= 256;
   const int TM = cta2 ? 256 : 128, BN = cta2 ? 256 : 128;
   const int sms = num_sms();
@@ -525,8 +522,9 @@ int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t 
     if (splits < 2) splits = 1;
   }
 
-  static TmapGroup tms;     // host staging (copied by value into the launch)
-  GroupArgs G = {};
+  static thread_local TmapGroup<NG> tms;     // host staging (copied by value into the launch)
+  static thread_local GroupArgs<NG> G;
+  G = GroupArgs<NG>{};
   G.n = n;
   int items = 0;
   bool ok = true;
@@ -607,10 +605,10 @@ int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t 
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = g_mm_pdl ? 2 : 1;
-    MM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true>, tms, G));
+    MM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, NG, FAM>, tms, G));
   } else {
-    MM_CUDA_OK(mm_launch(gemm_tc_kernel<false>, dim3((unsigned)units), dim3(NTHREADS), SMEM_BYTES,
-                         st, tms, G));
+    MM_CUDA_OK(mm_launch(gemm_tc_kernel<false, NG, FAM>, dim3((unsigned)units), dim3(NTHREADS),
+                         SMEM_BYTES, st, tms, G));
   }
   if (n == 1 && G.p[0].splits > 1 && !G.p[0].reduce_add) {
     const GemmArgs& g = gs[0];
@@ -628,7 +626,20 @@ int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_t 
   }
   return MMEMO_OK;
 }
+}  // namespace
 
-int gemm_tc(const GemmArgs& g, int c_bf16, cudaStream_t st) {
-  return gemm_tc_grouped(&g, &c_bf16, 1, st);
+int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, int family, cudaStream_t st) {
+  if (n < 1 || n > MAXG) return MMEMO_ERR_ARG;
+  if (n <= MAXG_SMALL) {
+    if (family == 0) return gemm_tc_grouped_t<MAXG_SMALL, 0>(gs, c_bf16s, n, st);
+    if (family == 1) return gemm_tc_grouped_t<MAXG_SMALL, 1>(gs, c_bf16s, n, st);
+    return gemm_tc_grouped_t<MAXG_SMALL, 2>(gs, c_bf16s, n, st);
+  }
+  if (family == 0) return gemm_tc_grouped_t<MAXG, 0>(gs, c_bf16s, n, st);
+  if (family == 1) return gemm_tc_grouped_t<MAXG, 1>(gs, c_bf16s, n, st);
+  return gemm_tc_grouped_t<MAXG, 2>(gs, c_bf16s, n, st);
+}
+
+int gemm_tc(const GemmArgs& g, int c_bf16, int family, cudaStream_t st) {
+  return gemm_tc_grouped(&g, &c_bf16, 1, family, st);
 }

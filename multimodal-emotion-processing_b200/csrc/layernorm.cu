@@ -64,17 +64,16 @@ template <> struct Vec<bf16> {
 // ---------------------------------------------------------------------------------------------
 // vector kernels: lane owns chunks c = lane + 32*i (i < NCH) of V consecutive columns
 // ---------------------------------------------------------------------------------------------
+// (bid, nblk): this CTA's index / the number of CTAs that share the rows of this problem
 template <typename T, int NCH>
-__global__ void __launch_bounds__(LN_WARPS * 32)
-ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, int64_t ldx,
-           const float* __restrict__ gate, const float* __restrict__ gamma,
-           const float* __restrict__ beta, T* __restrict__ y, int64_t ldy,
-           float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t M, int d, float eps,
-           int relu) {
+__device__ __forceinline__ void
+ln_fwd_vec_body(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, int64_t ldx,
+                const float* __restrict__ gate, const float* __restrict__ gamma,
+                const float* __restrict__ beta, T* __restrict__ y, int64_t ldy,
+                float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t M, int d,
+                float eps, int relu, unsigned bid, unsigned nblk) {
   constexpr int V = Vec<T>::N;
   const int lane = threadIdx.x & 31;
-  pdl_wait();
-  pdl_trigger();
   const float g = gate ? gate[0] : 1.f;
   const int nchunk = d / V;
   float gm[NCH][V], bt[NCH][V];
@@ -88,8 +87,8 @@ ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, in
         Vec<float>::load(beta + (lane + 32 * i) * V + 4, bt[i] + 4);
       }
     }
-  for (int64_t row = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5); row < M;
-       row += (int64_t)gridDim.x * LN_WARPS) {
+  for (int64_t row = (int64_t)bid * LN_WARPS + (threadIdx.x >> 5); row < M;
+       row += (int64_t)nblk * LN_WARPS) {
   float z[NCH][V];
   float sum = 0.f;
 #pragma unroll
@@ -141,6 +140,43 @@ ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, in
     if (rstd_out) rstd_out[row] = rstd;
   }
   }  // row loop
+}
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_vec(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, int64_t ldx,
+           const float* __restrict__ gate, const float* __restrict__ gamma,
+           const float* __restrict__ beta, T* __restrict__ y, int64_t ldy,
+           float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t M, int d, float eps,
+           int relu) {
+  pdl_wait();
+  pdl_trigger();
+  ln_fwd_vec_body<T, NCH>(res, ldres, x, ldx, gate, gamma, beta, y, ldy, mean_out, rstd_out, M, d,
+                          eps, relu, blockIdx.x, gridDim.x);
+}
+
+// Grouped launches: up to LN_MAXP independent problems (the nine chains of a fusion-trunk layer,
+// both towers, ...) share one grid; blockIdx.y selects the problem, the CTAs of a column of the
+// grid stride over its rows.  Rows are contiguous (leading dimension d).
+constexpr int LN_MAXP = 40;
+struct LnProb {
+  const void *res, *x, *dy;
+  const float *gate, *gamma, *beta;
+  void *y, *dres, *dx;
+  float *mean, *rstd, *dgate, *dgamma, *dbeta, *dxsum;
+  long long M;
+};
+struct LnTable { LnProb p[LN_MAXP]; };
+
+template <typename T, int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_vec_grouped(const __grid_constant__ LnTable tb, int d, float eps, int relu) {
+  const LnProb& a = tb.p[blockIdx.y];
+  pdl_wait();
+  pdl_trigger();
+  ln_fwd_vec_body<T, NCH>(static_cast<const T*>(a.res), d, static_cast<const T*>(a.x), d, a.gate,
+                          a.gamma, a.beta, static_cast<T*>(a.y), d, a.mean, a.rstd, a.M, d, eps,
+                          relu, blockIdx.x, gridDim.x);
 }
 
 template <typename T, int NCH>
@@ -232,22 +268,20 @@ ln_bwd_row_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res
 constexpr int LNB_WARPS = 16;
 
 template <typename T, int NCH, bool DXSUM>
-__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
-ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
-                 const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
-                 const float* __restrict__ gamma, const T* __restrict__ y, int64_t ldy,
-                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                 T* __restrict__ dres, int64_t lddres, T* __restrict__ dx, int64_t lddx,
-                 float* __restrict__ dgate, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                 float* __restrict__ dxsum, int64_t M, int d, int relu) {
+__device__ __forceinline__ void
+ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
+                  const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+                  const float* __restrict__ gamma,
+                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                  T* __restrict__ dres, int64_t lddres, T* __restrict__ dx, int64_t lddx,
+                  float* __restrict__ dgate, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                  float* __restrict__ dxsum, int64_t M, int d, unsigned bid, unsigned nblk) {
   constexpr int V = Vec<T>::N;
   extern __shared__ __align__(16) float ln_sm[];   // gamma [d] | staging [LNB_WARPS][d]
   float* sg = ln_sm;
   float* stage = ln_sm + d;
   __shared__ float dgs[LNB_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  pdl_wait();
-  pdl_trigger();
   for (int i = threadIdx.x; i < d; i += LNB_WARPS * 32) sg[i] = gamma[i];
   __syncthreads();
   const float g = gate ? gate[0] : 1.f;
@@ -264,8 +298,8 @@ ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ r
     }
   // the row loop is software-pipelined: the 16-byte vectors of the next row are requested (and
   // held packed) before the current row is reduced, so every warp keeps two rows of loads in flight
-  const int64_t rstep = (int64_t)gridDim.x * LNB_WARPS;
-  int64_t row = (int64_t)blockIdx.x * LNB_WARPS + warp;
+  const int64_t rstep = (int64_t)nblk * LNB_WARPS;
+  int64_t row = (int64_t)bid * LNB_WARPS + warp;
   uint4 cur[NCH][3], nxt[NCH][3];
   auto fetch = [&](int64_t r, uint4 (&buf)[NCH][3]) {
 #pragma unroll
@@ -366,6 +400,35 @@ ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ r
     for (int w2 = 0; w2 < LNB_WARPS; ++w2) t += dgs[w2];
     atomicAdd(dgate, t);
   }
+}
+
+template <typename T, int NCH, bool DXSUM>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
+ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
+                 const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
+                 const float* __restrict__ gamma, const T* __restrict__ y, int64_t ldy,
+                 const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                 T* __restrict__ dres, int64_t lddres, T* __restrict__ dx, int64_t lddx,
+                 float* __restrict__ dgate, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                 float* __restrict__ dxsum, int64_t M, int d, int relu) {
+  pdl_wait();
+  pdl_trigger();
+  ln_bwd_fused_body<T, NCH, DXSUM>(dy, lddy, res, ldres, x, ldx, gate, gamma, mean_in, rstd_in, dres,
+                                   lddres, dx, lddx, dgate, dgamma, dbeta, dxsum, M, d, blockIdx.x,
+                                   gridDim.x);
+}
+
+template <typename T, int NCH, bool DXSUM>
+__global__ void __launch_bounds__(LNB_WARPS * 32, 1)
+ln_bwd_fused_vec_grouped(const __grid_constant__ LnTable tb, int d) {
+  const LnProb& a = tb.p[blockIdx.y];
+  pdl_wait();
+  pdl_trigger();
+  ln_bwd_fused_body<T, NCH, DXSUM>(static_cast<const T*>(a.dy), d, static_cast<const T*>(a.res), d,
+                                   static_cast<const T*>(a.x), d, a.gate, a.gamma, a.mean, a.rstd,
+                                   static_cast<T*>(a.dres), d, static_cast<T*>(a.dx), d, a.dgate,
+                                   a.dgamma, a.dbeta, DXSUM ? a.dxsum : nullptr, a.M, d,
+                                   blockIdx.x, gridDim.x);
 }
 
 // dgamma / dbeta: CTA = (64 columns, strip of rows); lane owns 2 adjacent columns
@@ -647,9 +710,127 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
   return MMEMO_OK;
 }
 
+template <typename T>
+int fwd_grouped(int n, const void* const* res, const void* const* x, const float* const* gate,
+                const float* const* gamma, const float* const* beta, void* const* y,
+                float* const* mean, float* const* rstd, const int64_t* M, int64_t d, float eps,
+                int relu, cudaStream_t st) {
+  if (n < 1 || n > LN_MAXP) return MMEMO_ERR_ARG;
+  constexpr int V = Vec<T>::N;
+  if (d <= 0 || d % V || d / V > 256) return MMEMO_ERR_SHAPE;
+  static thread_local LnTable tb;
+  int64_t mmax = 0;
+  for (int i = 0; i < n; ++i) {
+    MM_REQUIRE(x[i] && gamma[i] && beta[i] && y[i] && M[i] >= 0);
+    if (!al16(x[i]) || !al16(y[i]) || (res && res[i] && !al16(res[i])) || !al16(gamma[i]) ||
+        !al16(beta[i]))
+      return MMEMO_ERR_SHAPE;
+    LnProb& a = tb.p[i];
+    a = LnProb{};
+    a.res = res ? res[i] : nullptr; a.x = x[i]; a.gate = gate ? gate[i] : nullptr;
+    a.gamma = gamma[i]; a.beta = beta[i]; a.y = y[i];
+    a.mean = mean ? mean[i] : nullptr; a.rstd = rstd ? rstd[i] : nullptr; a.M = M[i];
+    mmax = M[i] > mmax ? M[i] : mmax;
+  }
+  if (mmax == 0) return MMEMO_OK;
+  // ~6 CTAs (48 warps) per SM over the whole group
+  int64_t gx = cdiv(mmax, LN_WARPS);
+  const int64_t cap = cdiv(148 * 6, n);
+  if (gx > cap) gx = cap;
+  const dim3 grid((unsigned)gx, (unsigned)n);
+  const int nch = (int)cdiv(d / V, 32);
+#define MM_G(NCH_) MM_CUDA_OK(mm_launch(ln_fwd_vec_grouped<T, NCH_>, grid, dim3(LN_WARPS * 32), 0, st, tb, (int)d, eps, relu))
+  if (nch <= 1) MM_G(1); else if (nch <= 2) MM_G(2); else if (nch <= 4) MM_G(4); else MM_G(8);
+#undef MM_G
+  return MMEMO_OK;
+}
+
+template <typename T>
+int bwd_grouped(int n, const void* const* dy, const void* const* res, const void* const* x,
+                const float* const* gate, const float* const* gamma, const float* const* mean,
+                const float* const* rstd, void* const* dres, void* const* dx, float* const* dgate,
+                float* const* dgamma, float* const* dbeta, float* const* dxsum, const int64_t* M,
+                int64_t d, cudaStream_t st) {
+  if (n < 1 || n > LN_MAXP) return MMEMO_ERR_ARG;
+  constexpr int V = Vec<T>::N;
+  if (d <= 0 || d % V || cdiv(d / V, 32) * V > 16) return MMEMO_ERR_SHAPE;   // single-pass kernel only
+  static thread_local LnTable tb;
+  int64_t mmax = 0;
+  bool any_dxsum = false;
+  for (int i = 0; i < n; ++i) {
+    MM_REQUIRE(dy[i] && x[i] && gamma[i] && mean[i] && rstd[i] && dx[i] && M[i] >= 0);
+    if (!al16(dy[i]) || !al16(x[i]) || !al16(dx[i]) || (res && res[i] && !al16(res[i])) ||
+        (dres && dres[i] && !al16(dres[i])) || !al16(gamma[i]))
+      return MMEMO_ERR_SHAPE;
+    LnProb& a = tb.p[i];
+    a = LnProb{};
+    a.dy = dy[i]; a.res = res ? res[i] : nullptr; a.x = x[i]; a.gate = gate ? gate[i] : nullptr;
+    a.gamma = gamma[i]; a.mean = const_cast<float*>(mean[i]); a.rstd = const_cast<float*>(rstd[i]);
+    a.dres = dres ? dres[i] : nullptr; a.dx = dx[i]; a.dgate = dgate ? dgate[i] : nullptr;
+    a.dgamma = dgamma ? dgamma[i] : nullptr; a.dbeta = dbeta ? dbeta[i] : nullptr;
+    a.dxsum = dxsum ? dxsum[i] : nullptr; a.M = M[i];
+    any_dxsum = any_dxsum || a.dxsum;
+    mmax = M[i] > mmax ? M[i] : mmax;
+  }
+  if (mmax == 0) return MMEMO_OK;
+  // one persistent 16-warp CTA per SM over the whole group (at least one per problem)
+  int64_t gx = cdiv(mmax, LNB_WARPS);
+  const int64_t cap = cdiv(148, n) > 1 ? cdiv(148, n) : 1;
+  if (gx > cap) gx = cap;
+  const dim3 grid((unsigned)gx, (unsigned)n);
+  const int nch = (int)cdiv(d / V, 32);
+  const size_t sm_bytes = (1 + LNB_WARPS) * (size_t)d * sizeof(float);
+#define MM_G(NCH_)                                                                                \
+  do {                                                                                            \
+    if (any_dxsum)                                                                                \
+      MM_CUDA_OK(mm_launch(ln_bwd_fused_vec_grouped<T, NCH_, true>, grid, dim3(LNB_WARPS * 32),   \
+                           sm_bytes, st, tb, (int)d));                                            \
+    else                                                                                          \
+      MM_CUDA_OK(mm_launch(ln_bwd_fused_vec_grouped<T, NCH_, false>, grid, dim3(LNB_WARPS * 32),  \
+                           sm_bytes, st, tb, (int)d));                                            \
+  } while (0)
+  if (nch <= 1) MM_G(1); else if (nch <= 2) MM_G(2); else if (V == 4) MM_G(4);
+#undef MM_G
+  return MMEMO_OK;
+}
+
 }  // namespace
 
 extern "C" {
+int mmemo_add_ln_fwd_grouped_f32(int n, const void* const* res, const void* const* x,
+                                 const float* const* gate, const float* const* gamma,
+                                 const float* const* beta, void* const* y, float* const* mean,
+                                 float* const* rstd, const int64_t* M, int64_t d, float eps,
+                                 int relu, mmemo_stream_t s) {
+  return fwd_grouped<float>(n, res, x, gate, gamma, beta, y, mean, rstd, M, d, eps, relu, mm_stream(s));
+}
+int mmemo_add_ln_fwd_grouped_bf16(int n, const void* const* res, const void* const* x,
+                                  const float* const* gate, const float* const* gamma,
+                                  const float* const* beta, void* const* y, float* const* mean,
+                                  float* const* rstd, const int64_t* M, int64_t d, float eps,
+                                  int relu, mmemo_stream_t s) {
+  return fwd_grouped<bf16>(n, res, x, gate, gamma, beta, y, mean, rstd, M, d, eps, relu, mm_stream(s));
+}
+int mmemo_add_ln_bwd_grouped_f32(int n, const void* const* dy, const void* const* res,
+                                 const void* const* x, const float* const* gate,
+                                 const float* const* gamma, const float* const* mean,
+                                 const float* const* rstd, void* const* dres, void* const* dx,
+                                 float* const* dgate, float* const* dgamma, float* const* dbeta,
+                                 float* const* dxsum, const int64_t* M, int64_t d,
+                                 mmemo_stream_t s) {
+  return bwd_grouped<float>(n, dy, res, x, gate, gamma, mean, rstd, dres, dx, dgate, dgamma, dbeta,
+                            dxsum, M, d, mm_stream(s));
+}
+int mmemo_add_ln_bwd_grouped_bf16(int n, const void* const* dy, const void* const* res,
+                                  const void* const* x, const float* const* gate,
+                                  const float* const* gamma, const float* const* mean,
+                                  const float* const* rstd, void* const* dres, void* const* dx,
+                                  float* const* dgate, float* const* dgamma, float* const* dbeta,
+                                  float* const* dxsum, const int64_t* M, int64_t d,
+                                  mmemo_stream_t s) {
+  return bwd_grouped<bf16>(n, dy, res, x, gate, gamma, mean, rstd, dres, dx, dgate, dgamma, dbeta,
+                           dxsum, M, d, mm_stream(s));
+}
 int mmemo_add_ln_fwd_f32(const void* res, int64_t ldres, const void* x, int64_t ldx,
                          const float* gate, const float* gamma, const float* beta, void* y,
                          int64_t ldy, float* mean, float* rstd, int64_t M, int64_t d, float eps,

@@ -10,8 +10,8 @@ int mmemo_rowsum_dispatch(int bf16_mode, const void* x, int64_t ldx, float* out,
 
 namespace {
 
-int run(const GemmArgs& g, int a_bf16, int b_bf16, int c_bf16, cudaStream_t st) {
-  if (a_bf16 && b_bf16 && gemm_tc_supported(g, c_bf16)) return gemm_tc(g, c_bf16, st);
+int run(const GemmArgs& g, int a_bf16, int b_bf16, int c_bf16, int family, cudaStream_t st) {
+  if (a_bf16 && b_bf16 && gemm_tc_supported(g, c_bf16)) return gemm_tc(g, c_bf16, family, st);
   return gemm_simt(g, a_bf16, b_bf16, c_bf16, st);
 }
 
@@ -27,7 +27,7 @@ int linear_fwd(int bf, const void* x, int x_is_f32, int64_t ldx, const void* w, 
   g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.pos = pos; g.pos_period = pos ? pos_period : 1;
   g.relu = relu; g.accumulate = accumulate;
-  return run(g, bf && !x_is_f32, bf, bf, st);
+  return run(g, bf && !x_is_f32, bf, bf, 0, st);
 }
 
 int linear_bwd_x(int bf, const void* dy, int64_t lddy, const void* w, int64_t ldw, void* dx,
@@ -42,7 +42,7 @@ int linear_bwd_x(int bf, const void* dy, int64_t lddy, const void* w, int64_t ld
   g.pos_period = 1;
   g.relu_src = relu_src; g.ldrelu = ldrelu; g.relu_src_bf16 = bf;
   g.accumulate = accumulate;
-  return run(g, bf, bf, bf, st);
+  return run(g, bf, bf, bf, 1, st);
 }
 
 int linear_bwd_w(int bf, const void* dy, int64_t lddy, const void* x, int x_is_f32, int64_t ldx,
@@ -56,7 +56,7 @@ int linear_bwd_w(int bf, const void* dy, int64_t lddy, const void* x, int x_is_f
   g.M = N; g.N = K; g.K = M;
   g.pos_period = 1;
   g.accumulate = accumulate;
-  int rc = run(g, bf, bf && !x_is_f32, 0, st);
+  int rc = run(g, bf, bf && !x_is_f32, 0, 2, st);
   if (rc) return rc;
   if (dbias) rc = mmemo_rowsum_dispatch(bf, dy, lddy, dbias, M, N, st);
   return rc;
@@ -89,9 +89,9 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
                                   const float* const* bias, void* const* y, const int64_t* ldy,
                                   const int64_t* M, const int64_t* N, const int64_t* K,
                                   const int* relu, mmemo_stream_t s) {
-  if (n < 1 || n > 6) return MMEMO_ERR_ARG;
-  GemmArgs g[6] = {};
-  int cb[6];
+  if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
+  GemmArgs g[GEMM_TC_MAX_GROUP] = {};
+  int cb[GEMM_TC_MAX_GROUP];
   bool tc_ok = true;
   for (int i = 0; i < n; ++i) {
     MM_REQUIRE(x[i] && w[i] && y[i]);
@@ -104,9 +104,9 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
     cb[i] = 1;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 1);
   }
-  if (tc_ok) return gemm_tc_grouped(g, cb, n, mm_stream(s));
+  if (tc_ok) return gemm_tc_grouped(g, cb, n, 0, mm_stream(s));
   for (int i = 0; i < n; ++i) {
-    const int rc = run(g[i], 1, 1, 1, mm_stream(s));
+    const int rc = run(g[i], 1, 1, 1, 0, mm_stream(s));
     if (rc) return rc;
   }
   return MMEMO_OK;
@@ -115,9 +115,9 @@ int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t*
                                     const void* const* w, const int64_t* ldw, void* const* dx,
                                     const int64_t* lddx, const int64_t* M, const int64_t* N,
                                     const int64_t* K, const int* accumulate, mmemo_stream_t s) {
-  if (n < 1 || n > 6) return MMEMO_ERR_ARG;
-  GemmArgs g[6] = {};
-  int cb[6];
+  if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
+  GemmArgs g[GEMM_TC_MAX_GROUP] = {};
+  int cb[GEMM_TC_MAX_GROUP];
   bool tc_ok = true;
   for (int i = 0; i < n; ++i) {
     MM_REQUIRE(dy[i] && w[i] && dx[i]);
@@ -130,9 +130,9 @@ int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t*
     cb[i] = 1;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 1);
   }
-  if (tc_ok) return gemm_tc_grouped(g, cb, n, mm_stream(s));
+  if (tc_ok) return gemm_tc_grouped(g, cb, n, 1, mm_stream(s));
   for (int i = 0; i < n; ++i) {
-    const int rc = run(g[i], 1, 1, 1, mm_stream(s));
+    const int rc = run(g[i], 1, 1, 1, 1, mm_stream(s));
     if (rc) return rc;
   }
   return MMEMO_OK;
@@ -141,9 +141,9 @@ int mmemo_linear_bwd_w_grouped_bf16(int n, const void* const* dy, const int64_t*
                                     const void* const* x, const int64_t* ldx, float* const* dw,
                                     const int64_t* lddw, const int64_t* M, const int64_t* N,
                                     const int64_t* K, int accumulate, mmemo_stream_t s) {
-  if (n < 1 || n > 6) return MMEMO_ERR_ARG;
-  GemmArgs g[6] = {};
-  int cb[6];
+  if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
+  GemmArgs g[GEMM_TC_MAX_GROUP] = {};
+  int cb[GEMM_TC_MAX_GROUP];
   bool tc_ok = true;
   for (int i = 0; i < n; ++i) {
     MM_REQUIRE(dy[i] && x[i] && dw[i]);
@@ -157,9 +157,9 @@ int mmemo_linear_bwd_w_grouped_bf16(int n, const void* const* dy, const int64_t*
     cb[i] = 0;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 0);
   }
-  if (tc_ok) return gemm_tc_grouped(g, cb, n, mm_stream(s));
+  if (tc_ok) return gemm_tc_grouped(g, cb, n, 2, mm_stream(s));
   for (int i = 0; i < n; ++i) {
-    const int rc = run(g[i], 1, 1, 0, mm_stream(s));
+    const int rc = run(g[i], 1, 1, 0, 2, mm_stream(s));
     if (rc) return rc;
   }
   return MMEMO_OK;

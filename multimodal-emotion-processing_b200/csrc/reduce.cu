@@ -74,13 +74,14 @@ __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64
 }
 
 // several float32 tensors -> bf16 in ONE launch (all bf16 weight shadows of a block)
+constexpr int CAST_MAXT = 64;
 struct CastTable {
-  const float* src[8];
-  bf16* dst[8];
-  long long n[8];
+  const float* src[CAST_MAXT];
+  bf16* dst[CAST_MAXT];
+  long long n[CAST_MAXT];
   int count;
 };
-__global__ void __launch_bounds__(256) cast_multi_kernel(CastTable t) {
+__global__ void __launch_bounds__(256) cast_multi_kernel(const __grid_constant__ CastTable t) {
   const int which = blockIdx.y;
   pdl_wait();
   pdl_trigger();
@@ -122,6 +123,55 @@ colsum_bf16_vec_kernel(const bf16* __restrict__ x, int64_t ldx, float* __restric
 #pragma unroll 4
     for (int64_t m = r_beg + wy; m < r_end; m += 8) {
       const uint4 t = *reinterpret_cast<const uint4*>(x + m * ldx + n);
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[wy][lane * 8 + j] = acc[j];
+  __syncthreads();
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+// grouped column sums (the FFN-1 bias gradients of the nine chains of a trunk layer in one launch):
+// blockIdx.z selects the problem; same lane / warp layout as colsum_bf16_vec_kernel
+constexpr int CS_MAXP = 40;
+struct ColsumTable {
+  const bf16* x[CS_MAXP];
+  float* out[CS_MAXP];
+  long long M[CS_MAXP];
+};
+__global__ void __launch_bounds__(256)
+colsum_bf16_vec_grouped_kernel(const __grid_constant__ ColsumTable tb, int64_t N) {
+  __shared__ float red[8][256 + 8];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  pdl_wait();
+  pdl_trigger();
+  const bf16* __restrict__ x = tb.x[blockIdx.z];
+  float* __restrict__ out = tb.out[blockIdx.z];
+  const int64_t M = tb.M[blockIdx.z];
+  const int64_t rows_per_cta = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t n = (int64_t)blockIdx.x * 256 + lane * 8;
+  const int64_t r_beg = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t r_end = min(M, r_beg + rows_per_cta);
+  if (r_beg >= M) return;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (n < N) {
+#pragma unroll 4
+    for (int64_t m = r_beg + wy; m < r_end; m += 8) {
+      const uint4 t = *reinterpret_cast<const uint4*>(x + m * N + n);
       const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -205,8 +255,9 @@ int mmemo_cast_f32_to_bf16(const float* src, void* dst, int64_t n, mmemo_stream_
 int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const* dst,
                                  const int64_t* n, mmemo_stream_t s) {
   if (count <= 0) return MMEMO_OK;
-  if (count > 8) return MMEMO_ERR_ARG;
-  CastTable t = {};
+  if (count > CAST_MAXT) return MMEMO_ERR_ARG;
+  static thread_local CastTable t;
+  t = CastTable{};
   t.count = count;
   int64_t nmax = 0;
   for (int i = 0; i < count; ++i) {
@@ -224,6 +275,31 @@ int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const
   if (bx < 1) bx = 1;
   MM_CUDA_OK(mm_launch(cast_multi_kernel, dim3((unsigned)bx, (unsigned)count), dim3(256), 0,
                        mm_stream(s), t));
+  return MMEMO_OK;
+}
+/* out[i][c] += sum_m x[i][m, c] for n contiguous (M[i], N) bf16 matrices, one launch */
+int mmemo_colsum_grouped_bf16(int n, const void* const* x, float* const* out, const int64_t* M,
+                              int64_t N, mmemo_stream_t s) {
+  if (n < 1 || n > CS_MAXP) return MMEMO_ERR_ARG;
+  if (N <= 0 || N % 8) return MMEMO_ERR_SHAPE;
+  static thread_local ColsumTable tb;
+  int64_t mmax = 0;
+  for (int i = 0; i < n; ++i) {
+    MM_REQUIRE(x[i] && out[i] && M[i] >= 0);
+    if (reinterpret_cast<uintptr_t>(x[i]) % 16) return MMEMO_ERR_SHAPE;
+    tb.x[i] = static_cast<const bf16*>(x[i]);
+    tb.out[i] = out[i];
+    tb.M[i] = M[i];
+    mmax = M[i] > mmax ? M[i] : mmax;
+  }
+  if (mmax == 0) return MMEMO_OK;
+  const int64_t groups = cdiv(N, 256);
+  int64_t strips = cdiv(148 * 2, groups * n);
+  if (strips > cdiv(mmax, 32)) strips = cdiv(mmax, 32);
+  if (strips < 1) strips = 1;
+  MM_CUDA_OK(mm_launch(colsum_bf16_vec_grouped_kernel,
+                       dim3((unsigned)groups, (unsigned)strips, (unsigned)n), dim3(256), 0,
+                       mm_stream(s), tb, N));
   return MMEMO_OK;
 }
 int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_t s) {

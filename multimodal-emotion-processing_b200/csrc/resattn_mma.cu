@@ -37,7 +37,7 @@ namespace {
 constexpr int MAXP = 40;          // problems per launch
 constexpr int FWD_WARPS = 4, FWD_ROWS = 64;
 constexpr int BWD_WARPS = 8;
-constexpr size_t SMEM_MAX = 227 * 1024;
+constexpr size_t SMEM_MAX = 226 * 1024;   // dynamic part (227 KB per CTA minus static + reserve)
 
 struct Prob {
   const bf16 *q, *k, *v;
@@ -669,7 +669,7 @@ bool resattn_mma_supported(const mmemo_attn_problem& a, bool bwd) {
 
 int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
   if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
-  static Table T;      // host staging (copied by value into the launch)
+  static thread_local Table T;      // host staging (copied by value into the launch)
   T.n = n;
   const int hd = (int)ps[0].hd;
   size_t smem = 0;
@@ -687,7 +687,7 @@ int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
 #define MM_FWD(HD)                                                                               \
   {                                                                                              \
     MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_fwd_kernel<HD>,                                  \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
     MM_CUDA_OK(mm_launch(resattn_mma_fwd_kernel<HD>, dim3((unsigned)ctas), dim3(FWD_WARPS * 32), \
                          smem, st, T));                                                          \
   }
@@ -698,7 +698,7 @@ int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
 
 int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
   if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
-  static Table T;
+  static thread_local Table T;
   T.n = n;
   const int hd = (int)ps[0].hd;
   size_t smem64 = 0, smem32 = 0;
@@ -728,7 +728,7 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
 #define MM_BWD(HD, KBK, SM)                                                                       \
   {                                                                                               \
     MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_bwd_kernel<HD, KBK>,                              \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX)); \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)));     \
     MM_CUDA_OK(mm_launch(resattn_mma_bwd_kernel<HD, KBK>, dim3((unsigned)ctas),                   \
                          dim3(BWD_WARPS * 32), SM, st, T));                                       \
   }

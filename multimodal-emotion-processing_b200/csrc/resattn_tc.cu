@@ -283,12 +283,9 @@ int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const
   if (!aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o) ||
       (s_prev && !aligned16(s_prev)) || (s_out && !aligned16(s_out)))
     return MMEMO_ERR_ARG;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MM_CUDA_OK(cudaFuncSetAttribute(resattn_fwd_tc_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD));
-    attr_done = true;
-  }
+  // (idempotent: set on every call, so concurrent host threads cannot race on a guard variable)
+  MM_CUDA_OK(cudaFuncSetAttribute(resattn_fwd_tc_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_FWD));
   CUtensorMap tmQ, tmK, tmV, tmSp, tmSo, tmO;
   const uint64_t rows = (uint64_t)B * L, srows = (uint64_t)B * H * L, d = (uint64_t)H * HD;
   bool ok = make2d(&tmQ, q, d, rows, ldq, L) && make2d(&tmK, k, d, rows, ldk, L) &&
@@ -624,12 +621,8 @@ int resattn_bwd_tc(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
   const void* ptrs[] = {d_o, q, k, v, dq, dk, dv, s, s_prev, ds_next, ds_prev};
   for (const void* p : ptrs)
     if (p && !aligned16(p)) return MMEMO_ERR_ARG;
-  static bool attr_done = false;
-  if (!attr_done) {
-    MM_CUDA_OK(cudaFuncSetAttribute(resattn_bwd_tc_kernel,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD));
-    attr_done = true;
-  }
+  MM_CUDA_OK(cudaFuncSetAttribute(resattn_bwd_tc_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BWD));
   CUtensorMap tmQ, tmK, tmV, tmDO, tmS, tmSp, tmDSn, tmDSp, tmDQ, tmDK, tmDV;
   const uint64_t rows = (uint64_t)B * L, srows = (uint64_t)B * H * L, d = (uint64_t)H * HD;
   bool ok = make2d(&tmQ, q, d, rows, ldq, L) && make2d(&tmK, k, d, rows, ldk, L) &&

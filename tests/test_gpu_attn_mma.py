@@ -127,19 +127,28 @@ def test_grouped_attention_matches_oracle(si, prev, stored):
             if prev:
                 dsp = t["dsp"][..., :Lk].float().cpu()
                 assert rel_err(dsp[valid], r["dsp"][valid]) < 3e-2, tag
-                assert abs(t["dc"].item() - r["dc"].item()) < 3e-2 * max(1.0, abs(r["dc"].item())), tag
+                # dc = sum(dS * S_prev) is ONE cancelling sum over B*H*Lq*Lk signed bf16-noisy terms:
+                # its absolute error grows like sqrt(n) (0.05 at n = 6e5), not with |dc|
+                n_terms = p["B"] * p["H"] * p["Lq"] * Lk
+                tol = 3e-2 * max(1.0, abs(r["dc"].item()), n_terms ** 0.5 / 250.0)
+                assert abs(t["dc"].item() - r["dc"].item()) < tol, tag
 
 
 def test_fully_masked_rows_are_uniform_on_the_mma_path():
-    """mask all zero -> exactly uniform 1/Lk attention (the -1e8 absorbs QK^T), no NaN."""
+    """mask all zero -> exactly uniform 1/Lk attention, no NaN.  In bf16 mode EVERY score of such a
+    row is bf16(-1e8) (the ulp there is 2^19, far above any QK^T), so the output is the plain mean
+    of V - what the reference's own .bfloat16() run computes.  (The fp32 oracle is not the yardstick
+    for these rows: in fp32 a |QK^T/sqrt(hd)| >= 4 survives the subtraction quantised to 8.)"""
     p = _problem(5, 2, 6, 50, 50, 16, False, False)
     p["mask"][1] = 0
     r = _oracle(p, use_dsn=False)
     o, s, _ = ops.resattn_op(p["q"].to(DEV).bfloat16(), p["k"].to(DEV).bfloat16(),
                              p["v"].to(DEV).bfloat16(), p["mask"].to(DEV), None, None, 6)
     assert torch.isfinite(o.float()).all()
-    assert rel_err(o.float(), r["o"]) < 2e-2
-    assert torch.equal(s[1].float().cpu(), r["s"][1])          # -1e8 exactly
+    assert rel_err(o[0].float(), r["o"][0]) < 2e-2                 # the normally masked sample
+    expect = p["v"][1].mean(0, keepdim=True).expand(50, -1)        # uniform attention = mean of V
+    assert rel_err(o[1].float(), expect) < 2e-2
+    assert bool((s[1].float() == torch.tensor(-1.0e8).bfloat16().float()).all())
 
 
 def test_mma_path_is_the_one_that_runs():

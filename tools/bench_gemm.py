@@ -38,11 +38,4 @@ for (M, N, K) in shapes:
     t_br = timeit(lambda: ops._linear_fwd(True, x, w, b, None, y, relu=True))
     t_acc = timeit(lambda: ops._linear_bwd_x(True, dy, w, dx, accumulate=True))
     t_rs = timeit(lambda: ops._linear_bwd_x(True, dy, w, dx, relu_src=x))
-    import ctypes
-    L = ops._lib.load(); L.mmemo_debug_gemm_force_1cta.argtypes = [ctypes.c_int]
-    L.mmemo_debug_gemm_force_1cta(1)
-    t1 = timeit(lambda: ops._linear_fwd(True, x, w, None, None, y))
-    t1w = timeit(lambda: ops._linear_bwd_w(True, dy, x, dw))
-    L.mmemo_debug_gemm_force_1cta(0)
-    print(f"      1-CTA 128x128 config: fwd {t1:6.1f}us bwd_w {t1w:6.1f}us")
     print(f"      fwd+bias {t_b:6.1f}us  fwd+bias+relu {t_br:6.1f}us  bwd_x+accumulate {t_acc:6.1f}us  bwd_x+relu_mask {t_rs:6.1f}us", flush=True)
