@@ -155,15 +155,62 @@ def _algorithmic(name: str, a: tuple):
     formulas of SURVEY.md §8d)."""
     bf = name.endswith("_bf16")
     e = 2 if bf else 4
+    if name.startswith("mmemo_resattn") and "_grouped_" in name:
+        import ctypes as C
+        from mmemo_b200 import _lib
+        n = a[0]
+        ps = C.cast(a[1], C.POINTER(_lib.AttnProblem))
+        bwd = "_bwd_" in name
+        fl = by = 0
+        tags = {}
+        for i in range(n):
+            q = ps[i]
+            d, S = q.H * q.hd, q.B * q.H * q.Lq * q.Lk
+            kv = 1 if q.k == q.v else 2
+            if not bwd:
+                by += e * q.B * d * (q.Lq + kv * q.Lk) + 4 * q.B * q.Lk + e * q.B * q.Lq * d
+                by += e * S * (1 if q.s_prev else 0) + e * S * (1 if q.s_out else 0)
+                fl += 4 * q.B * q.Lq * q.Lk * d
+                t = f"L{q.Lq}x{q.Lk}{'+prev' if q.s_prev else ''}{'+S' if q.s_out else ''}"
+            else:
+                by += e * q.B * d * (2 * q.Lq + kv * q.Lk) + e * q.B * d * (q.Lq + kv * q.Lk)
+                by += e * q.B * q.Lq * d
+                by += e * S * ((1 if q.s else 0) + (1 if q.ds_next else 0))
+                by += e * S * ((1 if q.s_prev else 0) + (1 if q.ds_prev else 0))
+                fl += (8 if q.s else 10) * q.B * q.Lq * q.Lk * d
+                t = (f"L{q.Lq}x{q.Lk}{'+S' if q.s else '+recompute'}{'+prev' if q.s_prev else ''}"
+                     f"{'+dSnext' if q.ds_next else ''}")
+            tags[t] = tags.get(t, 0) + 1
+        q0 = ps[0]
+        return fl, by, f"G{n}:B{q0.B}H{q0.H}hd{q0.hd}:" + ",".join(f"{v}x{k}" for k, v in tags.items())
+    if name.startswith("mmemo_add_ln_fwd_grouped"):
+        Ms, d = list(a[9]), a[10]
+        nres = sum(1 for r in a[1] if r)
+        return (8 * sum(Ms) * d, e * d * (2 * sum(Ms) + (sum(Ms) * nres // max(1, len(Ms)))),
+                f"G{a[0]}:{max(Ms)}x{d}")
+    if name.startswith("mmemo_add_ln_bwd_grouped"):
+        Ms, d = list(a[14]), a[15]
+        nres = sum(1 for r in a[2] if r)
+        return (16 * sum(Ms) * d, e * d * (3 * sum(Ms) + 2 * (sum(Ms) * nres // max(1, len(Ms)))),
+                f"G{a[0]}:{max(Ms)}x{d}")
+    if name.startswith("mmemo_colsum_grouped"):
+        Ms, N = list(a[3]), a[4]
+        return sum(Ms) * N, e * sum(Ms) * N, f"G{a[0]}:{max(Ms)}x{N}"
     if "_grouped_" in name:   # host arrays of per-problem M, N, K
-        i0 = 8 if name.startswith("mmemo_linear_fwd") else 7
+        i0 = 8 if name.startswith("mmemo_linear_fwd") else (9 if name.startswith("mmemo_linear_bwd_x") else 7)
         Ms, Ns, Ks = list(a[i0]), list(a[i0 + 1]), list(a[i0 + 2])
         fl = sum(2 * m * n * k for m, n, k in zip(Ms, Ns, Ks))
         if name.startswith("mmemo_linear_bwd_w"):
             by = sum(e * (m * n + m * k) + 4 * n * k for m, n, k in zip(Ms, Ns, Ks))
         else:
             by = sum(e * (m * k + n * k + m * n) for m, n, k in zip(Ms, Ns, Ks))
-        return fl, by, "+".join(f"{m}x{n}x{k}" for m, n, k in zip(Ms, Ns, Ks))
+        shapes = [f"{m}x{n}x{k}" for m, n, k in zip(Ms, Ns, Ks)]
+        if len(shapes) > 6:       # large groups: count per distinct shape
+            cnt = {}
+            for sh in shapes:
+                cnt[sh] = cnt.get(sh, 0) + 1
+            return fl, by, f"G{len(shapes)}:" + ",".join(f"{v}x{k}" for k, v in cnt.items())
+        return fl, by, "+".join(shapes)
     if name.startswith("mmemo_linear_fwd"):
         M, N, K = a[10], a[11], a[12]
         ex = 4 if a[1] else e
@@ -299,12 +346,34 @@ def instrumented_step(step_fn, reps: int = 10, cold: bool = True):
         r["flops"] += fl
         r["bytes"] += by
 
+    real_try = ops._try_call
+
+    def try_via_call(name, *args):
+        real(name, *args)          # raises on any error (incl. unsupported shape)
+        return True
+
+    def hooked_try(name, *args):
+        if not real_try(name, *args):
+            return False
+        fl, by, tag = _algorithmic(name, args)
+        key = name.replace("mmemo_", "") + (":" + tag if tag else "")
+        r = fam.get(key)
+        if r is None:
+            r = fam[key] = dict(n=0, ms_each=measure(name, args), flops=0, bytes=0)
+            r["ms_cold"] = measure_cold(name, args) if cold else None
+        r["n"] += 1
+        r["flops"] += fl
+        r["bytes"] += by
+        return True
+
     ops._call = hooked
+    ops._try_call = hooked_try
     try:
         step_fn()
         torch.cuda.synchronize()
     finally:
         ops._call = real
+        ops._try_call = real_try
     for r in fam.values():
         r["ms"] = r["ms_each"] * r["n"]
     return fam, sum(r["ms"] for r in fam.values())

@@ -96,10 +96,11 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
                                   const void* const* w, const int64_t* ldw,
                                   const float* const* bias, void* const* y, const int64_t* ldy,
                                   const int64_t* M, const int64_t* N, const int64_t* K,
-                                  const int* relu, mmemo_stream_t stream);
+                                  const int* relu, const int* accumulate, mmemo_stream_t stream);
 int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
                                     const void* const* w, const int64_t* ldw, void* const* dx,
-                                    const int64_t* lddx, const int64_t* M, const int64_t* N,
+                                    const int64_t* lddx, const void* const* relu_src,
+                                    const int64_t* ldrelu, const int64_t* M, const int64_t* N,
                                     const int64_t* K, const int* accumulate, mmemo_stream_t stream);
 /* accumulate: 0 = dw is overwritten, 1 = dw += ..., 2 = the caller guarantees that every dw is
  * all zero (both are correct; the split-K reduce-add path then skips its own zero fill). */

@@ -4,6 +4,7 @@
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -140,6 +141,10 @@ class LiteAttentionBlock(nn.Module):
     def _norm(self) -> nn.LayerNorm:
         return getattr(self, self._norm_name)
 
+    def _params(self) -> List[torch.Tensor]:
+        n = self._norm
+        return [self.proj.weight, self.minus.weight, n.weight, n.bias, self.c]
+
     def multi_head_attention(self, q, k, v, mask, scores=None):
         bf = is_bf16()
         q, k, v = as_act(q), as_act(k), as_act(v)
@@ -172,11 +177,66 @@ CHAINS = [("l", "l"), ("l", "v"), ("l", "a"), ("v", "v"), ("v", "l"), ("v", "a")
           ("a", "a"), ("a", "l"), ("a", "v")]
 
 
+# One grouped launch per kernel and layer over all chains (group_ops.py); False = the per-block
+# path (one autograd node per block), kept for A/B measurements and as the dropout-training path.
+GROUPED_TRUNK = os.environ.get("MMEMO_GROUPED_TRUNK", "1") != "0"
+
+
 def fusion_trunk(blocks: Sequence[nn.Module], n_layers: int, feats: Dict[str, torch.Tensor],
                  masks: Dict[str, torch.Tensor], keep_all: bool) -> torch.Tensor:
     """Run the nine chains and pool.  Block ``n_layers*chain + i`` is layer i of a chain; scores
     restart at None per chain; the q-stream evolves while k = v = the un-evolved source modality.
     Returns the float32 pooled features (B, 6*d*(n_layers if keep_all else 1))."""
+    return fusion_trunk_multi([(blocks, feats, masks)], n_layers, keep_all)[0]
+
+
+def fusion_trunk_multi(towers, n_layers: int, keep_all: bool) -> List[torch.Tensor]:
+    """Several independent trunks of the same architecture at once — the two towers of
+    ``Concat_Trans`` / ``Base_model`` (cmu-mosei/run.py:330-331, Ren-MME/run.py:283-284), the
+    members of an ensemble (robot_demo.py:610-614).  ``towers`` = [(blocks, feats, masks), ...];
+    returns one pooled tensor per tower.  Layer i of every chain of every tower is one grouped op
+    (``group_ops``) unless dropout is active in training (no fused dropout in the grouped path)."""
+    blk0 = towers[0][0][0]
+    if not GROUPED_TRUNK or (blk0.training and blk0.drop.p > 0):
+        return [_fusion_trunk_per_block(b, n_layers, f, m, keep_all) for b, f, m in towers]
+    from . import group_ops
+    bf = is_bf16()
+    full = isinstance(blk0, FullAttentionBlock)
+    op = group_ops.trunk_full_op if full else group_ops.trunk_lite_op
+    n_out = group_ops.FULL_OUT if full else group_ops.LITE_OUT
+    qs, kvs, ms = [], [], []
+    for _, feats, masks in towers:
+        act = {k: as_act(v) for k, v in feats.items()}      # one cast per modality
+        for qm, sm in CHAINS:
+            qs.append(act[qm])
+            kvs.append(act[sm])
+            ms.append(masks[sm] if masks[sm] is not None else torch.empty(0, device=act[qm].device))
+    G = len(qs)
+    s_prev: List[torch.Tensor] = []
+    per_chain: List[List[torch.Tensor]] = [[] for _ in range(G)]
+    for i in range(n_layers):
+        params = [p for blocks, _, _ in towers for ci in range(len(CHAINS))
+                  for p in blocks[n_layers * ci + i]._params()]
+        emit = i + 1 < n_layers                 # the last layer's scores feed nothing
+        res = op(qs, kvs, ms, s_prev, params, blk0.n_heads, bf, emit)
+        qs = [res[n_out * g] for g in range(G)]
+        s_prev = [res[n_out * g + 1] for g in range(G)] if emit else []
+        for g in range(G):
+            if keep_all or i + 1 == n_layers:
+                per_chain[g].append(qs[g])
+    pooled = []
+    for t in range(len(towers)):
+        outs: Dict[str, List[torch.Tensor]] = {"l": [], "v": [], "a": []}
+        for ci, (qm, _) in enumerate(CHAINS):
+            outs[qm] += per_chain[t * len(CHAINS) + ci]
+        # feature concat per modality, position concat in the order (l, a, v), mean||max pooling
+        pooled.append(ops.pool(outs["l"] + outs["a"] + outs["v"], 3))
+    return pooled
+
+
+def _fusion_trunk_per_block(blocks: Sequence[nn.Module], n_layers: int,
+                            feats: Dict[str, torch.Tensor], masks: Dict[str, torch.Tensor],
+                            keep_all: bool) -> torch.Tensor:
     outs: Dict[str, List[torch.Tensor]] = {"l": [], "v": [], "a": []}
     for ci, (qm, sm) in enumerate(CHAINS):
         q, s = feats[qm], None

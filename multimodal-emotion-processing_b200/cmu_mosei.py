@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .blocks import LiteAttentionBlock, as_mask, fusion_trunk, is_bf16
+from .blocks import LiteAttentionBlock, as_mask, fusion_trunk_multi, is_bf16
 
 # reference module constants (cmu-mosei/run.py:24-42) read inside the classes
 L_DIM, V_DIM, A_DIM = 300, 35, 74
@@ -25,6 +25,9 @@ class Unify_Dimension(nn.Module):
 
     def forward(self, l, v, a):
         bf = is_bf16()
+        if bf:      # the bf16 shadows of all projection weights in one cast launch
+            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
+                                   for m in (self.linguistic, self.visual, self.acoustic)])
         return (ops.linear(l, self.linguistic.weight, bf16=bf),
                 ops.linear(v, self.visual.weight, bf16=bf),
                 ops.linear(a, self.acoustic.weight, bf16=bf))
@@ -50,11 +53,15 @@ class Multi_ATTN(nn.Module):
                                                 for _ in range(9 * n_layers)])
         self.classifier = nn.Linear(dim * 6 * n_layers, self.N_CLS, bias=False)
 
-    def forward(self, l, v, a, l_mask, v_mask, a_mask):
+    def _tower(self, l, v, a, l_mask, v_mask, a_mask):
+        """(blocks, projected features, masks) - the input of ``fusion_trunk_multi``."""
         l, v, a = self.unify_dimension(l, v, a)
-        x = fusion_trunk(self.multimodal_blocks, self.n_layers, {"l": l, "v": v, "a": a},
-                         {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)},
-                         keep_all=True)
+        return (self.multimodal_blocks, {"l": l, "v": v, "a": a},
+                {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)})
+
+    def forward(self, l, v, a, l_mask, v_mask, a_mask):
+        x = fusion_trunk_multi([self._tower(l, v, a, l_mask, v_mask, a_mask)], self.n_layers,
+                               keep_all=True)[0]
         return ops.linear(x, self.classifier.weight)
 
 
@@ -73,10 +80,14 @@ class Concat_Trans(nn.Module):
         self.out = nn.Linear(14, 7)
 
     def forward(self, l, v, a, l_mask, v_mask, a_mask):
-        last_feat = self.intensity(l[:, 0], v[:, 0], a[:, 0], l_mask[:, 0], v_mask[:, 0],
-                                   a_mask[:, 0])
-        this_feat = self.stimulation(l[:, 1], v[:, 1], a[:, 1], l_mask[:, 1], v_mask[:, 1],
-                                     a_mask[:, 1])
+        # both towers' trunks as ONE group per layer (they are independent until the bilinear head)
+        ti, ts = self.intensity, self.stimulation
+        pi, ps = fusion_trunk_multi(
+            [ti._tower(l[:, 0], v[:, 0], a[:, 0], l_mask[:, 0], v_mask[:, 0], a_mask[:, 0]),
+             ts._tower(l[:, 1], v[:, 1], a[:, 1], l_mask[:, 1], v_mask[:, 1], a_mask[:, 1])],
+            ti.n_layers, keep_all=True)
+        last_feat = ops.linear(pi, ti.classifier.weight)
+        this_feat = ops.linear(ps, ts.classifier.weight)
         return ops.bilinear_head(this_feat, last_feat, self.trans, self.norm1.weight,
                                  self.norm1.bias, self.out.weight, self.out.bias)
 

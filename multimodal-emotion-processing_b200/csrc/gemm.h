@@ -25,7 +25,7 @@ int gemm_simt(const GemmArgs& g, int a_bf16, int b_bf16, int c_bf16, cudaStream_
 
 // tcgen05/TMA path (bf16 operands, fp32 accumulate in TMEM).  c_bf16=0 -> float32 C.
 // Returns 1 if it accepts the shape/layout.
-bool gemm_tc_supported(const GemmArgs& g, int c_bf16);
+bool gemm_tc_supported(const GemmArgs& g, int c_bf16, bool any_size = false);
 // family: 0 forward, 1 dX, 2 dW (only names the kernel instantiation)
 int gemm_tc(const GemmArgs& g, int c_bf16, int family, cudaStream_t st);
 // up to 48 independent problems in one persistent launch (every problem must be gemm_tc_supported)

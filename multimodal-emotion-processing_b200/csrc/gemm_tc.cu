@@ -469,9 +469,16 @@ bool mm_make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box);
 }
 
-bool gemm_tc_supported(const GemmArgs& g, int c_bf16) {
-  if (g.M < 64 || g.N < 64 || g.K < 64) return false;
-  if ((double)g.M * (double)g.N * (double)g.K < (double)(1 << 22)) return false;
+bool gemm_tc_supported(const GemmArgs& g, int c_bf16, bool any_size) {
+  // Size floor: a lone small GEMM is faster on the SIMT kernel than on a 128-row tensor-core tile.
+  // Inside a GROUPED launch (any_size) small problems ride along with the others - TMA zero-fills
+  // / clips the rows and columns a tile has beyond the matrix - which is what keeps a batch-1
+  // inference layer (M = 25 rows) at one launch per kernel kind.
+  if (!any_size) {
+    if (g.M < 64 || g.N < 64 || g.K < 64) return false;
+    if ((double)g.M * (double)g.N * (double)g.K < (double)(1 << 22)) return false;
+  }
+  if (g.M < 1 || g.N < 8 || g.K < 8) return false;
   if (g.M > (1ll << 31) - 512 || g.N > (1ll << 31) - 512 || g.K > (1ll << 31) - 512) return false;
   const bool a_k = (g.sAk == 1 && g.sAm % 8 == 0), a_mn = (g.sAm == 1 && g.sAk % 8 == 0);
   const bool b_k = (g.sBk == 1 && g.sBn % 8 == 0), b_mn = (g.sBn == 1 && g.sBk % 8 == 0);

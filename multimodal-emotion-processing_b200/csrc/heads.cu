@@ -18,86 +18,101 @@ __device__ __forceinline__ float logsigmoidf_(float x) {
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void state_transfer_fwd_kernel(const float* __restrict__ feats,
-                                          const float* __restrict__ trans, float* __restrict__ out,
-                                          int B, int P, int C) {
+// One WARP per sample: lane k owns class k; the (C x C) transfer matrix sits in shared memory and
+// the previous window's mixed output travels between lanes by shuffles.  (One thread per sample
+// with register arrays indexed at run time put those arrays in local memory and left 31 lanes
+// idle: 280 us for B = 32 - the step's longest single kernel.)
+__global__ void __launch_bounds__(256)
+state_transfer_fwd_kernel(const float* __restrict__ feats, const float* __restrict__ trans,
+                          float* __restrict__ out, int B, int P, int C) {
   __shared__ float T[CMAX * CMAX];
   for (int i = threadIdx.x; i < C * C; i += blockDim.x) T[i] = trans[i];
   __syncthreads();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= B) return;
-  float op[CMAX], gp[CMAX], o[CMAX], g[CMAX];
+  const bool on = lane < C;
+  float op = 0.f, gp = 0.f;
   for (int i = 0; i < P; ++i) {
     const float* f = feats + ((int64_t)b * P + i) * 2 * C;
-    for (int k = 0; k < C; ++k) { o[k] = f[k]; g[k] = f[C + k]; }
+    float o = on ? f[lane] : 0.f;
+    const float g = on ? f[C + lane] : 0.f;
     if (i > 0) {
-      for (int k = 0; k < C; ++k) {
-        const float alpha = sigmoidf_(g[k] + gp[k]);
-        float u = 0.f;
-        for (int j = 0; j < C; ++j) u = fmaf(op[j], T[j * C + k], u);
-        o[k] = (1.0f - alpha) * o[k] + alpha * tanhf(u);
+      float u = 0.f;
+      for (int j = 0; j < C; ++j) {
+        const float opj = __shfl_sync(0xffffffffu, op, j);
+        if (on) u = fmaf(opj, T[j * C + lane], u);
       }
+      const float alpha = sigmoidf_(g + gp);
+      o = (1.0f - alpha) * o + alpha * tanhf(u);
     }
-    for (int k = 0; k < C; ++k) {
-      out[((int64_t)b * P + i) * C + k] = o[k];
-      op[k] = o[k];
-      gp[k] = g[k];
-    }
+    if (on) out[((int64_t)b * P + i) * C + lane] = o;
+    op = o;
+    gp = g;
   }
 }
 
-__global__ void state_transfer_bwd_kernel(const float* __restrict__ dout,
-                                          const float* __restrict__ feats,
-                                          const float* __restrict__ trans,
-                                          const float* __restrict__ out, float* __restrict__ dfeats,
-                                          float* __restrict__ dtrans, int B, int P, int C) {
+__global__ void __launch_bounds__(256)
+state_transfer_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ feats,
+                          const float* __restrict__ trans, const float* __restrict__ out,
+                          float* __restrict__ dfeats, float* __restrict__ dtrans, int B, int P,
+                          int C) {
   __shared__ float T[CMAX * CMAX];
-  __shared__ float dT[CMAX * CMAX];
-  for (int i = threadIdx.x; i < C * C; i += blockDim.x) { T[i] = trans[i]; dT[i] = 0.f; }
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) T[i] = trans[i];
   __syncthreads();
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {
-    float cdo[CMAX], cdg[CMAX], du[CMAX], ndo[CMAX];
-    for (int k = 0; k < C; ++k) { cdo[k] = 0.f; cdg[k] = 0.f; }
-    for (int i = P - 1; i >= 0; --i) {
-      const float* f = feats + ((int64_t)b * P + i) * 2 * C;
-      const float* dy = dout + ((int64_t)b * P + i) * C;
-      float* df = dfeats + ((int64_t)b * P + i) * 2 * C;
-      if (i > 0) {
-        const float* fp = feats + ((int64_t)b * P + i - 1) * 2 * C;
-        const float* op = out + ((int64_t)b * P + i - 1) * C;
-        for (int k = 0; k < C; ++k) {
-          const float dtot = dy[k] + cdo[k];
-          const float a = sigmoidf_(f[C + k] + fp[C + k]);
-          float u = 0.f;
-          for (int j = 0; j < C; ++j) u = fmaf(op[j], T[j * C + k], u);
-          const float t0 = tanhf(u);
-          df[k] = dtot * (1.0f - a);
-          const float dgs = dtot * (t0 - f[k]) * a * (1.0f - a);
-          df[C + k] = dgs + cdg[k];
-          cdg[k] = dgs;
-          du[k] = dtot * a * (1.0f - t0 * t0);
-        }
-        for (int j = 0; j < C; ++j) {
-          float t = 0.f;
-          for (int k = 0; k < C; ++k) {
-            t = fmaf(du[k], T[j * C + k], t);
-            atomicAdd(&dT[j * C + k], op[j] * du[k]);
-          }
-          ndo[j] = t;
-        }
-        for (int k = 0; k < C; ++k) cdo[k] = ndo[k];
-      } else {
-        for (int k = 0; k < C; ++k) {
-          df[k] = dy[k] + cdo[k];
-          df[C + k] = cdg[k];
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const bool on = lane < C;
+  float cdo = 0.f, cdg = 0.f;          // gradients carried from window i+1 into (o_i, g_i)
+  float dTr[CMAX];                     // column `lane` of dT, rows j
+#pragma unroll
+  for (int j = 0; j < CMAX; ++j) dTr[j] = 0.f;
+  for (int i = P - 1; i >= 0; --i) {
+    const float* f = feats + ((int64_t)b * P + i) * 2 * C;
+    float* df = dfeats + ((int64_t)b * P + i) * 2 * C;
+    const float dy = on ? dout[((int64_t)b * P + i) * C + lane] : 0.f;
+    const float dtot = dy + cdo;
+    if (i > 0) {
+      const float fo = on ? f[lane] : 0.f, fg = on ? f[C + lane] : 0.f;
+      const float gpv = on ? feats[((int64_t)b * P + i - 1) * 2 * C + C + lane] : 0.f;
+      const float op = on ? out[((int64_t)b * P + i - 1) * C + lane] : 0.f;
+      float u = 0.f;
+      for (int j = 0; j < C; ++j) {
+        const float opj = __shfl_sync(0xffffffffu, op, j);
+        if (on) u = fmaf(opj, T[j * C + lane], u);
+      }
+      const float a = sigmoidf_(fg + gpv);
+      const float t0 = tanhf(u);
+      const float dgs = dtot * (t0 - fo) * a * (1.0f - a);
+      const float du = on ? dtot * a * (1.0f - t0 * t0) : 0.f;
+      if (on) {
+        df[lane] = dtot * (1.0f - a);
+        df[C + lane] = dgs + cdg;
+      }
+      cdg = dgs;
+      // d o_{i-1}[j] = sum_k du[k] T[j][k]  (lane = j);  dT[j][k] += o_{i-1}[j] du[k]  (lane = k)
+      float ndo = 0.f;
+#pragma unroll
+      for (int k = 0; k < CMAX; ++k) {
+        if (k < C) {
+          const float duk = __shfl_sync(0xffffffffu, du, k);
+          const float opk = __shfl_sync(0xffffffffu, op, k);
+          if (on) ndo = fmaf(duk, T[lane * C + k], ndo);
+          dTr[k] = fmaf(opk, du, dTr[k]);
         }
       }
+      cdo = ndo;
+    } else if (on) {
+      df[lane] = dtot;
+      df[C + lane] = cdg;
     }
   }
-  __syncthreads();
-  if (dtrans)
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) atomicAdd(dtrans + i, dT[i]);
+  if (dtrans && on) {
+#pragma unroll
+    for (int j = 0; j < CMAX; ++j)
+      if (j < C) atomicAdd(dtrans + j * C + lane, dTr[j]);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -143,16 +158,22 @@ bilinear_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ th
                     const float* __restrict__ gamma, const float* __restrict__ W,
                     const float* __restrict__ zsave, float* __restrict__ dth,
                     float* __restrict__ dla, float* __restrict__ dT, float* __restrict__ dgamma,
-                    float* __restrict__ dbeta, float* __restrict__ dbias, int B, int C, float eps) {
-  extern __shared__ float sm[];  // [C^3] dT | [C] dbias | [C] dgamma | [C] dbeta
+                    float* __restrict__ dbeta, float* __restrict__ dbias, int B, int C, float eps,
+                    int copies) {
+  // [copies][C^3] dT | [C] dbias | [C] dgamma | [C] dbeta.  copies = 8 (one private dT per warp:
+  // plain += by the lane that owns class k, no shared-memory atomics - those are CAS loops and
+  // made this the longest kernel of the rencecps step) when it fits, else 1 (atomics).
+  extern __shared__ float sm[];
+  const int C3 = C * C * C;
   float* sT = sm;
-  float* sb = sT + C * C * C;
+  float* sb = sT + copies * C3;
   float* sg = sb + C;
   float* sbe = sg + C;
-  const int nsm = C * C * C + 3 * C;
+  const int nsm = copies * C3 + 3 * C;
   for (int i = threadIdx.x; i < nsm; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* myT = sT + (copies > 1 ? warp * C3 : 0);
   for (int b = blockIdx.x * 8 + warp; b < B; b += gridDim.x * 8) {
     const float z = lane < C ? zsave[b * C + lane] : 0.f;
     const float mean = warp_sum(z) / (float)C;
@@ -201,13 +222,20 @@ bilinear_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ th
       const float tj = __shfl_sync(0xffffffffu, thv, j);
       for (int m = 0; m < C; ++m) {
         const float lm = __shfl_sync(0xffffffffu, lav, m);
-        if (lane < C) atomicAdd(&sT[(j * C + m) * C + lane], tj * lm * dz);
+        if (lane < C) {
+          if (copies > 1) myT[(j * C + m) * C + lane] += tj * lm * dz;
+          else atomicAdd(&sT[(j * C + m) * C + lane], tj * lm * dz);
+        }
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * C * C; i += blockDim.x)
-    if (dT) atomicAdd(dT + i, sT[i]);
+  for (int i = threadIdx.x; i < C3; i += blockDim.x)
+    if (dT) {
+      float t = 0.f;
+      for (int c = 0; c < copies; ++c) t += sT[c * C3 + i];
+      atomicAdd(dT + i, t);
+    }
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     if (dgamma) atomicAdd(dgamma + i, sg[i]);
     if (dbeta) atomicAdd(dbeta + i, sbe[i]);
@@ -340,7 +368,7 @@ int mmemo_state_transfer_fwd(const float* feats, const float* trans, float* out,
   if (B <= 0 || P <= 0) return MMEMO_OK;
   MM_REQUIRE(feats && trans && out);
   if (C < 1 || C > CMAX) return MMEMO_ERR_SHAPE;
-  state_transfer_fwd_kernel<<<(unsigned)cdiv(B, 64), 64, 0, mm_stream(s)>>>(feats, trans, out,
+  state_transfer_fwd_kernel<<<(unsigned)cdiv(B, 8), 256, 0, mm_stream(s)>>>(feats, trans, out,
                                                                            (int)B, (int)P, (int)C);
   MM_LAUNCH_OK();
   return MMEMO_OK;
@@ -351,7 +379,7 @@ int mmemo_state_transfer_bwd(const float* dout, const float* feats, const float*
   if (B <= 0 || P <= 0) return MMEMO_OK;
   MM_REQUIRE(dout && feats && trans && out && dfeats);
   if (C < 1 || C > CMAX) return MMEMO_ERR_SHAPE;
-  state_transfer_bwd_kernel<<<(unsigned)cdiv(B, 64), 64, 0, mm_stream(s)>>>(
+  state_transfer_bwd_kernel<<<(unsigned)cdiv(B, 8), 256, 0, mm_stream(s)>>>(
       dout, feats, trans, out, dfeats, dtrans, (int)B, (int)P, (int)C);
   MM_LAUNCH_OK();
   return MMEMO_OK;
@@ -376,12 +404,13 @@ int mmemo_bilinear_head_bwd(const float* dout, const float* this_feat, const flo
   if (B <= 0) return MMEMO_OK;
   MM_REQUIRE(dout && this_feat && last_feat && trans && gamma && beta && w && z && dthis && dlast);
   if (C < 1 || C > CMAX) return MMEMO_ERR_SHAPE;
-  const size_t smem = sizeof(float) * (C * C * C + 3 * C);
+  const int copies = (C <= 10) ? 8 : 1;                    // 8 x C^3 floats <= 32 KB
+  const size_t smem = sizeof(float) * (copies * C * C * C + 3 * C);
   int64_t blocks = cdiv(B, 8);
   if (blocks > 32) blocks = 32;
   bilinear_bwd_kernel<<<(unsigned)blocks, 256, smem, mm_stream(s)>>>(
       dout, this_feat, last_feat, trans, gamma, w, z, dthis, dlast, dtrans, dgamma, dbeta, dbias,
-      (int)B, (int)C, eps);
+      (int)B, (int)C, eps, copies);
   MM_LAUNCH_OK();
   if (dw) {  // dW needs the full concat value LN(z)+beta: thread per weight, loop over the batch
     bilinear_dw_kernel<<<(unsigned)cdiv(2 * C * C, 128), 128, 0, mm_stream(s)>>>(

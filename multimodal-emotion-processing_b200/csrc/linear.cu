@@ -88,7 +88,7 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
                                   const void* const* w, const int64_t* ldw,
                                   const float* const* bias, void* const* y, const int64_t* ldy,
                                   const int64_t* M, const int64_t* N, const int64_t* K,
-                                  const int* relu, mmemo_stream_t s) {
+                                  const int* relu, const int* accumulate, mmemo_stream_t s) {
   if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
   GemmArgs g[GEMM_TC_MAX_GROUP] = {};
   int cb[GEMM_TC_MAX_GROUP];
@@ -101,8 +101,9 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
     g[i].M = M[i]; g[i].N = N[i]; g[i].K = K[i];
     g[i].bias = bias ? bias[i] : nullptr; g[i].pos_period = 1;
     g[i].relu = relu ? relu[i] : 0;
+    g[i].accumulate = accumulate ? accumulate[i] : 0;
     cb[i] = 1;
-    tc_ok = tc_ok && gemm_tc_supported(g[i], 1);
+    tc_ok = tc_ok && gemm_tc_supported(g[i], 1, n > 1);
   }
   if (tc_ok) return gemm_tc_grouped(g, cb, n, 0, mm_stream(s));
   for (int i = 0; i < n; ++i) {
@@ -113,7 +114,8 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
 }
 int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
                                     const void* const* w, const int64_t* ldw, void* const* dx,
-                                    const int64_t* lddx, const int64_t* M, const int64_t* N,
+                                    const int64_t* lddx, const void* const* relu_src,
+                                    const int64_t* ldrelu, const int64_t* M, const int64_t* N,
                                     const int64_t* K, const int* accumulate, mmemo_stream_t s) {
   if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
   GemmArgs g[GEMM_TC_MAX_GROUP] = {};
@@ -127,8 +129,11 @@ int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t*
     g[i].M = M[i]; g[i].N = K[i]; g[i].K = N[i];
     g[i].pos_period = 1;
     g[i].accumulate = accumulate ? accumulate[i] : 0;
+    if (relu_src && relu_src[i]) {
+      g[i].relu_src = relu_src[i]; g[i].ldrelu = ldrelu[i]; g[i].relu_src_bf16 = 1;
+    }
     cb[i] = 1;
-    tc_ok = tc_ok && gemm_tc_supported(g[i], 1);
+    tc_ok = tc_ok && gemm_tc_supported(g[i], 1, n > 1);
   }
   if (tc_ok) return gemm_tc_grouped(g, cb, n, 1, mm_stream(s));
   for (int i = 0; i < n; ++i) {
@@ -155,7 +160,7 @@ int mmemo_linear_bwd_w_grouped_bf16(int n, const void* const* dy, const int64_t*
     g[i].accumulate = accumulate == 1;
     g[i].c_zeroed = accumulate == 2;      // either overwrite or add is correct
     cb[i] = 0;
-    tc_ok = tc_ok && gemm_tc_supported(g[i], 0);
+    tc_ok = tc_ok && gemm_tc_supported(g[i], 0, n > 1);
   }
   if (tc_ok) return gemm_tc_grouped(g, cb, n, 2, mm_stream(s));
   for (int i = 0; i < n; ++i) {

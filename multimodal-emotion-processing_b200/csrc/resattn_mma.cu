@@ -547,39 +547,53 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     }
     __syncthreads();
     // ================= phase B: dV = P^T dO, dK = dS^T Q for the KB keys of this block ===========
-    for (int task = warp; task < (KB / 16) * 2; task += BWD_WARPS) {
-      const int ks = task >> 1, kind = task & 1;          // kind 0: dV (P, dO); 1: dK (dS, Q)
+    // When the caller passes ONE buffer for dk and dv (lite blocks: K = V = the source stream) the
+    // two are summed here: a task then owns 16 keys and runs both products into one accumulator.
+    const bool fuse_kv = (P.dk == P.dv);
+    const int n_tasks = fuse_kv ? (KB / 16) : (KB / 16) * 2;
+    for (int task = warp; task < n_tasks; task += BWD_WARPS) {
+      const int ks = fuse_kv ? task : (task >> 1);
       if (kb + 16 * ks >= Lk) continue;
-      const uint32_t sA = kind ? sdS : sP, sB = kind ? sQ : sdO;
       float acc[HD / 8][4];
 #pragma unroll
       for (int n = 0; n < HD / 8; ++n)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[n][e] = 0.f;
-      for (int kt = 0; kt < n_rt; ++kt) {
-        const int mi = lane >> 3, r = lane & 7;
-        uint32_t af[4];
-        ldsm4t(sA + swp<KB>(kt * 16 + r + 8 * (mi >> 1), 2 * ks + (mi & 1)), af);
+      // pass 0: dK = dS^T Q (scaled by 1/sqrt(hd)); pass 1: dV = P^T dO
+      const int p_beg = fuse_kv ? 0 : ((task & 1) ? 0 : 1), p_end = fuse_kv ? 2 : p_beg + 1;
+      for (int pass = p_beg; pass < p_end; ++pass) {
+        const uint32_t sA = pass == 0 ? sdS : sP, sB = pass == 0 ? sQ : sdO;
+        for (int kt = 0; kt < n_rt; ++kt) {
+          const int mi = lane >> 3, r = lane & 7;
+          uint32_t af[4];
+          ldsm4t(sA + swp<KB>(kt * 16 + r + 8 * (mi >> 1), 2 * ks + (mi & 1)), af);
 #pragma unroll
-        for (int c2 = 0; c2 < HD / 8; c2 += 2) {
-          uint32_t bf[4];
-          ldsm4t(sB + sw<HD>(kt * 16 + r + 8 * (mi & 1), c2 + (mi >> 1)), bf);
-          mma16816(acc[c2], af, bf[0], bf[1]);
-          mma16816(acc[c2 + 1], af, bf[2], bf[3]);
+          for (int c2 = 0; c2 < HD / 8; c2 += 2) {
+            uint32_t bf[4];
+            ldsm4t(sB + sw<HD>(kt * 16 + r + 8 * (mi & 1), c2 + (mi >> 1)), bf);
+            mma16816(acc[c2], af, bf[0], bf[1]);
+            mma16816(acc[c2 + 1], af, bf[2], bf[3]);
+          }
+        }
+        if (pass == 0) {
+#pragma unroll
+          for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[n][e] *= inv_sqrt;
         }
       }
-      bf16* out = kind ? P.dk : P.dv;
-      const int ld = kind ? P.lddk : P.lddv;
-      const float scl = kind ? inv_sqrt : 1.f;
+      const bool is_dk = fuse_kv || (task & 1);
+      bf16* out = is_dk ? P.dk : P.dv;
+      const int ld = is_dk ? P.lddk : P.lddv;
       const int keyA = kb + 16 * ks + g, keyB = keyA + 8;
 #pragma unroll
       for (int n = 0; n < HD / 8; ++n) {
         if (keyA < Lk)
           *reinterpret_cast<uint32_t*>(out + ((size_t)b * Lk + keyA) * ld + h * HD + 8 * n + 2 * t) =
-              pack2(acc[n][0] * scl, acc[n][1] * scl);
+              pack2(acc[n][0], acc[n][1]);
         if (keyB < Lk)
           *reinterpret_cast<uint32_t*>(out + ((size_t)b * Lk + keyB) * ld + h * HD + 8 * n + 2 * t) =
-              pack2(acc[n][2] * scl, acc[n][3] * scl);
+              pack2(acc[n][2], acc[n][3]);
       }
     }
     __syncthreads();

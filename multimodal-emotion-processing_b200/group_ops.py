@@ -1,0 +1,572 @@
+"""Grouped fusion-trunk layers: layer i of ALL chains as one autograd node and one launch per kernel.
+
+The nine chains of a fusion trunk (others/realformer.py:232-257, cmu-mosei/run.py:278-313,
+Ren-MME/run.py:230-265, robot_demo.py:399-434) are mutually independent (they share only their
+read-only inputs l, v, a), and so are the two towers of ``Concat_Trans`` / ``Base_model`` and the
+members of an inference ensemble.  The reference (and the per-block ops of ``ops.py``) walk them one
+after the other: 9 x n_layers blocks x ~18 launches of microsecond kernels per trunk.  Here layer i
+of every chain is ONE custom op whose forward / backward issue one GROUPED launch per kernel kind
+(weight casts, Q|KV projections, attention, output projection, LayerNorm, FFN, weight gradients ...)
+with the per-problem pointers in a table - ~8 launches per layer forward and ~10 backward,
+independent of the number of chains.
+
+Problem g of a group: q-stream ``qs[g]`` (B, Lq_g, d), source ``kvs[g]`` (B, Lk_g, d) (K = V, like
+every caller in the reference), mask ``masks[g]`` (B, Lk_g), previous scores ``s_prevs[g]`` or none,
+and the block's parameters.  Lengths and batch sizes may differ between problems; d, n_heads and the
+block type are shared.  Score tensors are allocated with a row stride padded to 8 elements
+(``ops.score_stride``) when the mma.sync attention kernels take the group.
+
+float32 (parity) mode runs the same code with the per-problem launchers (no grouped fp32 GEMM /
+attention kernels exist; that mode is not the performance path).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _lib, ops
+from .ops import BF, F32, LN_EPS, _act_dtype, _arr, _call, _p, _stream, _weight
+
+N_FULL = 15      # wq wk wv wo  n1w n1b n2w n2b  f1w f1b f2w f2b  a b c
+N_LITE = 5       # wo(proj) wm(minus, (d,2d)) nw nb c
+
+
+def _e(dev) -> Tensor:
+    return torch.empty(0, device=dev)
+
+
+def _opt(t: Tensor) -> Optional[Tensor]:
+    return t if t.numel() else None
+
+
+# ------------------------------------------------------------------------------------------------
+# grouped LayerNorm / column sums (one launch per group; per-problem launches when the vector
+# kernels do not take a shape)
+# ------------------------------------------------------------------------------------------------
+def _vpa(ts):
+    return _arr(C.c_void_p, [_p(t) for t in ts])
+
+
+def ln_fwd_group(bf16: bool, res, xs, gates, gammas, betas, relu=False):
+    """y_g = act(LN(res_g + gate_g * x_g)); returns ([y], [stat (2, M)])."""
+    ys = [torch.empty_like(x) for x in xs]
+    stats = [torch.empty(2, x.numel() // x.shape[-1], dtype=F32, device=x.device) for x in xs]
+    d = xs[0].shape[-1]
+    ok = False
+    if 1 < len(xs) <= 40 and all(x.is_contiguous() for x in xs) and \
+            all(r is None or r.is_contiguous() for r in res):
+        ok = ops._try_call(
+            f"mmemo_add_ln_fwd_grouped_{'bf16' if bf16 else 'f32'}",
+            len(xs), _vpa(res), _vpa(xs), _vpa(gates), _vpa(gammas), _vpa(betas), _vpa(ys),
+            _vpa([s[0] for s in stats]), _vpa([s[1] for s in stats]),
+            _arr(C.c_int64, [x.numel() // d for x in xs]), d, LN_EPS, int(relu), _stream())
+    if not ok:
+        for i, x in enumerate(xs):
+            ys[i], stats[i] = ops._add_ln_fwd(bf16, res[i], x, gates[i], gammas[i], betas[i], relu)
+    return ys, stats
+
+
+def ln_bwd_group(bf16: bool, dys, res, xs, gates, gammas, stats, want_dres: bool, dpars,
+                 dxsums=None):
+    """Backward of ln_fwd_group (no ReLU).  dpars[g] = zero-initialised float32 [1 + 2d] slot
+    (dgate | dgamma | dbeta); dxsums[g] (optional, zero-initialised [d]) receives colsum(dx).
+    Returns ([dres] or Nones, [dx])."""
+    d = xs[0].shape[-1]
+    dxs = [torch.empty_like(x) for x in xs]
+    dres = [torch.empty_like(x) if want_dres else None for x in xs]
+    ok = False
+    if 1 < len(xs) <= 40 and all(t.is_contiguous() for t in list(xs) + list(dys)) and \
+            all(r is None or r.is_contiguous() for r in res):
+        ok = ops._try_call(
+            f"mmemo_add_ln_bwd_grouped_{'bf16' if bf16 else 'f32'}",
+            len(xs), _vpa(dys), _vpa(res), _vpa(xs), _vpa(gates), _vpa(gammas),
+            _vpa([s[0] for s in stats]), _vpa([s[1] for s in stats]), _vpa(dres), _vpa(dxs),
+            _vpa([dp if g is not None else None for dp, g in zip(dpars, gates)]),
+            _vpa([dp[1:] for dp in dpars]), _vpa([dp[1 + d:] for dp in dpars]),
+            _vpa(dxsums if dxsums is not None else [None] * len(xs)),
+            _arr(C.c_int64, [x.numel() // d for x in xs]), d, _stream())
+    if not ok:
+        for i, x in enumerate(xs):
+            dres[i], dxs[i], _ = ops._add_ln_bwd(
+                bf16, dys[i], res[i], x, gates[i], gammas[i], None, stats[i], False, want_dres,
+                dpar=dpars[i], dxsum=None if dxsums is None else dxsums[i])
+    return dres, dxs
+
+
+def colsum_group(bf16: bool, xs, outs):
+    """outs[g] (zero-initialised float32 [N]) += column sums of xs[g] (M_g, N)."""
+    N = xs[0].shape[-1]
+    if bf16 and 1 < len(xs) <= 40 and N % 8 == 0 and all(x.is_contiguous() for x in xs):
+        if ops._try_call("mmemo_colsum_grouped_bf16", len(xs), _vpa(xs), _vpa(outs),
+                         _arr(C.c_int64, [x.numel() // N for x in xs]), N, _stream()):
+            return
+    for x, o in zip(xs, outs):
+        ops._rowsum(bf16, x.reshape(-1, N), o)
+
+
+# ------------------------------------------------------------------------------------------------
+# grouped attention core
+# ------------------------------------------------------------------------------------------------
+def _mma_group_ok(bf16: bool, qs, kvs, H: int, same_kv: bool) -> bool:
+    """True when every problem of the group runs on the mma.sync attention kernels (forward and
+    backward); the scores of such a group use the padded row stride."""
+    if not bf16:
+        return False
+    lib = _lib.load()
+    d = qs[0].shape[-1]
+    hd = d // H
+    for q, kv in zip(qs, kvs):
+        Lq, Lk = q.shape[1], kv.shape[1]
+        if lib.mmemo_resattn_uses_tensor_cores(Lq, Lk, hd, d):
+            return False        # hd = 64, L = 128: the tcgen05 kernels are faster
+        if not (lib.mmemo_resattn_uses_mma(Lq, Lk, hd, d, int(same_kv), 0) and
+                lib.mmemo_resattn_uses_mma(Lq, Lk, hd, d, int(same_kv), 1)):
+            return False
+    return True
+
+
+def attn_fwd_group(bf16, qs, ks, vs, masks, s_prevs, cs, H, want_s, grouped):
+    """Returns ([o], [s or None], [stat]).  ``grouped``: one mma.sync launch, padded score stride."""
+    dt = _act_dtype(bf16)
+    os_, ss, stats, probs = [], [], [], []
+    if not grouped:
+        for g, q in enumerate(qs):
+            o, s, st = ops._attn_fwd(bf16, q, ks[g], vs[g], masks[g], s_prevs[g], cs[g], H, want_s)
+            os_.append(o), ss.append(s), stats.append(st)
+        return os_, ss, stats
+    for g, q in enumerate(qs):
+        B, Lq, d = q.shape
+        Lk = ks[g].shape[1]
+        lds = ops.score_stride(Lk)
+        o = torch.empty(B, Lq, d, dtype=dt, device=q.device)
+        s = torch.empty(B, H, Lq, lds, dtype=dt, device=q.device) if want_s else None
+        st = torch.empty(B, H, Lq, 2, dtype=F32, device=q.device)
+        sp = s_prevs[g]
+        assert sp is None or sp.shape[-1] == lds, "previous scores must use the padded stride"
+        probs.append(ops._attn_problem(q, ks[g], vs[g], masks[g], sp, cs[g], s, o, st, H, lds))
+        os_.append(o), ss.append(s), stats.append(st)
+    if not ops._attn_group_call("mmemo_resattn_fwd_grouped_bf16", probs):
+        raise RuntimeError("grouped attention forward rejected a shape it reported as supported")
+    return os_, ss, stats
+
+
+def attn_bwd_group(bf16, dos, qs, ks, vs, masks, ss, s_prevs, cs, ds_nexts, os_, stats, H, dqs, dks,
+                   dvs, want_dsprev, dcs, grouped):
+    """Fills dqs / dks / dvs; returns [ds_prev or None].  dcs[g]: zero-initialised float32 [1]."""
+    dt = _act_dtype(bf16)
+    out = []
+    if not grouped:
+        for g, q in enumerate(qs):
+            dsp, _ = ops._attn_bwd(bf16, dos[g], q, ks[g], vs[g], masks[g], ss[g], s_prevs[g], cs[g],
+                                   ds_nexts[g], os_[g], stats[g], H, dqs[g], dks[g], dvs[g],
+                                   want_dsprev, dc_out=dcs[g])
+            out.append(dsp)
+        return out
+    probs = []
+    for g, q in enumerate(qs):
+        B, Lq, d = q.shape
+        Lk = ks[g].shape[1]
+        lds = ops.score_stride(Lk)
+        sp = s_prevs[g]
+        dsp = None
+        if sp is not None and want_dsprev:
+            dsp = torch.empty(B, H, Lq, lds, dtype=dt, device=q.device)
+        probs.append(ops._attn_problem(q, ks[g], vs[g], masks[g], sp, cs[g], None, os_[g], stats[g],
+                                       H, lds, d_o=dos[g], s=ss[g], ds_next=ds_nexts[g], dq=dqs[g],
+                                       dk=dks[g], dv=dvs[g], ds_prev=dsp,
+                                       dc=dcs[g] if sp is not None else None))
+        out.append(dsp)
+    if not ops._attn_group_call("mmemo_resattn_bwd_grouped_bf16", probs):
+        raise RuntimeError("grouped attention backward rejected a shape it reported as supported")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::trunk_full — layer i of G chains of FULL RealFormer blocks
+#   (others/realformer.py:182-209 == robot_demo.py:347-374), one node
+# outputs per problem (12): h2 s qp kvp o stat x h1 st1 f1 f2 st2
+# ------------------------------------------------------------------------------------------------
+FULL_OUT = 12
+
+
+@torch.library.custom_op("mmemo::trunk_full", mutates_args=())
+def trunk_full_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[Tensor],
+                  s_prevs: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
+                  emit_s: bool) -> List[Tensor]:
+    ops._need_cuda(*qs, *kvs)
+    G = len(qs)
+    dt, dev = _act_dtype(bf16), qs[0].device
+    d = qs[0].shape[-1]
+    P = [params[N_FULL * g:N_FULL * (g + 1)] for g in range(G)]
+    qs = [q.contiguous() for q in qs]
+    kvs = [qs[g] if kvs[g].data_ptr() == qs[g].data_ptr() and kvs[g].shape == qs[g].shape
+           else kvs[g].contiguous() for g in range(G)]
+    masks_ = [_opt(m) for m in masks]
+    sp = [s_prevs[g] if len(s_prevs) else None for g in range(G)]
+    if bf16:   # every bf16 weight shadow of the layer in one cast launch
+        ops.shadow_bf16_block([grp for p in P for grp in
+                               ([p[0]], [p[1], p[2]], [p[3]], [p[8]], [p[10]])])
+    dff = P[0][8].shape[0]
+    # Q projection and fused [K|V] projection (N = 2d) of every chain: one grouped GEMM
+    qps = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    kvps = [torch.empty(*kv.shape[:2], 2 * d, dtype=dt, device=dev) for kv in kvs]
+    items = []
+    for g in range(G):
+        items.append((qs[g], _weight(bf16, P[g][0]), None, qps[g].view(-1, d), False))
+        items.append((kvs[g], _weight(bf16, P[g][1], P[g][2]), None, kvps[g].view(-1, 2 * d), False))
+    ops._linear_fwd_group(bf16, items)
+    ks = [t[..., :d] for t in kvps]
+    vs = [t[..., d:] for t in kvps]
+    grouped = _mma_group_ok(bf16, qs, kvs, n_heads, False)
+    os_, ss, stats = attn_fwd_group(bf16, qps, ks, vs, masks_, sp, [p[14] for p in P], n_heads,
+                                    emit_s, grouped)
+    # output projection, gated residual + LN1
+    xs = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    ops._linear_fwd_group(bf16, [(os_[g], _weight(bf16, P[g][3]), None, xs[g].view(-1, d), False)
+                                 for g in range(G)])
+    h1s, st1s = ln_fwd_group(bf16, qs, xs, [p[12] for p in P], [p[4] for p in P],
+                             [p[5] for p in P])
+    # FFN (bias + ReLU fused in the first GEMM's epilogue), gated residual + LN2
+    f1s = [torch.empty(*q.shape[:2], dff, dtype=dt, device=dev) for q in qs]
+    f2s = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    ops._linear_fwd_group(bf16, [(h1s[g], _weight(bf16, P[g][8]), P[g][9], f1s[g].view(-1, dff), True)
+                                 for g in range(G)])
+    ops._linear_fwd_group(bf16, [(f1s[g], _weight(bf16, P[g][10]), P[g][11], f2s[g].view(-1, d), False)
+                                 for g in range(G)])
+    h2s, st2s = ln_fwd_group(bf16, h1s, f2s, [p[13] for p in P], [p[6] for p in P],
+                             [p[7] for p in P])
+    out = []
+    for g in range(G):
+        out += [h2s[g], ss[g] if ss[g] is not None else _e(dev), qps[g], kvps[g], os_[g], stats[g],
+                xs[g], h1s[g], st1s[g], f1s[g], f2s[g], st2s[g]]
+    return out
+
+
+def _full_zlayout(d: int, dff: int):
+    """Per-problem zero buffer: [dp2 (1+2d) | dp1 (1+2d) | db_f2 (d) | db_f1 (dff) | dc (1) | pad]
+    then dWq (d,d) dWkv (2d,d) dWo (d,d) dWf1 (dff,d) dWf2 (d,dff)."""
+    n_small = (2 * (1 + 2 * d) + d + dff + 1 + 63) // 64 * 64
+    sizes = [d * d, 2 * d * d, d * d, dff * d, d * dff]
+    return n_small, sizes, n_small + sum(sizes)
+
+
+def _full_zviews(z: Tensor, d: int, dff: int):
+    n_small, sizes, _ = _full_zlayout(d, dff)
+    dp2, dp1 = z[:1 + 2 * d], z[1 + 2 * d:2 * (1 + 2 * d)]
+    o = 2 * (1 + 2 * d)
+    db_f2, db_f1, dc = z[o:o + d], z[o + d:o + d + dff], z[o + d + dff:o + d + dff + 1]
+    ws, o = [], n_small
+    for n, sh in zip(sizes, [(d, d), (2 * d, d), (d, d), (dff, d), (d, dff)]):
+        ws.append(z[o:o + n].view(sh))
+        o += n
+    return dp2, dp1, db_f2, db_f1, dc, ws
+
+
+@torch.library.custom_op("mmemo::trunk_full_bwd", mutates_args=())
+def trunk_full_bwd_op(dh2s: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Sequence[Tensor],
+                      kvs: Sequence[Tensor], masks: Sequence[Tensor], s_prevs: Sequence[Tensor],
+                      saved: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
+                      need_dsprev: bool) -> List[Tensor]:
+    """Returns per problem [dq, dkv, ds_prev] (empty placeholders where undefined) followed by ONE
+    float32 buffer holding every parameter gradient of the group (layout: _full_zlayout)."""
+    G = len(qs)
+    dt, dev = _act_dtype(bf16), qs[0].device
+    d = qs[0].shape[-1]
+    P = [params[N_FULL * g:N_FULL * (g + 1)] for g in range(G)]
+    S = [saved[(FULL_OUT - 1) * g:(FULL_OUT - 1) * (g + 1)] for g in range(G)]
+    # saved per problem: s qp kvp o stat x h1 st1 f1 f2 st2
+    ss = [_opt(s[0]) for s in S]
+    qps, kvps, os_, stats = [s[1] for s in S], [s[2] for s in S], [s[3] for s in S], [s[4] for s in S]
+    xs, h1s, st1s = [s[5] for s in S], [s[6] for s in S], [s[7] for s in S]
+    f1s, f2s, st2s = [s[8] for s in S], [s[9] for s in S], [s[10] for s in S]
+    dff = P[0][8].shape[0]
+    qs = [q.contiguous() for q in qs]
+    same = [kvs[g].data_ptr() == qs[g].data_ptr() and kvs[g].shape == qs[g].shape for g in range(G)]
+    kvs = [qs[g] if same[g] else kvs[g].contiguous() for g in range(G)]
+    masks_ = [_opt(m) for m in masks]
+    sp = [s_prevs[g] if len(s_prevs) else None for g in range(G)]
+    dsn = [_opt(t) for t in ds_nexts]
+    dh2s = [t.contiguous() for t in dh2s]
+    _, _, zlen = _full_zlayout(d, dff)
+    zall = torch.zeros(G * zlen, dtype=F32, device=dev)      # ONE fill for every "+=" output
+    Z = [_full_zviews(zall[g * zlen:(g + 1) * zlen], d, dff) for g in range(G)]
+    # LN2: h2 = LN(h1 + b*f2); colsum(df2) = the FFN-2 bias gradient comes out of the same pass
+    dh1s, df2s = ln_bwd_group(bf16, dh2s, h1s, f2s, [p[13] for p in P], [p[6] for p in P], st2s,
+                              True, [z[0] for z in Z], [z[2] for z in Z])
+    # FFN backward: df1 = (df2 W2) * (f1 > 0) fused in the epilogue; dh1 += df1 W1
+    df1s = [torch.empty(f.shape, dtype=dt, device=dev) for f in f1s]
+    ops._linear_bwd_x_group(bf16, [(df2s[g], _weight(bf16, P[g][10]), df1s[g].view(-1, dff), False,
+                                    f1s[g].view(-1, dff)) for g in range(G)])
+    ops._linear_bwd_x_group(bf16, [(df1s[g], _weight(bf16, P[g][8]), dh1s[g].view(-1, d), True)
+                                   for g in range(G)])
+    colsum_group(bf16, [t.view(-1, dff) for t in df1s], [z[3] for z in Z])
+    # LN1: h1 = LN(q + a*x)
+    dqs, dxs = ln_bwd_group(bf16, dh1s, qs, xs, [p[12] for p in P], [p[4] for p in P], st1s, True,
+                            [z[1] for z in Z])
+    # output projection
+    dos = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    ops._linear_bwd_x_group(bf16, [(dxs[g], _weight(bf16, P[g][3]), dos[g].view(-1, d), False)
+                                   for g in range(G)])
+    # attention core
+    dqps = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    dkvps = [torch.empty(t.shape, dtype=dt, device=dev) for t in kvps]
+    grouped = _mma_group_ok(bf16, qs, kvs, n_heads, False)
+    dsps = attn_bwd_group(bf16, dos, qps, [t[..., :d] for t in kvps], [t[..., d:] for t in kvps],
+                          masks_, ss, sp, [p[14] for p in P], dsn, os_, stats, n_heads, dqps,
+                          [t[..., :d] for t in dkvps], [t[..., d:] for t in dkvps], need_dsprev,
+                          [z[4] for z in Z], grouped)
+    # projections: dq += dqp Wq ; dkv = dkvp [Wk;Wv]  (same tensor for q and kv: two ordered passes)
+    dkvs = [None if same[g] else torch.empty(kvs[g].shape, dtype=dt, device=dev) for g in range(G)]
+    first, second = [], []
+    for g in range(G):
+        first.append((dqps[g], _weight(bf16, P[g][0]), dqs[g].view(-1, d), True))
+        kvitem = (dkvps[g], _weight(bf16, P[g][1], P[g][2]),
+                  (dqs[g] if same[g] else dkvs[g]).view(-1, d), same[g])
+        (second if same[g] else first).append(kvitem)
+    ops._linear_bwd_x_group(bf16, first)
+    if second:
+        ops._linear_bwd_x_group(bf16, second)
+    # the five weight gradients of every chain: one grouped launch per 48 problems
+    items = []
+    for g in range(G):
+        w = Z[g][5]
+        items += [(df2s[g].view(-1, d), f1s[g].view(-1, dff), w[4]),
+                  (df1s[g].view(-1, dff), h1s[g].view(-1, d), w[3]),
+                  (dxs[g].view(-1, d), os_[g].view(-1, d), w[2]),
+                  (dqps[g].view(-1, d), qs[g].view(-1, d), w[0]),
+                  (dkvps[g].view(-1, 2 * d), kvs[g].view(-1, d), w[1])]
+    ops._linear_bwd_w_group(bf16, items, zeroed=True)
+    out = []
+    for g in range(G):
+        out += [dqs[g], dkvs[g] if dkvs[g] is not None else _e(dev),
+                dsps[g] if dsps[g] is not None else _e(dev)]
+    return out + [zall]
+
+
+def _trunk_full_setup(ctx, inputs, output):
+    qs, kvs, masks, s_prevs, params, H, bf16, emit_s = inputs
+    G = len(qs)
+    ctx.G, ctx.cfg, ctx.has_prev = G, (H, bf16), len(s_prevs) > 0
+    ctx.n_params = len(params)
+    saved = []
+    for g in range(G):
+        saved += list(output[FULL_OUT * g + 1:FULL_OUT * (g + 1)])
+    ctx.save_for_backward(*qs, *kvs, *masks, *s_prevs, *saved, *params)
+    ctx.set_materialize_grads(False)
+
+
+def _trunk_full_backward(ctx, grads):
+    G = ctx.G
+    H, bf16 = ctx.cfg
+    t = list(ctx.saved_tensors)
+    qs, kvs, masks = t[:G], t[G:2 * G], t[2 * G:3 * G]
+    o = 3 * G
+    s_prevs = t[o:o + G] if ctx.has_prev else []
+    o += G if ctx.has_prev else 0
+    ns = (FULL_OUT - 1) * G
+    saved, params = t[o:o + ns], t[o + ns:]
+    dev = qs[0].device
+    dh2s, dsn = [], []
+    for g in range(G):
+        gh, gs = grads[FULL_OUT * g], grads[FULL_OUT * g + 1]
+        dh2s.append(gh if gh is not None else torch.zeros_like(qs[g]))
+        dsn.append(gs if gs is not None else _e(dev))
+    need_dsprev = ctx.has_prev and any(ctx.needs_input_grad[3])
+    res = trunk_full_bwd_op(dh2s, dsn, qs, kvs, masks, s_prevs, saved, params, H, bf16, need_dsprev)
+    zall = res[-1]
+    d = qs[0].shape[-1]
+    dff = params[8].shape[0]
+    _, _, zlen = _full_zlayout(d, dff)
+    dqs, dkvs, dsps, pgrads = [], [], [], []
+    for g in range(G):
+        dq, dkv, dsp = res[3 * g:3 * g + 3]
+        dqs.append(dq)
+        dkvs.append(dkv if dkv.numel() else None)
+        dsps.append(dsp if dsp.numel() else None)
+        dp2, dp1, db_f2, db_f1, dc, ws = _full_zviews(zall[g * zlen:(g + 1) * zlen], d, dff)
+        pgrads += [ws[0], ws[1][:d], ws[1][d:], ws[2], dp1[1:1 + d], dp1[1 + d:], dp2[1:1 + d],
+                   dp2[1 + d:], ws[3], db_f1, ws[4], db_f2, dp1[0:1], dp2[0:1],
+                   dc if ctx.has_prev else None]
+    n_prev = G if ctx.has_prev else 0
+    return (dqs, dkvs, [None] * G, dsps if need_dsprev else [None] * n_prev, pgrads, None, None,
+            None)
+
+
+trunk_full_op.register_autograd(_trunk_full_backward, setup_context=_trunk_full_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::trunk_lite — layer i of G chains of LITE blocks (cmu-mosei/run.py:236-262,
+#   Ren-MME/run.py:188-214): attention on the raw streams, proj, LN(minus([q | x]))
+# outputs per problem (7): out s o stat x y st
+# ------------------------------------------------------------------------------------------------
+LITE_OUT = 7
+
+
+@torch.library.custom_op("mmemo::trunk_lite", mutates_args=())
+def trunk_lite_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[Tensor],
+                  s_prevs: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
+                  emit_s: bool) -> List[Tensor]:
+    ops._need_cuda(*qs, *kvs)
+    G = len(qs)
+    dt, dev = _act_dtype(bf16), qs[0].device
+    d = qs[0].shape[-1]
+    P = [params[N_LITE * g:N_LITE * (g + 1)] for g in range(G)]
+    qs = [q.contiguous() for q in qs]
+    kvs = [qs[g] if kvs[g].data_ptr() == qs[g].data_ptr() and kvs[g].shape == qs[g].shape
+           else kvs[g].contiguous() for g in range(G)]
+    masks_ = [_opt(m) for m in masks]
+    sp = [s_prevs[g] if len(s_prevs) else None for g in range(G)]
+    if bf16:
+        ops.shadow_bf16_block([[w] for p in P for w in (p[0], p[1])])
+    grouped = _mma_group_ok(bf16, qs, kvs, n_heads, True)
+    os_, ss, stats = attn_fwd_group(bf16, qs, kvs, kvs, masks_, sp, [p[4] for p in P], n_heads,
+                                    emit_s, grouped)
+    xs = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    ops._linear_fwd_group(bf16, [(os_[g], _weight(bf16, P[g][0]), None, xs[g].view(-1, d), False)
+                                 for g in range(G)])
+    # y = [q | x] Wm^T as two accumulating grouped GEMMs over the halves of Wm (no concat copy)
+    ys = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    wms = [_weight(bf16, P[g][1]) for g in range(G)]
+    ops._linear_fwd_group(bf16, [(qs[g], wms[g][:, :d], None, ys[g].view(-1, d), False, False)
+                                 for g in range(G)])
+    ops._linear_fwd_group(bf16, [(xs[g], wms[g][:, d:], None, ys[g].view(-1, d), False, True)
+                                 for g in range(G)])
+    outs, sts = ln_fwd_group(bf16, [None] * G, ys, [None] * G, [p[2] for p in P], [p[3] for p in P])
+    out = []
+    for g in range(G):
+        out += [outs[g], ss[g] if ss[g] is not None else _e(dev), os_[g], stats[g], xs[g], ys[g],
+                sts[g]]
+    return out
+
+
+def _lite_zlayout(d: int):
+    """[dpn (1+2d) | dc (1) | pad] then dWo (d,d), dWm (d,2d)."""
+    n_small = (1 + 2 * d + 1 + 63) // 64 * 64
+    return n_small, n_small + d * d + 2 * d * d
+
+
+def _lite_zviews(z: Tensor, d: int):
+    n_small, _ = _lite_zlayout(d)
+    dpn, dc = z[:1 + 2 * d], z[1 + 2 * d:2 + 2 * d]
+    dwo = z[n_small:n_small + d * d].view(d, d)
+    dwm = z[n_small + d * d:n_small + 3 * d * d].view(d, 2 * d)
+    return dpn, dc, dwo, dwm
+
+
+@torch.library.custom_op("mmemo::trunk_lite_bwd", mutates_args=())
+def trunk_lite_bwd_op(douts: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Sequence[Tensor],
+                      kvs: Sequence[Tensor], masks: Sequence[Tensor], s_prevs: Sequence[Tensor],
+                      saved: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
+                      need_dsprev: bool) -> List[Tensor]:
+    G = len(qs)
+    dt, dev = _act_dtype(bf16), qs[0].device
+    d = qs[0].shape[-1]
+    P = [params[N_LITE * g:N_LITE * (g + 1)] for g in range(G)]
+    S = [saved[(LITE_OUT - 1) * g:(LITE_OUT - 1) * (g + 1)] for g in range(G)]
+    # saved per problem: s o stat x y st
+    ss = [_opt(s[0]) for s in S]
+    os_, stats, xs, ys, sts = ([s[i] for s in S] for i in range(1, 6))
+    qs = [q.contiguous() for q in qs]
+    same = [kvs[g].data_ptr() == qs[g].data_ptr() and kvs[g].shape == qs[g].shape for g in range(G)]
+    kvs = [qs[g] if same[g] else kvs[g].contiguous() for g in range(G)]
+    masks_ = [_opt(m) for m in masks]
+    sp = [s_prevs[g] if len(s_prevs) else None for g in range(G)]
+    dsn = [_opt(t) for t in ds_nexts]
+    douts = [t.contiguous() for t in douts]
+    _, zlen = _lite_zlayout(d)
+    zall = torch.zeros(G * zlen, dtype=F32, device=dev)
+    Z = [_lite_zviews(zall[g * zlen:(g + 1) * zlen], d) for g in range(G)]
+    _, dys = ln_bwd_group(bf16, douts, [None] * G, ys, [None] * G, [p[2] for p in P], sts, False,
+                          [z[0] for z in Z])
+    wms = [_weight(bf16, P[g][1]) for g in range(G)]
+    # minus: dx = dy Wm[:, d:]; proj: do = dx Wo
+    dxs = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    ops._linear_bwd_x_group(bf16, [(dys[g], wms[g][:, d:], dxs[g].view(-1, d), False)
+                                   for g in range(G)])
+    dos = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    ops._linear_bwd_x_group(bf16, [(dxs[g], _weight(bf16, P[g][0]), dos[g].view(-1, d), False)
+                                   for g in range(G)])
+    # attention core (Q = q, K = V = kv): dk and dv both flow into kv -> the kernel sums them when
+    # it is handed the same buffer for both
+    grouped = _mma_group_ok(bf16, qs, kvs, n_heads, True)
+    dqs = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
+    dks = [torch.empty(kv.shape, dtype=dt, device=dev) for kv in kvs]
+    dvs = dks if grouped else [torch.empty(kv.shape, dtype=dt, device=dev) for kv in kvs]
+    dsps = attn_bwd_group(bf16, dos, qs, kvs, kvs, masks_, ss, sp, [p[4] for p in P], dsn, os_,
+                          stats, n_heads, dqs, dks, dvs, need_dsprev, [z[1] for z in Z], grouped)
+    if not grouped:
+        dks = [dk + dv for dk, dv in zip(dks, dvs)]
+    # minus, q half: dq += dy Wm[:, :d]  (accumulates onto the attention's dq)
+    ops._linear_bwd_x_group(bf16, [(dys[g], wms[g][:, :d], dqs[g].view(-1, d), True)
+                                   for g in range(G)])
+    dkv_out = []
+    for g in range(G):
+        if same[g]:        # q and kv are one tensor: a single gradient
+            dqs[g] = dqs[g] + dks[g]
+            dkv_out.append(_e(dev))
+        else:
+            dkv_out.append(dks[g])
+    # weight gradients: dWo = dx^T o; dWm = dy^T [q | x] as two GEMMs into the halves of dWm
+    items = []
+    for g in range(G):
+        _, _, dwo, dwm = Z[g]
+        items += [(dxs[g].view(-1, d), os_[g].view(-1, d), dwo),
+                  (dys[g].view(-1, d), qs[g].view(-1, d), dwm[:, :d]),
+                  (dys[g].view(-1, d), xs[g].view(-1, d), dwm[:, d:])]
+    ops._linear_bwd_w_group(bf16, items, zeroed=True)
+    out = []
+    for g in range(G):
+        out += [dqs[g], dkv_out[g], dsps[g] if dsps[g] is not None else _e(dev)]
+    return out + [zall]
+
+
+def _trunk_lite_setup(ctx, inputs, output):
+    qs, kvs, masks, s_prevs, params, H, bf16, emit_s = inputs
+    G = len(qs)
+    ctx.G, ctx.cfg, ctx.has_prev = G, (H, bf16), len(s_prevs) > 0
+    saved = []
+    for g in range(G):
+        saved += list(output[LITE_OUT * g + 1:LITE_OUT * (g + 1)])
+    ctx.save_for_backward(*qs, *kvs, *masks, *s_prevs, *saved, *params)
+    ctx.set_materialize_grads(False)
+
+
+def _trunk_lite_backward(ctx, grads):
+    G = ctx.G
+    H, bf16 = ctx.cfg
+    t = list(ctx.saved_tensors)
+    qs, kvs, masks = t[:G], t[G:2 * G], t[2 * G:3 * G]
+    o = 3 * G
+    s_prevs = t[o:o + G] if ctx.has_prev else []
+    o += G if ctx.has_prev else 0
+    ns = (LITE_OUT - 1) * G
+    saved, params = t[o:o + ns], t[o + ns:]
+    dev = qs[0].device
+    douts, dsn = [], []
+    for g in range(G):
+        gh, gs = grads[LITE_OUT * g], grads[LITE_OUT * g + 1]
+        douts.append(gh if gh is not None else torch.zeros_like(qs[g]))
+        dsn.append(gs if gs is not None else _e(dev))
+    need_dsprev = ctx.has_prev and any(ctx.needs_input_grad[3])
+    res = trunk_lite_bwd_op(douts, dsn, qs, kvs, masks, s_prevs, saved, params, H, bf16, need_dsprev)
+    zall = res[-1]
+    d = qs[0].shape[-1]
+    _, zlen = _lite_zlayout(d)
+    dqs, dkvs, dsps, pgrads = [], [], [], []
+    for g in range(G):
+        dq, dkv, dsp = res[3 * g:3 * g + 3]
+        dqs.append(dq)
+        dkvs.append(dkv if dkv.numel() else None)
+        dsps.append(dsp if dsp.numel() else None)
+        dpn, dc, dwo, dwm = _lite_zviews(zall[g * zlen:(g + 1) * zlen], d)
+        pgrads += [dwo, dwm, dpn[1:1 + d], dpn[1 + d:], dc if ctx.has_prev else None]
+    n_prev = G if ctx.has_prev else 0
+    return (dqs, dkvs, [None] * G, dsps if need_dsprev else [None] * n_prev, pgrads, None, None,
+            None)
+
+
+trunk_lite_op.register_autograd(_trunk_lite_backward, setup_context=_trunk_lite_setup)

@@ -85,6 +85,21 @@ def _call(name: str, *args) -> None:
             _lib.check(_lib.load().mmemo_set_sm_budget(0), "sm_budget")
 
 
+def _try_call(name: str, *args) -> bool:
+    """Like ``_call`` for the grouped entry points: False when the library answers
+    MMEMO_ERR_SHAPE (a problem of the group is outside the grouped kernel's limits; the caller then
+    issues the problems one by one), raises on any other error."""
+    global launch_count
+    if not _workspace:
+        _ensure_workspace()
+    rc = getattr(_lib.load(), name)(*args)
+    if rc == -2:
+        return False
+    _lib.check(rc, name)
+    launch_count += 1
+    return True
+
+
 def _sfx(bf16: bool) -> str:
     return "bf16" if bf16 else "f32"
 
@@ -141,8 +156,9 @@ def shadow_bf16_block(groups: Sequence[Sequence[Tensor]]) -> List[Tensor]:
     if all(k in _shadow for k in keys):
         return [_shadow[k] for k in keys]
     flat = [w for g in groups for w in g]
-    if len(flat) > 8:
-        return [shadow_bf16(*g) for g in groups]
+    if len(flat) > 64:
+        half = len(groups) // 2
+        return shadow_bf16_block(groups[:half]) + shadow_bf16_block(groups[half:])
     outs, srcs, dsts, ns = [], [], [], []
     for g, k in zip(groups, keys):
         ptrs = {e[0] for e in k}
@@ -287,59 +303,78 @@ def _arr(ctype, vals):
     return (ctype * len(vals))(*vals)
 
 
+MAX_GEMM_GROUP = 48     # problems per grouped tensor-core launch (csrc/gemm.h GEMM_TC_MAX_GROUP)
+
+
+def _chunks(items, n=MAX_GEMM_GROUP):
+    return [items[i:i + n] for i in range(0, len(items), n)]
+
+
 def _linear_fwd_group(bf16, items):
-    """items: [(x, w, bias, out2d, relu)].  One grouped tensor-core launch in bf16 mode."""
+    """items: [(x, w, bias, out2d, relu[, accumulate])].  One grouped tensor-core launch (per 48
+    problems) in bf16 mode; N, K and the weight's leading dimension come from ``w`` (a 2-D view,
+    e.g. one half of a concat weight)."""
+    items = [it if len(it) == 6 else (*it, False) for it in items]
     if not bf16 or len(items) == 1:
-        for x, w, b, out, relu in items:
-            _linear_fwd(bf16, x, w, b, None, out, relu=relu)
+        for x, w, b, out, relu, acc in items:
+            _linear_fwd(bf16, x, w, b, None, out, relu=relu, accumulate=acc, ldw=w.stride(0),
+                        N=w.shape[0], K=w.shape[1])
         return
-    xs = [_rows(it[0]) for it in items]
-    _call("mmemo_linear_fwd_grouped_bf16", len(items),
-          _arr(C.c_void_p, [x.data_ptr() for x, _, _ in xs]), _arr(C.c_int64, [ld for _, _, ld in xs]),
-          _arr(C.c_void_p, [it[1].data_ptr() for it in items]),
-          _arr(C.c_int64, [it[1].stride(0) for it in items]),
-          _arr(C.c_void_p, [_p(it[2]) for it in items]),
-          _arr(C.c_void_p, [it[3].data_ptr() for it in items]),
-          _arr(C.c_int64, [it[3].stride(-2) for it in items]),
-          _arr(C.c_int64, [M for _, M, _ in xs]), _arr(C.c_int64, [it[1].shape[0] for it in items]),
-          _arr(C.c_int64, [x.shape[-1] for x, _, _ in xs]),
-          _arr(C.c_int, [int(it[4]) for it in items]), _stream())
+    for part in _chunks(items):
+        xs = [_rows(it[0]) for it in part]
+        _call("mmemo_linear_fwd_grouped_bf16", len(part),
+              _arr(C.c_void_p, [x.data_ptr() for x, _, _ in xs]), _arr(C.c_int64, [ld for _, _, ld in xs]),
+              _arr(C.c_void_p, [it[1].data_ptr() for it in part]),
+              _arr(C.c_int64, [it[1].stride(0) for it in part]),
+              _arr(C.c_void_p, [_p(it[2]) for it in part]),
+              _arr(C.c_void_p, [it[3].data_ptr() for it in part]),
+              _arr(C.c_int64, [it[3].stride(-2) for it in part]),
+              _arr(C.c_int64, [M for _, M, _ in xs]), _arr(C.c_int64, [it[1].shape[0] for it in part]),
+              _arr(C.c_int64, [it[1].shape[1] for it in part]),
+              _arr(C.c_int, [int(it[4]) for it in part]), _arr(C.c_int, [int(it[5]) for it in part]),
+              _stream())
 
 
 def _linear_bwd_x_group(bf16, items):
-    """items: [(dy, w, dx2d, accumulate)] — outputs must not alias each other."""
+    """items: [(dy, w, dx2d, accumulate[, relu_src2d])] — outputs must not alias each other."""
+    items = [it if len(it) == 5 else (*it, None) for it in items]
     if not bf16 or len(items) == 1:
-        for dy, w, dx, acc in items:
-            _linear_bwd_x(bf16, dy, w, dx, accumulate=acc)
+        for dy, w, dx, acc, rs in items:
+            _linear_bwd_x(bf16, dy, w, dx, relu_src=rs, accumulate=acc, ldw=w.stride(0),
+                          N=w.shape[0], K=w.shape[1])
         return
-    dys = [_rows(it[0]) for it in items]
-    _call("mmemo_linear_bwd_x_grouped_bf16", len(items),
-          _arr(C.c_void_p, [d.data_ptr() for d, _, _ in dys]), _arr(C.c_int64, [ld for _, _, ld in dys]),
-          _arr(C.c_void_p, [it[1].data_ptr() for it in items]),
-          _arr(C.c_int64, [it[1].stride(0) for it in items]),
-          _arr(C.c_void_p, [it[2].data_ptr() for it in items]),
-          _arr(C.c_int64, [it[2].stride(-2) for it in items]),
-          _arr(C.c_int64, [M for _, M, _ in dys]), _arr(C.c_int64, [it[1].shape[0] for it in items]),
-          _arr(C.c_int64, [it[1].shape[1] for it in items]),
-          _arr(C.c_int, [int(it[3]) for it in items]), _stream())
+    for part in _chunks(items):
+        dys = [_rows(it[0]) for it in part]
+        _call("mmemo_linear_bwd_x_grouped_bf16", len(part),
+              _arr(C.c_void_p, [d.data_ptr() for d, _, _ in dys]), _arr(C.c_int64, [ld for _, _, ld in dys]),
+              _arr(C.c_void_p, [it[1].data_ptr() for it in part]),
+              _arr(C.c_int64, [it[1].stride(0) for it in part]),
+              _arr(C.c_void_p, [it[2].data_ptr() for it in part]),
+              _arr(C.c_int64, [it[2].stride(-2) for it in part]),
+              _arr(C.c_void_p, [_p(it[4]) for it in part]),
+              _arr(C.c_int64, [0 if it[4] is None else it[4].stride(-2) for it in part]),
+              _arr(C.c_int64, [M for _, M, _ in dys]), _arr(C.c_int64, [it[1].shape[0] for it in part]),
+              _arr(C.c_int64, [it[1].shape[1] for it in part]),
+              _arr(C.c_int, [int(it[3]) for it in part]), _stream())
 
 
 def _linear_bwd_w_group(bf16, items, zeroed=False):
-    """items: [(dy, x, dw)] -> dw = dy^T x (float32), all in one grouped launch in bf16 mode.
-    ``zeroed``: every dw is already all zero (saves the split-K path its own zero fills)."""
+    """items: [(dy, x, dw)] -> dw = dy^T x (float32), all in one grouped launch (per 48 problems) in
+    bf16 mode.  ``zeroed``: every dw is already all zero (saves the split-K path its own fills)."""
     if not bf16 or len(items) == 1:
         for dy, x, dw in items:
             _linear_bwd_w(bf16, dy, x, dw)
         return
-    dys = [_rows(it[0]) for it in items]
-    xs = [_rows(it[1]) for it in items]
-    _call("mmemo_linear_bwd_w_grouped_bf16", len(items),
-          _arr(C.c_void_p, [d.data_ptr() for d, _, _ in dys]), _arr(C.c_int64, [ld for _, _, ld in dys]),
-          _arr(C.c_void_p, [x.data_ptr() for x, _, _ in xs]), _arr(C.c_int64, [ld for _, _, ld in xs]),
-          _arr(C.c_void_p, [it[2].data_ptr() for it in items]),
-          _arr(C.c_int64, [it[2].stride(0) for it in items]),
-          _arr(C.c_int64, [M for _, M, _ in dys]), _arr(C.c_int64, [d.shape[-1] for d, _, _ in dys]),
-          _arr(C.c_int64, [x.shape[-1] for x, _, _ in xs]), 2 if zeroed else 0, _stream())
+    for part in _chunks(items):
+        dys = [_rows(it[0]) for it in part]
+        xs = [_rows(it[1]) for it in part]
+        _call("mmemo_linear_bwd_w_grouped_bf16", len(part),
+              _arr(C.c_void_p, [d.data_ptr() for d, _, _ in dys]), _arr(C.c_int64, [ld for _, _, ld in dys]),
+              _arr(C.c_void_p, [x.data_ptr() for x, _, _ in xs]), _arr(C.c_int64, [ld for _, _, ld in xs]),
+              _arr(C.c_void_p, [it[2].data_ptr() for it in part]),
+              _arr(C.c_int64, [it[2].stride(0) for it in part]),
+              _arr(C.c_int64, [M for _, M, _ in dys]), _arr(C.c_int64, [d.shape[-1] for d, _, _ in dys]),
+              _arr(C.c_int64, [x.shape[-1] for x, _, _ in xs]), 2 if zeroed else 0, _stream())
 
 
 def _add_ln_fwd(bf16, res, x, gate, gamma, beta, relu=False):
@@ -475,14 +510,8 @@ def _attn_problem(q, k, v, mask, s_prev, c, s_out, o, stat, H, lds, d_o=None, s=
 
 def _attn_group_call(name: str, probs) -> bool:
     """One grouped launch; False when the mma kernels do not take one of the shapes."""
-    global launch_count
     arr = (_lib.AttnProblem * len(probs))(*probs)
-    rc = getattr(_lib.load(), name)(len(probs), C.cast(arr, C.c_void_p), _stream())
-    if rc == -2:
-        return False
-    _lib.check(rc, name)
-    launch_count += 1
-    return True
+    return _try_call(name, len(probs), C.cast(arr, C.c_void_p), _stream())
 
 
 # ------------------------------------------------------------------------------------------------

@@ -28,6 +28,9 @@ class Unify_Dimension_Conv1d(nn.Module):
 
     def forward(self, l, v, a, pos=(None, None, None)):
         bf = is_bf16()
+        if bf:      # the bf16 shadows of all projection weights in one cast launch
+            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
+                                   for m in (self.linguistic, self.visual, self.acoustic)])
         out = []
         for x, conv, p in ((l, self.linguistic, pos[0]), (v, self.visual, pos[1]),
                            (a, self.acoustic, pos[2])):

@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .blocks import LiteAttentionBlock, as_mask, fusion_trunk, is_bf16
+from .blocks import LiteAttentionBlock, as_mask, fusion_trunk_multi, is_bf16
 
 # reference module constants (Ren-MME/run.py:21-39)
 L_LEN, V_LEN, A_LEN = 40, 76, 275
@@ -26,6 +26,9 @@ class Unify_Dimension(nn.Module):
 
     def forward(self, l, v, a):
         bf = is_bf16()
+        if bf:      # the bf16 shadows of all projection weights in one cast launch
+            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
+                                   for m in (self.linguistic, self.visual, self.acoustic)])
         w, b = self.norm1.weight, self.norm1.bias
         return tuple(ops.add_ln(None, ops.linear(x, lin.weight, bf16=bf), None, w, b)
                      for x, lin in ((l, self.linguistic), (v, self.visual), (a, self.acoustic)))
@@ -51,11 +54,15 @@ class Multi_ATTN(nn.Module):
                                                 for _ in range(9 * n_layers)])
         self.classifier = nn.Linear(dim * 6 * n_layers, self.N_CLS, bias=False)
 
-    def forward(self, l, v, a, l_mask, v_mask, a_mask):
+    def _tower(self, l, v, a, l_mask, v_mask, a_mask):
+        """(blocks, projected features, masks) - the input of ``fusion_trunk_multi``."""
         l, v, a = self.unify_dimension(l, v, a)
-        x = fusion_trunk(self.multimodal_blocks, self.n_layers, {"l": l, "v": v, "a": a},
-                         {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)},
-                         keep_all=True)
+        return (self.multimodal_blocks, {"l": l, "v": v, "a": a},
+                {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)})
+
+    def forward(self, l, v, a, l_mask, v_mask, a_mask):
+        x = fusion_trunk_multi([self._tower(l, v, a, l_mask, v_mask, a_mask)], self.n_layers,
+                               keep_all=True)[0]
         return ops.linear(x, self.classifier.weight)
 
 
@@ -76,10 +83,15 @@ class Base_model(nn.Module):
     def forward(self, pre_text_feat, pre_text_mask, pro_text_feat, pro_text_mask, pre_video_feat,
                 pre_video_mask, pro_video_feat, pro_video_mask, pre_audio_feat, pre_audio_mask,
                 pro_audio_feat, pro_audio_mask):
-        last_feat = self.intensity(pre_text_feat, pre_video_feat, pre_audio_feat, pre_text_mask,
-                                   pre_video_mask, pre_audio_mask)
-        this_feat = self.stimulation(pro_text_feat, pro_video_feat, pro_audio_feat, pro_text_mask,
-                                     pro_video_mask, pro_audio_mask)
+        # both towers' trunks as ONE group per layer (they are independent until the bilinear head)
+        ti, ts = self.intensity, self.stimulation
+        pi, ps = fusion_trunk_multi(
+            [ti._tower(pre_text_feat, pre_video_feat, pre_audio_feat, pre_text_mask, pre_video_mask,
+                       pre_audio_mask),
+             ts._tower(pro_text_feat, pro_video_feat, pro_audio_feat, pro_text_mask, pro_video_mask,
+                       pro_audio_mask)], ti.n_layers, keep_all=True)
+        last_feat = ops.linear(pi, ti.classifier.weight)
+        this_feat = ops.linear(ps, ts.classifier.weight)
         return ops.bilinear_head(this_feat, last_feat, self.trans, self.norm3.weight,
                                  self.norm3.bias, self.out.weight, self.out.bias)
 

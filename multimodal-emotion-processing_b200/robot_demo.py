@@ -6,7 +6,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .blocks import FullAttentionBlock, as_act, as_mask, fusion_trunk, is_bf16
+from .blocks import FullAttentionBlock, as_act, as_mask, fusion_trunk_multi, is_bf16
 
 DROP = 0.1  # robot_demo.py:41
 
@@ -25,6 +25,9 @@ class Unify_Dimension_Conv1d(nn.Module):
 
     def forward(self, l, v_256, v_512, v_1024, a):
         bf = is_bf16()
+        if bf:      # the bf16 shadows of all projection weights in one cast launch
+            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
+                                   for m in (self.linguistic, self.visual_1024, self.visual_512, self.visual_256, self.acoustic)])
 
         def proj(x, conv):
             return ops.dropout(ops.linear(x, conv.weight, conv.bias, bf16=bf), self.drop.p,
@@ -72,14 +75,18 @@ class Multi_class(nn.Module):
         self.drop = nn.Dropout(DROP)
         self.classifier = nn.Linear(dim * 6 * n_layers, 7)
 
-    def forward(self, l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask):
+    def _tower(self, l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask):
+        """(blocks, projected + position-embedded features, masks) for ``fusion_trunk_multi``."""
         l, v, a = self.unify_dimension(l, v_256, v_512, v_1024, a)
         l = l + self.linguistic_position(l)
         v = v + self.visual_position(v)
         a = a + self.acoustic_position(a)
-        x = fusion_trunk(self.multimodal_blocks, self.n_layers, {"l": l, "v": v, "a": a},
-                         {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)},
-                         keep_all=True)
+        return (self.multimodal_blocks, {"l": l, "v": v, "a": a},
+                {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)})
+
+    def forward(self, l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask):
+        x = fusion_trunk_multi([self._tower(l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask)],
+                               self.n_layers, keep_all=True)[0]
         return ops.linear(x, self.classifier.weight, self.classifier.bias)
 
 
@@ -126,17 +133,28 @@ class Ensemble:
         self._graphs.clear()
 
     def _forward(self, args):
-        """All members concurrently: one side stream per member, joined before the average."""
-        cur = torch.cuda.current_stream()
-        if self._streams is None or len(self._streams) != len(self.models):
-            self._streams = [torch.cuda.Stream() for _ in self.models]
-        preds = []
-        for m, s in zip(self.models, self._streams):
-            s.wait_stream(cur)
-            with torch.cuda.stream(s):
-                preds.append(m(*args))
-        for s in self._streams:
-            cur.wait_stream(s)
+        """All members at once.  Members that are this module's ``Multi_class`` with one
+        architecture run as ONE group: layer i of every chain of every member (4 x 9 = 36
+        problems) is one launch per kernel kind (``fusion_trunk_multi``; weights stay per member -
+        the problem tables carry each member's own pointers, nothing is copied or stacked).  Other
+        member types run concurrently on side streams, joined before the average."""
+        ms = self.models
+        if all(isinstance(m, Multi_class) for m in ms) and \
+                len({(m.n_layers, len(m.multimodal_blocks)) for m in ms}) == 1:
+            pooled = fusion_trunk_multi([m._tower(*args) for m in ms], ms[0].n_layers, keep_all=True)
+            preds = [ops.linear(x, m.classifier.weight, m.classifier.bias)
+                     for m, x in zip(ms, pooled)]
+        else:
+            cur = torch.cuda.current_stream()
+            if self._streams is None or len(self._streams) != len(ms):
+                self._streams = [torch.cuda.Stream() for _ in ms]
+            preds = []
+            for m, s in zip(ms, self._streams):
+                s.wait_stream(cur)
+                with torch.cuda.stream(s):
+                    preds.append(m(*args))
+            for s in self._streams:
+                cur.wait_stream(s)
         pred = preds[0]
         for p in preds[1:]:            # same summation order as robot_demo.py:614
             pred = pred + p

@@ -37,18 +37,62 @@ def test_linear_formulas_and_positions():
 def test_grouped_linear_formulas():
     Ms, Ns, Ks = [8192, 8192], [512, 1024], [512, 512]
     name = "mmemo_linear_fwd_grouped_bf16"
-    assert len(_lib.SIGNATURES[name]) == 13
-    a = [2] + [None] * 12
+    assert len(_lib.SIGNATURES[name]) == 14
+    a = [2] + [None] * 13
     a[8], a[9], a[10] = Ms, Ns, Ks
     fl, by, tag = bench._algorithmic(name, tuple(a))
     assert fl == sum(2 * m * n * k for m, n, k in zip(Ms, Ns, Ks))
     assert tag == "8192x512x512+8192x1024x512"
+    name = "mmemo_linear_bwd_x_grouped_bf16"      # ..., relu_src, ldrelu, M, N, K, accumulate, stream
+    assert len(_lib.SIGNATURES[name]) == 14
+    a = [2] + [None] * 13
+    a[9], a[10], a[11] = Ms, Ns, Ks
+    fl, by, _ = bench._algorithmic(name, tuple(a))
+    assert fl == sum(2 * m * n * k for m, n, k in zip(Ms, Ns, Ks))
     name = "mmemo_linear_bwd_w_grouped_bf16"
     assert len(_lib.SIGNATURES[name]) == 12
     a = [2] + [None] * 11
     a[7], a[8], a[9] = Ms, Ns, Ks
     fl, by, _ = bench._algorithmic(name, tuple(a))
     assert by == sum(2 * (m * n + m * k) + 4 * n * k for m, n, k in zip(Ms, Ns, Ks))
+    # large groups (a fusion-trunk layer): one tag entry per distinct shape
+    a[7], a[8], a[9] = [9600] * 9, [96] * 9, [96] * 9
+    a[0] = 9
+    _, _, tag = bench._algorithmic(name, tuple(a))
+    assert tag == "G9:9x9600x96x96"
+
+
+def test_grouped_attention_and_layernorm_formulas():
+    """The grouped entry points take a table: bench reads it back through the ctypes struct."""
+    B, H, Lq, Lk, hd = 192, 6, 50, 50, 16
+    d, S = H * hd, B * H * Lq * Lk
+    probs = (_lib.AttnProblem * 2)()
+    for i in range(2):
+        q = probs[i]
+        q.q, q.k, q.v = 0x1000, 0x2000, 0x3000
+        q.B, q.H, q.Lq, q.Lk, q.hd = B, H, Lq, Lk, hd
+        q.s_out = 0x4000
+    probs[1].s_prev = 0x5000
+    fl, by, tag = bench._algorithmic("mmemo_resattn_fwd_grouped_bf16",
+                                     (2, C.cast(probs, C.c_void_p), None))
+    assert fl == 2 * 4 * B * Lq * Lk * d
+    assert by == 2 * (2 * B * d * 3 * Lq + 4 * B * Lk + 2 * B * Lq * d + 2 * S) + 2 * S
+    assert tag.startswith("G2:B192H6hd16:")
+    probs[0].v = probs[0].k            # lite block: K = V read once
+    _, by2, _ = bench._algorithmic("mmemo_resattn_fwd_grouped_bf16",
+                                   (2, C.cast(probs, C.c_void_p), None))
+    assert by - by2 == 2 * B * d * Lk
+    Ms = [9600] * 9
+    name = "mmemo_add_ln_fwd_grouped_bf16"
+    a = [9] + [None] * 13
+    a[1], a[9], a[10] = [1] * 9, Ms, 96
+    _, by, _ = bench._algorithmic(name, tuple(a))
+    assert by == 3 * 2 * sum(Ms) * 96
+    name = "mmemo_add_ln_bwd_grouped_bf16"
+    a = [9] + [None] * 16
+    a[2], a[14], a[15] = [1] * 9, Ms, 96
+    _, by, _ = bench._algorithmic(name, tuple(a))
+    assert by == 5 * 2 * sum(Ms) * 96
 
 
 def test_attention_formulas_match_survey_8d():

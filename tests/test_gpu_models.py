@@ -385,3 +385,59 @@ def test_robot_demo_graphed_ensemble_equals_sequential_members(B):
     emo = ens.emotions(out)
     assert list(emo) == ["happy", "sad", "angry", "disgust", "surprise", "fear"]
     assert all(0.0 <= v <= 1.0 for v in emo.values())
+
+
+# ------------------------------------------------------------------------------------------------
+# grouped trunk (group_ops.py) vs the per-block path
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["realformer_state_transfer", "mosei_concat_trans",
+                                  "renmme_base_model", "robot_multi_class"])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_grouped_trunk_equals_per_block_path(name, mode, monkeypatch):
+    """One grouped op per layer over all chains / towers must give what the chain-by-chain blocks
+    give: float32 to summation order (the same launchers run per problem), bf16 to bf16 noise
+    (different kernels: grouped mma.sync attention, grouped tcgen05 GEMMs), for logits AND every
+    parameter / input gradient - this pins the slot layout of the grouped weight-gradient buffer."""
+    from mmemo_b200 import blocks
+    c = cases.CASES[name]
+    g = torch.load(cases.golden_path(name))
+    model = c.our_model(mmemo_b200).to(DEV).train()
+    model.load_state_dict(g["state"])
+    b = to_dev(g["batch"])
+    with mmemo_b200.precision(mode):
+        monkeypatch.setattr(blocks, "GROUPED_TRUNK", True)
+        lg_g, _, gr_g, ig_g = cases.run_module_with_grads(model, c, b, Loss)
+        monkeypatch.setattr(blocks, "GROUPED_TRUNK", False)
+        lg_b, _, gr_b, ig_b = cases.run_module_with_grads(model, c, b, Loss)
+    tol = 2e-5 if mode == "fp32" else 4e-2
+    assert rel_err(lg_g.float(), lg_b.float()) < tol
+    assert set(gr_g) == set(gr_b)
+    worst = max((rel_err(gr_g[k], v), k) for k, v in gr_b.items() if v.numel() > 1)
+    assert worst[0] < tol, worst
+    for k, v in ig_b.items():
+        assert rel_err(ig_g[k].float(), v.float()) < tol, k
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_cfg5_ensemble_matches_oracle_mean_of_members(prec):
+    """robot_demo.py:610-615 at native shapes: the grouped 4-member ensemble (36 problems per
+    launch) against the ORACLE's mean of the four members' logits, B = 1 and B = 32."""
+    kw = dict(dim=192, l_len=25, v_len=100, a_len=100, n_heads=6, n_layers=2, ffn=2)
+    models, sds = [], []
+    for i in range(4):
+        torch.manual_seed(i)
+        m = mmemo_b200.robot_demo.Multi_class(**kw)
+        sd = synth.randomize_gates({k: v.detach().clone() for k, v in m.state_dict().items()},
+                                   seed=10 + i)
+        m.load_state_dict(sd)
+        sds.append(sd)
+        models.append(m.to(DEV).eval())
+    ens = mmemo_b200.robot_demo.Ensemble(models)
+    names = mmemo_b200.robot_demo.Ensemble.NAMES
+    with mmemo_b200.precision(prec):
+        for B in (1, 32):
+            b = synth.robot_batch(seed=21 + B, B=B)
+            with torch.no_grad():
+                ref = sum(O.robot_multi_class(sd, *[b[k] for k in names], 6, 2) for sd in sds) / 4
+            out = ens(*[b[k].to(DEV) for k in names])
+            assert rel_err(out.float(), ref) < (TOL32 if prec == "fp32" else TOLBF), (prec, B)

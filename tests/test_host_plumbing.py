@@ -18,11 +18,15 @@ class _FakeLib:
     def mmemo_resattn_uses_tensor_cores(self, *a):
         return 0
 
+    def mmemo_resattn_uses_mma(self, *a):
+        return 1
+
 
 @pytest.fixture()
 def stub(monkeypatch):
     calls = []
     monkeypatch.setattr(ops, "_call", lambda name, *a: calls.append(name))
+    monkeypatch.setattr(ops, "_try_call", lambda name, *a: calls.append(name) or True)
     monkeypatch.setattr(ops, "_need_cuda", lambda *a: None)
     monkeypatch.setattr(ops, "_stream", lambda: 0)
     monkeypatch.setattr(ops._lib, "load", lambda: _FakeLib())
@@ -80,25 +84,54 @@ def test_unfused_paths_when_k_is_not_v(stub):
 
 
 def test_trunk_skips_unused_score_writes(stub, monkeypatch):
-    """The last layer of a chain must not write its scores (nothing consumes them), and the drop-in
-    blocks themselves keep returning scores afterwards (emit_scores is a per-call argument, not
-    module state)."""
-    emitted = []
-    real = ops.block_lite_op
+    """The last layer of a chain must not write its scores (nothing consumes them) - in the grouped
+    trunk (one op per layer over the nine chains) and in the per-block path - and the drop-in blocks
+    themselves keep returning scores afterwards (emit_scores is a per-call argument, not module
+    state)."""
+    from mmemo_b200 import blocks, group_ops
+    emitted, groups = [], []
+    real, real_g = ops.block_lite_op, group_ops.trunk_lite_op
 
     def spy(q, kv, mask, s_prev, params, H, bf16, emit_s):
         emitted.append(emit_s)
         return real(q, kv, mask, s_prev, params, H, bf16, emit_s)
 
+    def spy_g(qs, kvs, masks, s_prevs, params, H, bf16, emit_s):
+        groups.append((len(qs), len(s_prevs), emit_s))
+        return real_g(qs, kvs, masks, s_prevs, params, H, bf16, emit_s)
+
     monkeypatch.setattr(ops, "block_lite_op", spy)
+    monkeypatch.setattr(group_ops, "trunk_lite_op", spy_g)
     m = mmemo_b200.cmu_mosei.Multi_ATTN(16, 4, 5, 6, 2, 2, 1, l_dim=8, v_dim=6, a_dim=7)
-    m(torch.randn(2, 4, 8), torch.randn(2, 5, 6), torch.randn(2, 6, 7), torch.ones(2, 4),
-      torch.ones(2, 5), torch.ones(2, 6))
-    assert emitted == [True, False] * 9
+    args = (torch.randn(2, 4, 8), torch.randn(2, 5, 6), torch.randn(2, 6, 7), torch.ones(2, 4),
+            torch.ones(2, 5), torch.ones(2, 6))
+    out_g = m(*args)
+    assert groups == [(9, 0, True), (9, 9, False)] and emitted == []
+    monkeypatch.setattr(blocks, "GROUPED_TRUNK", False)
+    out_b = m(*args)
+    assert emitted == [True, False] * 9 and out_b.shape == out_g.shape
     blk = m.multimodal_blocks[1]                  # a last-layer block, called directly
     x = torch.randn(2, 4, 16)
     out, s = blk(x, x, x, torch.ones(2, 4))
     assert s is not None and s.shape == (2, 2, 4, 4)
+
+
+def test_grouped_trunk_launch_count(stub):
+    """One grouped launch per kernel kind and layer: a State_Transfer step (2 layers x 9 chains,
+    fwd+bwd) stays under 60 libmmemo launches in bf16 mode (~350 before)."""
+    m = mmemo_b200.realformer.State_Transfer(l_dim=16, v_dim=8, a_dim=8, dim=16, l_len=4, v_len=4,
+                                             a_len=4, n_heads=2, n_layers=2, ffn=2).train()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith((".a", ".b", ".c")):
+                p.fill_(0.3)
+    b = dict(l=torch.randn(2, 3, 4, 16), v=torch.randn(2, 3, 4, 8), a=torch.randn(2, 3, 4, 8))
+    ones = torch.ones(2, 3, 4)
+    with mmemo_b200.precision("bf16"):
+        out = m(b["l"], b["v"], b["a"], ones, ones, ones)
+        ops.circle_loss_op(out, torch.zeros(2, 3, 6)).mean().backward()
+    assert len(stub) <= 60, (len(stub), stub)
+    assert sum(n.startswith("mmemo_resattn") for n in stub) == 4      # 2 layers x (fwd + bwd)
 
 
 def test_shadow_cache_tracks_parameter_version(stub):
