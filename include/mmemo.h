@@ -96,7 +96,9 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
                                   const void* const* w, const int64_t* ldw,
                                   const float* const* bias, void* const* y, const int64_t* ldy,
                                   const int64_t* M, const int64_t* N, const int64_t* K,
-                                  const int* relu, const int* accumulate, mmemo_stream_t stream);
+                                  const int* relu, const int* accumulate,
+                                  const float* const* pos, const int64_t* pos_period,
+                                  mmemo_stream_t stream);
 int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
                                     const void* const* w, const int64_t* ldw, void* const* dx,
                                     const int64_t* lddx, const void* const* relu_src,
@@ -267,6 +269,13 @@ int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_
  * whole trunk layer */
 int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const* dst,
                                  const int64_t* n, mmemo_stream_t stream);
+/* `count` <= 16 float32 (M, K) matrices (row stride lds) -> bf16 (M, ldd) with ldd % 8 == 0 and
+ * zero-filled padding columns, in one launch: raw input features (the float tensors built at
+ * others/realformer.py:307-309, Ren-MME/run.py:316-327) and their projection weights become
+ * 16-byte-strided operands of the tensor-core GEMM. */
+int mmemo_cast_pad_f32_to_bf16_multi(int count, const float* const* src, const int64_t* lds,
+                                     void* const* dst, const int64_t* ldd, const int64_t* M,
+                                     const int64_t* K, mmemo_stream_t stream);
 /* y = x * keep/(1-p), keep ~ Bernoulli(1-p) from a counter-based RNG keyed by (seed, element).
  * Forward and backward are the same call (nn.Dropout at others/realformer.py:139,159,167,222). */
 int mmemo_dropout_f32(const void* x, void* y, int64_t n, float p, uint64_t seed,

@@ -51,7 +51,7 @@ SIGNATURES = {
     "mmemo_linear_fwd_f32": _LINEAR_FWD, "mmemo_linear_fwd_bf16": _LINEAR_FWD,
     "mmemo_linear_bwd_x_f32": _LINEAR_BWD_X, "mmemo_linear_bwd_x_bf16": _LINEAR_BWD_X,
     "mmemo_linear_bwd_w_f32": _LINEAR_BWD_W, "mmemo_linear_bwd_w_bf16": _LINEAR_BWD_W,
-    "mmemo_linear_fwd_grouped_bf16": [_i32] + [_vp] * 12 + [_vp],
+    "mmemo_linear_fwd_grouped_bf16": [_i32] + [_vp] * 14 + [_vp],
     "mmemo_linear_bwd_x_grouped_bf16": [_i32] + [_vp] * 12 + [_vp],
     "mmemo_linear_bwd_w_grouped_bf16": [_i32] + [_vp] * 9 + [_i32, _vp],
     "mmemo_resattn_fwd_f32": _ATTN_FWD, "mmemo_resattn_fwd_bf16": _ATTN_FWD,
@@ -70,6 +70,7 @@ SIGNATURES = {
     "mmemo_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mmemo_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "mmemo_cast_f32_to_bf16_multi": [_i32, _vp, _vp, _vp, _vp],
+    "mmemo_cast_pad_f32_to_bf16_multi": [_i32] + [_vp] * 6 + [_vp],
     "mmemo_dropout_f32": _DROPOUT, "mmemo_dropout_bf16": _DROPOUT,
     "mmemo_pool_fwd_f32": _POOL_FWD, "mmemo_pool_fwd_bf16": _POOL_FWD,
     "mmemo_pool_bwd_f32": _POOL_BWD, "mmemo_pool_bwd_bf16": _POOL_BWD,

@@ -24,13 +24,9 @@ class Unify_Dimension(nn.Module):
         self.acoustic = nn.Linear(A_DIM if a_dim is None else a_dim, dim, bias=False)
 
     def forward(self, l, v, a):
-        bf = is_bf16()
-        if bf:      # the bf16 shadows of all projection weights in one cast launch
-            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
-                                   for m in (self.linguistic, self.visual, self.acoustic)])
-        return (ops.linear(l, self.linguistic.weight, bf16=bf),
-                ops.linear(v, self.visual.weight, bf16=bf),
-                ops.linear(a, self.acoustic.weight, bf16=bf))
+        from .group_ops import project
+        return tuple(project([l, v, a], [self.linguistic.weight, self.visual.weight,
+                                         self.acoustic.weight], bf16=is_bf16()))
 
 
 class Attention_Block(LiteAttentionBlock):

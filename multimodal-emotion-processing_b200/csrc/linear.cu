@@ -88,7 +88,9 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
                                   const void* const* w, const int64_t* ldw,
                                   const float* const* bias, void* const* y, const int64_t* ldy,
                                   const int64_t* M, const int64_t* N, const int64_t* K,
-                                  const int* relu, const int* accumulate, mmemo_stream_t s) {
+                                  const int* relu, const int* accumulate,
+                                  const float* const* pos, const int64_t* pos_period,
+                                  mmemo_stream_t s) {
   if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
   GemmArgs g[GEMM_TC_MAX_GROUP] = {};
   int cb[GEMM_TC_MAX_GROUP];
@@ -102,6 +104,10 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
     g[i].bias = bias ? bias[i] : nullptr; g[i].pos_period = 1;
     g[i].relu = relu ? relu[i] : 0;
     g[i].accumulate = accumulate ? accumulate[i] : 0;
+    if (pos && pos[i]) {
+      MM_REQUIRE(pos_period && pos_period[i] > 0);
+      g[i].pos = pos[i]; g[i].pos_period = pos_period[i];
+    }
     cb[i] = 1;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 1, n > 1);
   }

@@ -192,6 +192,51 @@ colsum_bf16_vec_grouped_kernel(const __grid_constant__ ColsumTable tb, int64_t N
   }
 }
 
+// float32 (M, K) matrices with arbitrary leading dimension -> bf16 (M, ldd) with ldd = K rounded up
+// to 8 and zero padding: the raw input features (others/realformer.py:307-309 float tensors of
+// width 300 / 35 / 74, Ren-MME 768 / 640 / 205) become TMA-legal operands of the tcgen05 GEMM
+// (16-byte row stride).  One launch for all modalities / towers: blockIdx.y = tensor.
+constexpr int PC_MAXT = 16;
+struct PadCastTable {
+  const float* src[PC_MAXT];
+  bf16* dst[PC_MAXT];
+  long long M[PC_MAXT];
+  int K[PC_MAXT], lds[PC_MAXT], ldd[PC_MAXT];
+};
+__global__ void __launch_bounds__(256) cast_pad_kernel(const __grid_constant__ PadCastTable t) {
+  const int w = blockIdx.y;
+  pdl_wait();
+  pdl_trigger();
+  const float* __restrict__ s = t.src[w];
+  bf16* __restrict__ d = t.dst[w];
+  const int K = t.K[w], lds = t.lds[w], ldd = t.ldd[w];
+  const int cpr = ldd >> 3;                                 // 8-column chunks per row
+  const long long total = t.M[w] * cpr;
+  const bool vec = (lds & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total;
+       i += (long long)gridDim.x * 256) {
+    const long long r = i / cpr;
+    const int c0 = (int)(i - r * cpr) * 8;
+    const float* sp = s + r * lds + c0;
+    float v[8];
+    if (vec && c0 + 8 <= K) {
+      const float4 a = *reinterpret_cast<const float4*>(sp);
+      const float4 b = *reinterpret_cast<const float4*>(sp + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < K) ? sp[j] : 0.f;
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      o[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(d + r * ldd + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 template <typename T>
 int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
            cudaStream_t st) {
@@ -274,6 +319,29 @@ int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const
   if (bx > 148) bx = 148;
   if (bx < 1) bx = 1;
   MM_CUDA_OK(mm_launch(cast_multi_kernel, dim3((unsigned)bx, (unsigned)count), dim3(256), 0,
+                       mm_stream(s), t));
+  return MMEMO_OK;
+}
+int mmemo_cast_pad_f32_to_bf16_multi(int count, const float* const* src, const int64_t* lds,
+                                     void* const* dst, const int64_t* ldd, const int64_t* M,
+                                     const int64_t* K, mmemo_stream_t s) {
+  if (count <= 0) return MMEMO_OK;
+  if (count > PC_MAXT) return MMEMO_ERR_ARG;
+  static thread_local PadCastTable t;
+  long long most = 0;
+  for (int i = 0; i < count; ++i) {
+    MM_REQUIRE(src[i] && dst[i] && M[i] >= 0 && K[i] > 0 && lds[i] >= K[i] && ldd[i] >= K[i]);
+    MM_REQUIRE(ldd[i] % 8 == 0 && (reinterpret_cast<uintptr_t>(dst[i]) & 15) == 0);
+    t.src[i] = src[i]; t.dst[i] = static_cast<bf16*>(dst[i]);
+    t.M[i] = M[i]; t.K[i] = (int)K[i]; t.lds[i] = (int)lds[i]; t.ldd[i] = (int)ldd[i];
+    const long long n = M[i] * (ldd[i] / 8);
+    most = n > most ? n : most;
+  }
+  if (most == 0) return MMEMO_OK;
+  long long bx = cdiv(most, 256);
+  const long long cap = cdiv(148 * 8, count);
+  if (bx > cap) bx = cap;
+  MM_CUDA_OK(mm_launch(cast_pad_kernel, dim3((unsigned)bx, (unsigned)count), dim3(256), 0,
                        mm_stream(s), t));
   return MMEMO_OK;
 }

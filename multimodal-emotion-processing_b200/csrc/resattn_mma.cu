@@ -60,6 +60,7 @@ struct Prob {
 struct Table {
   int n, total;
   float inv_sqrt;
+  int kv_blocked;   // backward: K / V are staged one key block at a time (long hd = 64 sequences)
   Prob p[MAXP];
 };
 
@@ -353,13 +354,15 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   const int h = local % H, b = local / H;
   const int LqP = (Lq + 15) & ~15, LkP = (Lk + KB - 1) / KB * KB;
   const bool same_kv = (P.k == P.v) && (P.ldk == P.ldv);
+  const bool kv_blocked = T.kv_blocked != 0;
+  const int kv_rows = kv_blocked ? KB : LkP;       // rows of the K / V tiles in shared memory
   // carve-up: Q | dO | K | (V) | P | dS | dQ(fp32) | stat(m, 1/l, D) | bias
   uint32_t off = 0;
   const uint32_t sQ = s_u32(smem) + off;   off += LqP * HD * 2;
   const uint32_t sdO = s_u32(smem) + off;  off += LqP * HD * 2;
-  const uint32_t sK = s_u32(smem) + off;   off += LkP * HD * 2;
+  const uint32_t sK = s_u32(smem) + off;   off += kv_rows * HD * 2;
   uint32_t sV = sK;
-  if (!same_kv) { sV = s_u32(smem) + off;  off += LkP * HD * 2; }
+  if (!same_kv) { sV = s_u32(smem) + off;  off += kv_rows * HD * 2; }
   const uint32_t sP = s_u32(smem) + off;   off += LqP * KB * 2;
   const uint32_t sdS = s_u32(smem) + off;  off += LqP * KB * 2;
   float* sdQ = reinterpret_cast<float*>(smem + off);    off += LqP * HD * 4;
@@ -372,8 +375,10 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   pdl_trigger();
   stage<HD, NT>(sQ, P.q + (size_t)b * Lq * P.ldq + h * HD, P.ldq, Lq, LqP);
   stage<HD, NT>(sdO, P.d_o + (size_t)b * Lq * P.lddo + h * HD, P.lddo, Lq, LqP);
-  stage<HD, NT>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
-  if (!same_kv) stage<HD, NT>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
+  if (!kv_blocked) {
+    stage<HD, NT>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
+    if (!same_kv) stage<HD, NT>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
+  }
   for (int j = threadIdx.x; j < LkP; j += NT)
     sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
   for (int i = threadIdx.x; i < LqP * HD; i += NT) sdQ[i] = 0.f;
@@ -410,6 +415,14 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   float dc_part = 0.f;
 
   for (int kb = 0; kb < Lk; kb += KB) {
+    const int kofs = kv_blocked ? kb : 0;            // first key held in the K / V tiles
+    if (kv_blocked) {       // (the previous block's readers passed the barrier ending the loop body)
+      stage<HD, NT>(sK, P.k + ((size_t)b * Lk + kb) * P.ldk + h * HD, P.ldk, min(KB, Lk - kb), KB);
+      if (!same_kv)
+        stage<HD, NT>(sV, P.v + ((size_t)b * Lk + kb) * P.ldv + h * HD, P.ldv, min(KB, Lk - kb), KB);
+      cp_commit_wait();
+      __syncthreads();
+    }
     // ================= phase A: one warp per 16-row tile ========================================
     for (int rt = warp; rt < n_rt; rt += BWD_WARPS) {
       const int rowA = rt * 16 + g, rowB = rowA + 8;
@@ -439,7 +452,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
               const int mi = lane >> 3, r = lane & 7;
               const int key = kb + 32 * G + perm_key(ip * 2 + (mi >> 1), r);
               uint32_t kf[4];
-              ldsm4(sK + sw<HD>(key, 2 * kt + (mi & 1)), kf);
+              ldsm4(sK + sw<HD>(key - kofs, 2 * kt + (mi & 1)), kf);
               mma16816(sc[G * 4 + ip * 2], qa[kt], kf[0], kf[1]);
               mma16816(sc[G * 4 + ip * 2 + 1], qa[kt], kf[2], kf[3]);
             }
@@ -454,7 +467,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
             const int mi = lane >> 3, r = lane & 7;
             const int key = kb + 32 * G + perm_key(ip * 2 + (mi >> 1), r);
             uint32_t vf[4];
-            ldsm4(sV + sw<HD>(key, 2 * kt + (mi & 1)), vf);
+            ldsm4(sV + sw<HD>(key - kofs, 2 * kt + (mi & 1)), vf);
             mma16816(dp[G * 4 + ip * 2], doa[kt], vf[0], vf[1]);
             mma16816(dp[G * 4 + ip * 2 + 1], doa[kt], vf[2], vf[3]);
           }
@@ -531,7 +544,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
             const int mi = lane >> 3, r = lane & 7;
             const int key = kb + 32 * G + perm_key(2 * pp + (mi & 1), r);
             uint32_t kf[4];
-            ldsm4t(sK + sw<HD>(key, c2 + (mi >> 1)), kf);
+            ldsm4t(sK + sw<HD>(key - kofs, c2 + (mi >> 1)), kf);
             mma16816(dq[c2], da, kf[0], kf[1]);
             mma16816(dq[c2 + 1], da, kf[2], kf[3]);
           }
@@ -628,9 +641,10 @@ size_t fwd_smem(int hd, int Lk, bool same_kv) {
   const int LkP = (Lk + 63) & ~63;
   return (size_t)FWD_ROWS * hd * 2 + (size_t)(same_kv ? 1 : 2) * LkP * hd * 2 + (size_t)LkP * 4;
 }
-size_t bwd_smem(int hd, int kbk, int Lq, int Lk, bool same_kv) {
+size_t bwd_smem(int hd, int kbk, int Lq, int Lk, bool same_kv, bool kv_blocked = false) {
   const int LqP = (Lq + 15) & ~15, LkP = (Lk + kbk - 1) / kbk * kbk;
-  return (size_t)2 * LqP * hd * 2 + (size_t)(same_kv ? 1 : 2) * LkP * hd * 2 +
+  const int kv_rows = kv_blocked ? kbk : LkP;
+  return (size_t)2 * LqP * hd * 2 + (size_t)(same_kv ? 1 : 2) * kv_rows * hd * 2 +
          (size_t)2 * LqP * kbk * 2 + (size_t)LqP * hd * 4 + (size_t)LqP * 12 + (size_t)LkP * 4;
 }
 
@@ -678,7 +692,7 @@ bool resattn_mma_supported(const mmemo_attn_problem& a, bool bwd) {
   if (!operands_ok(a, bwd)) return false;
   const bool same = a.k == a.v && a.ldk == a.ldv;
   if (!bwd) return fwd_smem((int)a.hd, (int)a.Lk, same) <= SMEM_MAX;
-  return bwd_smem((int)a.hd, 32, (int)a.Lq, (int)a.Lk, same) <= SMEM_MAX;
+  return bwd_smem((int)a.hd, 32, (int)a.Lq, (int)a.Lk, same, true) <= SMEM_MAX;
 }
 
 int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
@@ -715,7 +729,7 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
   static thread_local Table T;
   T.n = n;
   const int hd = (int)ps[0].hd;
-  size_t smem64 = 0, smem32 = 0;
+  size_t smem64 = 0, smem32 = 0, full32 = 0;
   int ctas = 0;
   for (int i = 0; i < n; ++i) {
     if (ps[i].hd != hd || !resattn_mma_supported(ps[i], true)) return MMEMO_ERR_SHAPE;
@@ -723,8 +737,17 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
     T.p[i].cta_start = ctas;
     ctas += (int)(ps[i].B * ps[i].H);
     const bool same = ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv;
-    const size_t s64 = bwd_smem(hd, 64, (int)ps[i].Lq, (int)ps[i].Lk, same);
-    const size_t s32 = bwd_smem(hd, 32, (int)ps[i].Lq, (int)ps[i].Lk, same);
+    const size_t f32_ = bwd_smem(hd, 32, (int)ps[i].Lq, (int)ps[i].Lk, same, false);
+    full32 = f32_ > full32 ? f32_ : full32;
+  }
+  // K and V whole in shared memory when that fits (one load per CTA); otherwise one key block at
+  // a time (hd = 64 with L = 256: 64 KB of K, V would not fit next to Q, dO, P, dS and the dQ tile)
+  const bool blocked = full32 > SMEM_MAX;
+  T.kv_blocked = blocked ? 1 : 0;
+  for (int i = 0; i < n; ++i) {
+    const bool same = ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv;
+    const size_t s64 = bwd_smem(hd, 64, (int)ps[i].Lq, (int)ps[i].Lk, same, blocked);
+    const size_t s32 = bwd_smem(hd, 32, (int)ps[i].Lq, (int)ps[i].Lk, same, blocked);
     smem64 = s64 > smem64 ? s64 : smem64;
     smem32 = s32 > smem32 ? s32 : smem32;
   }

@@ -570,3 +570,194 @@ def _trunk_lite_backward(ctx, grads):
 
 
 trunk_lite_op.register_autograd(_trunk_lite_backward, setup_context=_trunk_lite_setup)
+
+
+# ------------------------------------------------------------------------------------------------
+# mmemo::proj_group — the modality projections ("unify dimension") of one or several towers:
+#   y_g = x_g W_g^T (+ bias_g) (+ position table)  with x_g the RAW float32 features
+#   (others/realformer.py:133-143,225-227; cmu-mosei/run.py:207-214; Ren-MME/run.py:158-166;
+#   robot_demo.py:293-311).  bf16 mode only.
+# The features arrive as float32 with widths the tensor-core GEMM's TMA cannot address (300, 35,
+# 74, 205: rows are not 16-byte multiples), so the per-problem launchers ran them on the CUDA-core
+# GEMM — the largest mandatory HBM read of Ren-MME (278 MB / step) at ~4 % of the HBM roofline.
+# Here ONE launch casts all inputs (and weights) to bf16 with the row length padded to 8, ONE
+# grouped tcgen05 launch does all projections (bias / position table fused in its epilogue), and the
+# bf16 copy - half the bytes - is what backward re-reads for the weight gradients.
+# ------------------------------------------------------------------------------------------------
+def _pad8(k: int) -> int:
+    return (k + 7) // 8 * 8
+
+
+def _cast_pad(pairs) -> None:
+    """pairs: [(float32 2-D source, bf16 (M, Kp) destination)], one launch per 16 tensors."""
+    for i in range(0, len(pairs), 16):
+        part = pairs[i:i + 16]
+        _call("mmemo_cast_pad_f32_to_bf16_multi", len(part),
+              _arr(C.c_void_p, [s.data_ptr() for s, _ in part]),
+              _arr(C.c_int64, [s.stride(0) for s, _ in part]),
+              _arr(C.c_void_p, [d.data_ptr() for _, d in part]),
+              _arr(C.c_int64, [d.stride(0) for _, d in part]),
+              _arr(C.c_int64, [s.shape[0] for s, _ in part]),
+              _arr(C.c_int64, [s.shape[1] for s, _ in part]), _stream())
+
+
+def _w2d(w: Tensor) -> Tensor:
+    w = w.detach()
+    return w.reshape(w.shape[0], -1)          # Conv1d(k=1) weight (N, K, 1) == Linear weight (N, K)
+
+
+def _padded_shadow(w: Tensor, todo: list) -> Tensor:
+    """bf16 (N, Kp) zero-padded shadow of a float32 weight; cached like ops.shadow_bf16 (keyed on
+    the parameter's version counter).  Cache misses are appended to ``todo`` for one cast launch."""
+    w2 = _w2d(w)
+    key = (w.data_ptr(), w._version, tuple(w2.shape))
+    hit = ops._shadow_pad.get(key)
+    if hit is not None:
+        return hit
+    for k in [k for k in ops._shadow_pad if k[0] == w.data_ptr()]:
+        del ops._shadow_pad[k]
+    out = torch.empty(w2.shape[0], _pad8(w2.shape[1]), dtype=BF, device=w.device)
+    todo.append((w2 if w2.is_contiguous() else w2.contiguous(), out))
+    ops._shadow_pad[key] = out
+    return out
+
+
+@torch.library.custom_op("mmemo::proj_group", mutates_args=())
+def proj_group_op(xs: Sequence[Tensor], ws: Sequence[Tensor], biases: Sequence[Tensor],
+                  poss: Sequence[Tensor]) -> List[Tensor]:
+    """Returns [y_0 .. y_{G-1}, xb_0 .. xb_{G-1}] (xb = the padded bf16 copy of x, saved for the
+    weight gradient).  biases / poss entries with numel() == 0 mean "none"."""
+    ops._need_cuda(*xs)
+    G = len(xs)
+    todo, xbs, wps, ys, items = [], [], [], [], []
+    for g in range(G):
+        x = xs[g]
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        x2 = x2 if x2.stride(1) == 1 else x2.contiguous()
+        xb = torch.empty(x2.shape[0], _pad8(K), dtype=BF, device=x.device)
+        todo.append((x2, xb))
+        xbs.append(xb)
+    for g in range(G):
+        wps.append(_padded_shadow(ws[g], todo))
+    _cast_pad(todo)
+    for g in range(G):
+        N = wps[g].shape[0]
+        pos = _opt(poss[g])
+        if pos is not None:
+            assert xs[g].dim() == 3 and pos.shape[0] == xs[g].shape[1], \
+                "position table length != seq length"
+        y = torch.empty(*xs[g].shape[:-1], N, dtype=BF, device=xs[g].device)
+        ys.append(y)
+        items.append((xbs[g], wps[g], _opt(biases[g]), y.view(-1, N), False, False, pos))
+    ops._linear_fwd_group(True, items)
+    return ys + xbs
+
+
+def _proj_zlayout(Ns, Kps, has_bias, pos_lens):
+    """Offsets (floats, 256-byte aligned) of [dW_g (N, Kp) | dbias_g (N) | dpos_g (L, N)] per
+    problem inside the one zero-filled gradient buffer, and its total length."""
+    offs, tot = [], 0
+    for g in range(len(Ns)):
+        for n in (Ns[g] * Kps[g], Ns[g] if has_bias[g] else 0, pos_lens[g] * Ns[g]):
+            offs.append(tot)
+            tot += (n + 63) // 64 * 64
+    return offs, tot
+
+
+@torch.library.custom_op("mmemo::proj_group_bwd", mutates_args=())
+def proj_group_bwd_op(dys: Sequence[Tensor], xbs: Sequence[Tensor], ws: Sequence[Tensor],
+                      has_bias: Sequence[bool], pos_lens: Sequence[int],
+                      need_dx: Sequence[bool]) -> List[Tensor]:
+    """Returns [z] + [dx_g (float32 (M, K)) or empty]: z = ONE zero-initialised float32 buffer with
+    every parameter gradient of the group (layout: _proj_zlayout; dW_g padded to (N, Kp))."""
+    G = len(dys)
+    dev = dys[0].device
+    Ns = [_w2d(w).shape[0] for w in ws]
+    Ks = [_w2d(w).shape[1] for w in ws]
+    Kps = [_pad8(k) for k in Ks]
+    dys = [dy.contiguous().view(-1, n) for dy, n in zip(dys, Ns)]
+    offs, tot = _proj_zlayout(Ns, Kps, has_bias, pos_lens)
+    z = torch.zeros(tot, dtype=F32, device=dev)
+    dwp = [z[offs[3 * g]:offs[3 * g] + Ns[g] * Kps[g]].view(Ns[g], Kps[g]) for g in range(G)]
+    ops._linear_bwd_w_group(True, [(dys[g], xbs[g], dwp[g]) for g in range(G)], zeroed=True)
+    by_n = {}
+    for g in range(G):
+        if has_bias[g]:
+            by_n.setdefault(Ns[g], []).append(g)
+        if pos_lens[g]:
+            dp = z[offs[3 * g + 2]:offs[3 * g + 2] + pos_lens[g] * Ns[g]].view(pos_lens[g], Ns[g])
+            ops._rowsum(True, dys[g], dp, period=pos_lens[g])
+    for n, gs in by_n.items():
+        colsum_group(True, [dys[g] for g in gs],
+                     [z[offs[3 * g + 1]:offs[3 * g + 1] + n] for g in gs])
+    dxs = []
+    for g in range(G):
+        if need_dx[g]:
+            todo: list = []
+            wp = _padded_shadow(ws[g], todo)
+            _cast_pad(todo)
+            dxb = torch.empty(dys[g].shape[0], Kps[g], dtype=BF, device=dev)
+            ops._linear_bwd_x(True, dys[g], wp, dxb)
+            dxs.append(dxb[:, :Ks[g]].float())
+        else:
+            dxs.append(_e(dev))
+    return [z] + dxs
+
+
+def _proj_setup(ctx, inputs, output):
+    xs, ws, biases, poss = inputs
+    G = len(xs)
+    ctx.G = G
+    ctx.has_bias = [b.numel() > 0 for b in biases]
+    ctx.pos_lens = [p.shape[0] if p.numel() else 0 for p in poss]
+    ctx.x_shapes = [tuple(x.shape) for x in xs]
+    ctx.save_for_backward(*output[G:], *ws)
+    ctx.set_materialize_grads(False)
+
+
+def _proj_backward(ctx, grads):
+    G = ctx.G
+    t = list(ctx.saved_tensors)
+    xbs, ws = t[:G], t[G:]
+    need_dx = list(ctx.needs_input_grad[0])
+    Ns = [_w2d(w).shape[0] for w in ws]
+    Ks = [_w2d(w).shape[1] for w in ws]
+    Kps = [_pad8(k) for k in Ks]
+    dys = []
+    for g in range(G):
+        if grads[g] is None:
+            dys.append(torch.zeros(*ctx.x_shapes[g][:-1], Ns[g], dtype=BF, device=xbs[g].device))
+        else:
+            dys.append(grads[g])
+    res = proj_group_bwd_op(dys, xbs, ws, ctx.has_bias, ctx.pos_lens, need_dx)
+    z, dxs = res[0], res[1:]
+    offs, _ = _proj_zlayout(Ns, Kps, ctx.has_bias, ctx.pos_lens)
+    dws, dbs, dps = [], [], []
+    for g in range(G):
+        dw = z[offs[3 * g]:offs[3 * g] + Ns[g] * Kps[g]].view(Ns[g], Kps[g])
+        if Kps[g] != Ks[g]:
+            dw = dw[:, :Ks[g]].contiguous()
+        dws.append(dw.view(ws[g].shape))
+        dbs.append(z[offs[3 * g + 1]:offs[3 * g + 1] + Ns[g]] if ctx.has_bias[g] else None)
+        L = ctx.pos_lens[g]
+        dps.append(z[offs[3 * g + 2]:offs[3 * g + 2] + L * Ns[g]].view(L, Ns[g]) if L else None)
+    return ([dxs[g].view(ctx.x_shapes[g]) if need_dx[g] else None for g in range(G)], dws, dbs, dps)
+
+
+proj_group_op.register_autograd(_proj_backward, setup_context=_proj_setup)
+
+
+def project(xs, ws, biases=None, poss=None, bf16: bool = False) -> List[Tensor]:
+    """Modality projections of one or several towers.  bf16 mode with float32 inputs: the grouped
+    cast + tensor-core path above; otherwise the per-problem ``ops.linear`` (float32 parity mode,
+    or inputs that are already bf16)."""
+    G = len(xs)
+    biases = biases if biases is not None else [None] * G
+    poss = poss if poss is not None else [None] * G
+    if bf16 and all(x.dtype == F32 for x in xs):
+        dev = xs[0].device
+        ys = proj_group_op(list(xs), list(ws), [b if b is not None else _e(dev) for b in biases],
+                           [p if p is not None else _e(dev) for p in poss])
+        return list(ys[:G])
+    return [ops.linear(x, w, b, p, bf16=bf16) for x, w, b, p in zip(xs, ws, biases, poss)]

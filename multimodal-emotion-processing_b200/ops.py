@@ -118,11 +118,13 @@ def _need_cuda(*ts: Optional[Tensor]) -> None:
 # bf16 shadow copies of float32 master weights
 # ------------------------------------------------------------------------------------------------
 _shadow: dict = {}
+_shadow_pad: dict = {}     # zero-padded (N, K rounded up to 8) shadows of the projection weights
 
 
 def clear_shadow_cache() -> None:
     """Drop all bf16 weight shadows (call before CUDA-graph capture so the casts are captured)."""
     _shadow.clear()
+    _shadow_pad.clear()
 
 
 def shadow_bf16(*ws: Tensor) -> Tensor:
@@ -311,13 +313,13 @@ def _chunks(items, n=MAX_GEMM_GROUP):
 
 
 def _linear_fwd_group(bf16, items):
-    """items: [(x, w, bias, out2d, relu[, accumulate])].  One grouped tensor-core launch (per 48
-    problems) in bf16 mode; N, K and the weight's leading dimension come from ``w`` (a 2-D view,
-    e.g. one half of a concat weight)."""
-    items = [it if len(it) == 6 else (*it, False) for it in items]
+    """items: [(x, w, bias, out2d, relu[, accumulate[, pos]])].  One grouped tensor-core launch (per
+    48 problems) in bf16 mode; N, K and the weight's leading dimension come from ``w`` (a 2-D view,
+    e.g. one half of a concat weight); ``pos`` = (L, N) position table added with period L."""
+    items = [tuple(it) + (False, None)[len(it) - 5:] for it in items]
     if not bf16 or len(items) == 1:
-        for x, w, b, out, relu, acc in items:
-            _linear_fwd(bf16, x, w, b, None, out, relu=relu, accumulate=acc, ldw=w.stride(0),
+        for x, w, b, out, relu, acc, pos in items:
+            _linear_fwd(bf16, x, w, b, pos, out, relu=relu, accumulate=acc, ldw=w.stride(0),
                         N=w.shape[0], K=w.shape[1])
         return
     for part in _chunks(items):
@@ -332,7 +334,8 @@ def _linear_fwd_group(bf16, items):
               _arr(C.c_int64, [M for _, M, _ in xs]), _arr(C.c_int64, [it[1].shape[0] for it in part]),
               _arr(C.c_int64, [it[1].shape[1] for it in part]),
               _arr(C.c_int, [int(it[4]) for it in part]), _arr(C.c_int, [int(it[5]) for it in part]),
-              _stream())
+              _arr(C.c_void_p, [_p(it[6]) for it in part]),
+              _arr(C.c_int64, [0 if it[6] is None else it[6].shape[0] for it in part]), _stream())
 
 
 def _linear_bwd_x_group(bf16, items):

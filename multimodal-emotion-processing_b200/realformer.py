@@ -28,19 +28,16 @@ class Unify_Dimension_Conv1d(nn.Module):
 
     def forward(self, l, v, a, pos=(None, None, None)):
         bf = is_bf16()
-        if bf:      # the bf16 shadows of all projection weights in one cast launch
-            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
-                                   for m in (self.linguistic, self.visual, self.acoustic)])
+        convs = (self.linguistic, self.visual, self.acoustic)
+        if not (self.training and self.drop.p > 0):
+            # all three projections (+ fused position tables) as one group (group_ops.project)
+            from .group_ops import project
+            return tuple(project([l, v, a], [c.weight for c in convs], None, list(pos), bf16=bf))
         out = []
-        for x, conv, p in ((l, self.linguistic, pos[0]), (v, self.visual, pos[1]),
-                           (a, self.acoustic, pos[2])):
-            if self.training and self.drop.p > 0 and p is not None:
-                # reference order: drop(conv(x)) THEN + position
-                y = ops.dropout(ops.linear(x, conv.weight, bf16=bf), self.drop.p, True)
+        for x, conv, p in zip((l, v, a), convs, pos):
+            y = ops.dropout(ops.linear(x, conv.weight, bf16=bf), self.drop.p, True)
+            if p is not None:           # reference order: drop(conv(x)) THEN + position
                 y = y + as_act(p)[None, : y.shape[1]]
-            else:
-                y = ops.dropout(ops.linear(x, conv.weight, pos=p, bf16=bf), self.drop.p,
-                                self.training)
             out.append(y)
         return tuple(out)
 

@@ -25,13 +25,11 @@ class Unify_Dimension(nn.Module):
         self.norm1 = nn.LayerNorm(dim)
 
     def forward(self, l, v, a):
-        bf = is_bf16()
-        if bf:      # the bf16 shadows of all projection weights in one cast launch
-            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
-                                   for m in (self.linguistic, self.visual, self.acoustic)])
+        from .group_ops import project
         w, b = self.norm1.weight, self.norm1.bias
-        return tuple(ops.add_ln(None, ops.linear(x, lin.weight, bf16=bf), None, w, b)
-                     for x, lin in ((l, self.linguistic), (v, self.visual), (a, self.acoustic)))
+        ys = project([l, v, a], [self.linguistic.weight, self.visual.weight, self.acoustic.weight],
+                     bf16=is_bf16())
+        return tuple(ops.add_ln(None, y, None, w, b) for y in ys)
 
 
 class Attention_Block(LiteAttentionBlock):

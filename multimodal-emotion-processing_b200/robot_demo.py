@@ -25,17 +25,17 @@ class Unify_Dimension_Conv1d(nn.Module):
 
     def forward(self, l, v_256, v_512, v_1024, a):
         bf = is_bf16()
-        if bf:      # the bf16 shadows of all projection weights in one cast launch
-            ops.shadow_bf16_block([[m.weight.squeeze(-1) if m.weight.dim() == 3 else m.weight]
-                                   for m in (self.linguistic, self.visual_1024, self.visual_512, self.visual_256, self.acoustic)])
-
-        def proj(x, conv):
-            return ops.dropout(ops.linear(x, conv.weight, conv.bias, bf16=bf), self.drop.p,
-                               self.training)
-
-        v = torch.cat((proj(v_256, self.visual_256), proj(v_512, self.visual_512),
-                       proj(v_1024, self.visual_1024)), 2)
-        return proj(l, self.linguistic), v, proj(a, self.acoustic)
+        convs = (self.linguistic, self.visual_256, self.visual_512, self.visual_1024, self.acoustic)
+        xs = (l, v_256, v_512, v_1024, a)
+        if not (self.training and self.drop.p > 0):
+            from .group_ops import project
+            yl, y256, y512, y1024, ya = project(list(xs), [c.weight for c in convs],
+                                                [c.bias for c in convs], bf16=bf)
+        else:
+            yl, y256, y512, y1024, ya = (
+                ops.dropout(ops.linear(x, c.weight, c.bias, bf16=bf), self.drop.p, True)
+                for x, c in zip(xs, convs))
+        return yl, torch.cat((y256, y512, y1024), 2), ya
 
 
 class Position_Embedding(nn.Module):

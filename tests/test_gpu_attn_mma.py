@@ -69,6 +69,9 @@ SETS = [
     # cfg 5 (hd 32) and ragged lengths
     [(2, 6, 25, 100, 32, False), (2, 6, 100, 25, 32, False), (1, 6, 100, 100, 32, False)],
     [(1, 3, 7, 9, 16, False), (2, 2, 33, 65, 64, False), (1, 2, 130, 70, 64, True)],
+    # cfg 3 composite shape (hd 64, L 256): K / V staged one key block at a time in the backward;
+    # the small problem rides along in the same (blocked) launch
+    [(1, 4, 256, 256, 64, False), (1, 2, 40, 72, 64, False)],
 ]
 
 
