@@ -386,6 +386,16 @@ int mmemo_assemble_batch_f32(const float* flat, const int64_t* row_start, const 
                              float* out, float* mask, int64_t N, int64_t m_len, int64_t D,
                              int mode, int do_scrub, float scrub_value, mmemo_stream_t stream);
 
+/* cmu-mosei/run.py:104-151 (masking, the non-BERT branch used by its data_loader :169-180):
+ * out rows 0,1,2 = column-wise max, min, mean over ALL rows of the sample (after the NaN/Inf
+ * scrub), rows 3.. = m_len-3 body rows: view 0 = the first ones, view 1 = the last ones (identical
+ * to view 0 when the sample has fewer than m_len-3 rows: such samples have ONE view, zero-padded,
+ * mask = 1 on their n_rows+3 rows).  n_rows[n] == 0 -> all-zero sample and mask. */
+int mmemo_assemble_stats_batch_f32(const float* flat, const int64_t* row_start,
+                                   const int64_t* n_rows, float* out, float* mask, int64_t N,
+                                   int64_t m_len, int64_t D, int view, int do_scrub,
+                                   float scrub_value, mmemo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -80,3 +80,34 @@ class RaggedBatch:
             out = out.view(*lead_shape, m_len, D)
             mask = mask.view(*lead_shape, m_len)
         return out, mask
+
+    # ---- cmu-mosei/run.py:104-151: statistics rows + head / tail views -----------------------------
+    def two_views(self, m_len: int) -> torch.Tensor:
+        """bool (N,): samples long enough (>= m_len - 3 rows) to yield a head AND a tail view
+        (cmu-mosei/run.py:137; the loader emits two training samples when the current sentence's
+        text does, :181-188)."""
+        return self.n_rows >= (m_len - 3)
+
+    def assemble_stats(self, m_len: int, view: str = "head", scrub: Optional[float] = None,
+                       lead_shape: Optional[Sequence[int]] = None):
+        """cmu-mosei ``masking`` (non-BERT branch): rows 0-2 = column-wise max / min / mean over the
+        whole sample, then ``m_len - 3`` body rows — ``view="head"``: the first ones (``feat[0]`` of
+        the reference), ``view="tail"``: the last ones (``feat[-1]``; equals the head view for
+        samples with a single view).  ``scrub=-71`` for the acoustic features (is_audio=True)."""
+        if view not in ("head", "tail"):
+            raise ValueError("view must be 'head' or 'tail'")
+        if m_len < 3:
+            raise ValueError("m_len must be >= 3 (three statistics rows)")
+        if not self.flat.is_cuda:
+            raise RuntimeError("RaggedBatch.assemble_stats runs on the GPU: call .cuda() first "
+                               "(mmemo_b200 has no CPU fallback)")
+        N, D = len(self), self.flat.shape[1]
+        out = torch.empty(N, m_len, D, dtype=torch.float32, device=self.flat.device)
+        mask = torch.empty(N, m_len, dtype=torch.float32, device=self.flat.device)
+        ops._call("mmemo_assemble_stats_batch_f32", self.flat.data_ptr(), self.row_start.data_ptr(),
+                  self.n_rows.data_ptr(), out.data_ptr(), mask.data_ptr(), N, m_len, D,
+                  int(view == "tail"), int(scrub is not None), float(scrub or 0.0), ops._stream())
+        if lead_shape is not None:
+            out = out.view(*lead_shape, m_len, D)
+            mask = mask.view(*lead_shape, m_len)
+        return out, mask

@@ -59,7 +59,65 @@ assemble_kernel(const float* __restrict__ flat, const int64_t* __restrict__ row_
   }
 }
 
+// cmu-mosei/run.py:104-151 (masking, non-BERT branch): every sample is prefixed by three
+// STATISTICS rows (column-wise max, min, mean over ALL its rows, after the audio NaN/Inf scrub) and
+// followed by m_len-3 body rows.  A sequence with T >= m_len-3 rows yields two views: the head
+// (rows 0 .. m_len-4) and the tail (the last m_len-3 rows); a shorter one yields one zero-padded
+// view with mask = 1 on its T+3 rows.  Thread = feature column: the T rows of a column are walked
+// once for the statistics (coalesced across the columns), then the body rows are copied.
+__global__ void __launch_bounds__(128)
+assemble_stats_kernel(const float* __restrict__ flat, const int64_t* __restrict__ row_start,
+                      const int64_t* __restrict__ n_rows, float* __restrict__ out,
+                      float* __restrict__ mask, int m_len, int D, int view, int do_scrub,
+                      float scrub_value) {
+  const int n = blockIdx.y;
+  const int64_t T = n_rows[n];
+  const int64_t start = row_start[n];
+  const int body = m_len - 3;
+  const bool two = T >= body;
+  if (mask && blockIdx.x == 0)
+    for (int t = threadIdx.x; t < m_len; t += 128)
+      mask[(int64_t)n * m_len + t] = (T > 0 && (two || t < T + 3)) ? 1.f : 0.f;
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= D) return;
+  float* dst = out + (int64_t)n * m_len * D + c;
+  if (T <= 0) {                       // 'no_name' slot (cmu-mosei/run.py:162-168): all zeros
+    for (int t = 0; t < m_len; ++t) dst[(int64_t)t * D] = 0.f;
+    return;
+  }
+  const float* src = flat + start * D + c;
+  float mx = -INFINITY, mn = INFINITY;
+  double sum = 0.0;
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = scrub(src[t * D], do_scrub, scrub_value);
+    mx = fmaxf(mx, v);
+    mn = fminf(mn, v);
+    sum += (double)v;
+  }
+  if (m_len > 0) dst[0] = mx;
+  if (m_len > 1) dst[(int64_t)D] = mn;
+  if (m_len > 2) dst[2 * (int64_t)D] = (float)(sum / (double)T);
+  const int64_t first = (view == 1 && two) ? T - body : 0;
+  for (int r = 0; r < body; ++r) {
+    const int64_t t = first + r;
+    dst[(int64_t)(3 + r) * D] = t < T ? scrub(src[t * D], do_scrub, scrub_value) : 0.f;
+  }
+}
+
 }  // namespace
+
+extern "C" int mmemo_assemble_stats_batch_f32(const float* flat, const int64_t* row_start,
+                                              const int64_t* n_rows, float* out, float* mask,
+                                              int64_t N, int64_t m_len, int64_t D, int view,
+                                              int do_scrub, float scrub_value, mmemo_stream_t s) {
+  if (N <= 0 || m_len <= 0 || D <= 0) return N == 0 || m_len == 0 || D == 0 ? MMEMO_OK : MMEMO_ERR_ARG;
+  MM_REQUIRE(flat && row_start && n_rows && out && (view == 0 || view == 1) && m_len >= 3);
+  if (N > 65535 || m_len > (1 << 20) || D > (1 << 20)) return MMEMO_ERR_SHAPE;
+  assemble_stats_kernel<<<dim3((unsigned)cdiv(D, 128), (unsigned)N), 128, 0, mm_stream(s)>>>(
+      flat, row_start, n_rows, out, mask, (int)m_len, (int)D, view, do_scrub, scrub_value);
+  MM_LAUNCH_OK();
+  return MMEMO_OK;
+}
 
 extern "C" int mmemo_assemble_batch_f32(const float* flat, const int64_t* row_start,
                                         const int64_t* n_rows, float* out, float* mask, int64_t N,

@@ -160,10 +160,11 @@ __device__ __forceinline__ const Prob& locate(const Table& T, int& local) {
 
 // stage `rows` rows of a (.., ld) bf16 matrix (head slice: HD columns starting at col0) into a
 // swizzled tile; rows >= n_rows are zero-filled
-template <int HD, int NT>
+template <int HD>
 __device__ __forceinline__ void stage(uint32_t dst, const bf16* src, int ld, int n_rows,
                                       int rows_padded) {
   constexpr int CPR = HD / 8;
+  const int NT = blockDim.x;
   for (int i = threadIdx.x; i < rows_padded * CPR; i += NT) {
     const int r = i / CPR, ch = i - r * CPR;
     const bool ok = r < n_rows;
@@ -195,10 +196,10 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
 
   pdl_wait();
   pdl_trigger();
-  stage<HD, FWD_WARPS * 32>(sQ, P.q + ((size_t)b * Lq + q0) * P.ldq + h * HD, P.ldq,
+  stage<HD>(sQ, P.q + ((size_t)b * Lq + q0) * P.ldq + h * HD, P.ldq,
                             min(FWD_ROWS, Lq - q0), FWD_ROWS);
-  stage<HD, FWD_WARPS * 32>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
-  if (!same_kv) stage<HD, FWD_WARPS * 32>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
+  stage<HD>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
+  if (!same_kv) stage<HD>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
   for (int j = threadIdx.x; j < LkP; j += FWD_WARPS * 32)
     sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
   cp_commit_wait();
@@ -345,7 +346,7 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
 template <int HD, int KB>
 __global__ void __launch_bounds__(BWD_WARPS * 32)
 resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
-  constexpr int NT = BWD_WARPS * 32;
+  const int NT = blockDim.x, nwarps = blockDim.x >> 5;   // 2..8 warps, chosen per launch (host)
   constexpr int NG = KB / 32;              // 32-key groups per block
   extern __shared__ __align__(128) uint8_t smem[];
   int local;
@@ -373,11 +374,11 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
 
   pdl_wait();
   pdl_trigger();
-  stage<HD, NT>(sQ, P.q + (size_t)b * Lq * P.ldq + h * HD, P.ldq, Lq, LqP);
-  stage<HD, NT>(sdO, P.d_o + (size_t)b * Lq * P.lddo + h * HD, P.lddo, Lq, LqP);
+  stage<HD>(sQ, P.q + (size_t)b * Lq * P.ldq + h * HD, P.ldq, Lq, LqP);
+  stage<HD>(sdO, P.d_o + (size_t)b * Lq * P.lddo + h * HD, P.lddo, Lq, LqP);
   if (!kv_blocked) {
-    stage<HD, NT>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
-    if (!same_kv) stage<HD, NT>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
+    stage<HD>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
+    if (!same_kv) stage<HD>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
   }
   for (int j = threadIdx.x; j < LkP; j += NT)
     sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
@@ -417,14 +418,14 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   for (int kb = 0; kb < Lk; kb += KB) {
     const int kofs = kv_blocked ? kb : 0;            // first key held in the K / V tiles
     if (kv_blocked) {       // (the previous block's readers passed the barrier ending the loop body)
-      stage<HD, NT>(sK, P.k + ((size_t)b * Lk + kb) * P.ldk + h * HD, P.ldk, min(KB, Lk - kb), KB);
+      stage<HD>(sK, P.k + ((size_t)b * Lk + kb) * P.ldk + h * HD, P.ldk, min(KB, Lk - kb), KB);
       if (!same_kv)
-        stage<HD, NT>(sV, P.v + ((size_t)b * Lk + kb) * P.ldv + h * HD, P.ldv, min(KB, Lk - kb), KB);
+        stage<HD>(sV, P.v + ((size_t)b * Lk + kb) * P.ldv + h * HD, P.ldv, min(KB, Lk - kb), KB);
       cp_commit_wait();
       __syncthreads();
     }
     // ================= phase A: one warp per 16-row tile ========================================
-    for (int rt = warp; rt < n_rt; rt += BWD_WARPS) {
+    for (int rt = warp; rt < n_rt; rt += nwarps) {
       const int rowA = rt * 16 + g, rowB = rowA + 8;
       const bool okA = rowA < Lq, okB = rowB < Lq;
       uint32_t doa[HD / 16][4];
@@ -564,7 +565,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     // two are summed here: a task then owns 16 keys and runs both products into one accumulator.
     const bool fuse_kv = (P.dk == P.dv);
     const int n_tasks = fuse_kv ? (KB / 16) : (KB / 16) * 2;
-    for (int task = warp; task < n_tasks; task += BWD_WARPS) {
+    for (int task = warp; task < n_tasks; task += nwarps) {
       const int ks = fuse_kv ? task : (task >> 1);
       if (kb + 16 * ks >= Lk) continue;
       float acc[HD / 8][4];
@@ -627,8 +628,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     __syncthreads();
     if (threadIdx.x == 0) {
       float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < BWD_WARPS; ++w) s += red[w];
+      for (int w = 0; w < nwarps; ++w) s += red[w];
       atomicAdd(P.dc, s);
     }
   }
@@ -724,20 +724,30 @@ int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
   return MMEMO_OK;
 }
 
-int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
-  if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
+namespace {
+// Warps per backward CTA: phase A hands one 16-row tile to a warp per round, so the CTA is sized
+// to the number of tiles split evenly over the rounds (18 tiles -> 3 rounds of 6 warps instead of
+// 8 + 8 + 2 on eight; 4 tiles -> 4 warps, twice as many CTAs per SM) - idle warps only add
+// barrier stalls (ncu: 7 of 10 issue slots stalled on the barrier with 4 of 8 warps working).
+int bwd_warps(int64_t Lq) {
+  const int n_rt = (int)cdiv(Lq, 16);
+  const int rounds = (int)cdiv(n_rt, BWD_WARPS);
+  int w = (int)cdiv(n_rt, rounds);
+  return w < 2 ? 2 : w;
+}
+
+int bwd_launch(const mmemo_attn_problem* const* ps, int n, int warps, cudaStream_t st) {
   static thread_local Table T;
   T.n = n;
-  const int hd = (int)ps[0].hd;
+  const int hd = (int)ps[0]->hd;
   size_t smem64 = 0, smem32 = 0, full32 = 0;
   int ctas = 0;
   for (int i = 0; i < n; ++i) {
-    if (ps[i].hd != hd || !resattn_mma_supported(ps[i], true)) return MMEMO_ERR_SHAPE;
-    fill(T.p[i], ps[i]);
+    fill(T.p[i], *ps[i]);
     T.p[i].cta_start = ctas;
-    ctas += (int)(ps[i].B * ps[i].H);
-    const bool same = ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv;
-    const size_t f32_ = bwd_smem(hd, 32, (int)ps[i].Lq, (int)ps[i].Lk, same, false);
+    ctas += (int)(ps[i]->B * ps[i]->H);
+    const bool same = ps[i]->k == ps[i]->v && ps[i]->ldk == ps[i]->ldv;
+    const size_t f32_ = bwd_smem(hd, 32, (int)ps[i]->Lq, (int)ps[i]->Lk, same, false);
     full32 = f32_ > full32 ? f32_ : full32;
   }
   // K and V whole in shared memory when that fits (one load per CTA); otherwise one key block at
@@ -745,17 +755,17 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
   const bool blocked = full32 > SMEM_MAX;
   T.kv_blocked = blocked ? 1 : 0;
   for (int i = 0; i < n; ++i) {
-    const bool same = ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv;
-    const size_t s64 = bwd_smem(hd, 64, (int)ps[i].Lq, (int)ps[i].Lk, same, blocked);
-    const size_t s32 = bwd_smem(hd, 32, (int)ps[i].Lq, (int)ps[i].Lk, same, blocked);
+    const bool same = ps[i]->k == ps[i]->v && ps[i]->ldk == ps[i]->ldv;
+    const size_t s64 = bwd_smem(hd, 64, (int)ps[i]->Lq, (int)ps[i]->Lk, same, blocked);
+    const size_t s32 = bwd_smem(hd, 32, (int)ps[i]->Lq, (int)ps[i]->Lk, same, blocked);
     smem64 = s64 > smem64 ? s64 : smem64;
     smem32 = s32 > smem32 ? s32 : smem32;
   }
   T.total = ctas;
   T.inv_sqrt = (float)(1.0 / sqrt((double)hd));
-  // Key block: the 64-key instantiation needs ~155 registers (one 8-warp CTA per SM), the 32-key
-  // one ~100 (two CTAs per SM when shared memory allows): prefer 32 whenever two CTAs fit, 64
-  // when only one CTA fits either way (fewer block iterations), 32 when 64 does not fit at all.
+  // Key block: the 64-key instantiation needs ~155 registers, the 32-key one ~110: prefer 32
+  // whenever two or more CTAs fit (measured 2x faster on cfg 1a and cfg 4), 64 when only one CTA
+  // fits either way (fewer block iterations), 32 when 64 does not fit at all.
   // MMEMO_ATTN_KB=32|64 overrides (experiments).
   bool kb64 = smem32 > 110 * 1024 && smem64 <= SMEM_MAX;
   if (const char* e = getenv("MMEMO_ATTN_KB")) {
@@ -767,7 +777,7 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
     MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_bwd_kernel<HD, KBK>,                              \
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)));     \
     MM_CUDA_OK(mm_launch(resattn_mma_bwd_kernel<HD, KBK>, dim3((unsigned)ctas),                   \
-                         dim3(BWD_WARPS * 32), SM, st, T));                                       \
+                         dim3((unsigned)(warps * 32)), SM, st, T));                               \
   }
   if (kb64) {
     if (hd == 16) MM_BWD(16, 64, smem64) else if (hd == 32) MM_BWD(32, 64, smem64)
@@ -777,5 +787,31 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
     else MM_BWD(64, 32, smem32)
   }
 #undef MM_BWD
+  return MMEMO_OK;
+}
+}  // namespace
+
+int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
+  if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
+  const int hd = (int)ps[0].hd;
+  for (int i = 0; i < n; ++i)
+    if (ps[i].hd != hd || !resattn_mma_supported(ps[i], true)) return MMEMO_ERR_SHAPE;
+  int fixed = 0;
+  if (const char* e = getenv("MMEMO_ATTN_WARPS")) fixed = atoi(e);      // experiments
+  // one launch per CTA size (all chains of realformer / robot_demo share one; Ren-MME's three
+  // query lengths give three)
+  const mmemo_attn_problem* sel[MAXP];
+  bool done[MAXP] = {};
+  for (int i = 0; i < n; ++i) {
+    if (done[i]) continue;
+    const int w = (fixed >= 2 && fixed <= BWD_WARPS) ? fixed : bwd_warps(ps[i].Lq);
+    int m = 0;
+    for (int j = i; j < n; ++j) {
+      const int wj = (fixed >= 2 && fixed <= BWD_WARPS) ? fixed : bwd_warps(ps[j].Lq);
+      if (!done[j] && wj == w) { sel[m++] = &ps[j]; done[j] = true; }
+    }
+    const int rc = bwd_launch(sel, m, w, st);
+    if (rc) return rc;
+  }
   return MMEMO_OK;
 }

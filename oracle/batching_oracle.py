@@ -50,3 +50,29 @@ def head(feat, m_len):
     pad = m_len - len(feat)
     return (np.concatenate([feat, np.zeros((pad, feat.shape[1]))], axis=0),
             np.concatenate((np.ones(len(feat)), np.zeros(pad))))
+
+
+def mosei_masking(m, m_len, is_audio=False):
+    """cmu-mosei/run.py:104-151, the ``is_bert=False`` branch (the only one its data_loader calls,
+    :169-180): NaN/Inf -> -71 for audio; three statistics rows (column max / min / mean over ALL
+    rows) in front; >= m_len-3 rows -> two views (head ``m[:m_len-3]``, tail ``m[len-m_len+3:]``)
+    with all-ones masks, else one zero-padded view with mask = 1 on len+3 rows.
+    Returns (list of views, list of masks) like the reference."""
+    m = np.array(m, dtype=np.float64, copy=True)
+    feat, feat_mask = [], []
+    if is_audio:
+        for i in range(len(m)):
+            for j in range(len(m[i])):
+                if math.isinf(m[i][j]) or math.isnan(m[i][j]):
+                    m[i][j] = -71.
+    stats = np.stack([m.max(axis=0), m.min(axis=0), m.mean(axis=0)], axis=0)
+    if len(m) >= m_len - 3:
+        for body in (m[:m_len - 3], m[len(m) - m_len + 3:]):
+            feat.append(np.concatenate((stats, body), axis=0))
+            feat_mask.append(np.ones(m_len))
+    else:
+        mm = np.concatenate((stats, m), axis=0)
+        mm = np.concatenate([mm, np.zeros([m_len] + list(mm.shape[1:]))], axis=0)[:m_len, ...]
+        feat.append(mm)
+        feat_mask.append(np.concatenate((np.ones(len(m) + 3), np.zeros(m_len - len(m) - 3))))
+    return feat, feat_mask

@@ -48,8 +48,13 @@ def _is_const_assign(node: ast.AST) -> bool:
     return isinstance(v, (int, float))
 
 
-def load(which: str, device: str = "cpu", **overrides) -> SimpleNamespace:
+def load(which: str, device: str = "cpu", functions=(), inject=None, **overrides) -> SimpleNamespace:
     """Return a namespace holding the reference classes/constants of one script.
+
+    ``functions``: extra top-level ``def``s to execute as they are (e.g. the training loops
+    ``train`` / ``valid``); ``inject``: names placed in the namespace before anything runs (what the
+    script would have imported or built at module level: ``tqdm``, a ``torch`` stand-in on boxes
+    without CUDA, ...).
 
     ``overrides`` replace module-level constants *before* class construction (the classes read
     ``DROP``, ``FFN``, ``L_DIM`` ... from module globals at construction/forward time,
@@ -66,12 +71,14 @@ def load(which: str, device: str = "cpu", **overrides) -> SimpleNamespace:
     for node in tree.body:
         if isinstance(node, ast.ClassDef):
             keep.append(node)
-        elif isinstance(node, ast.FunctionDef) and node.name in _LOSS_FUNCS:
+        elif isinstance(node, ast.FunctionDef) and (node.name in _LOSS_FUNCS
+                                                    or node.name in functions):
             keep.append(node)
         elif _is_const_assign(node):
             keep.append(node)
     ns = {"np": np, "torch": torch, "nn": nn, "F": F, "math": math,
           "device": torch.device(device)}
+    ns.update(inject or {})
     # constants first so that overrides win, then classes
     consts = [n for n in keep if isinstance(n, ast.Assign)]
     others = [n for n in keep if not isinstance(n, ast.Assign)]

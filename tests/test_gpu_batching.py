@@ -71,3 +71,29 @@ def test_assemble_windows_feed_the_model():
     with torch.no_grad():
         out = model(l, v, a, lm, vm, am)
     assert out.shape == (B, P, 6) and bool(torch.isfinite(out).all())
+
+
+@pytest.mark.parametrize("D,m_len,audio", [(300, 20, False), (35, 100, False), (74, 200, True)])
+def test_assemble_stats_equals_cmu_mosei_masking(D, m_len, audio):
+    """cmu-mosei/run.py:104-151: three statistics rows (max / min / mean over the whole sample) +
+    head / tail views.  max, min and the body rows are bit-exact; the mean is a float64 sum
+    rounded to float32 on both sides (numpy sums pairwise, the kernel sequentially: <= 1 ulp)."""
+    lens = [0, 1, 5, m_len - 4, m_len - 3, m_len - 2, m_len + 40, 3 * m_len, 2]
+    seqs = _ragged(D + m_len, D, lens, bad=audio)
+    rb = RaggedBatch.pack(seqs, dim=D)
+    two = rb.two_views(m_len).tolist()
+    assert two == [len(a) >= m_len - 3 for a in seqs]
+    dev = rb.cuda()
+    for view in ("head", "tail"):
+        x, mask = dev.assemble_stats(m_len, view, scrub=-71.0 if audio else None)
+        x, mask = x.cpu(), mask.cpu()
+        for i, a in enumerate(seqs):
+            if len(a) == 0:
+                assert float(x[i].abs().sum()) == 0.0 and float(mask[i].sum()) == 0.0
+                continue
+            f, m = BO.mosei_masking(a.astype(np.float64), m_len, is_audio=audio)
+            ef = torch.from_numpy(f[-1] if view == "tail" else f[0]).float()
+            em = torch.from_numpy(m[-1] if view == "tail" else m[0]).float()
+            assert torch.equal(mask[i], em), (i, view)
+            assert torch.equal(x[i, :2], ef[:2]) and torch.equal(x[i, 3:], ef[3:]), (i, view)
+            assert torch.allclose(x[i, 2], ef[2], rtol=2e-7, atol=1e-9), (i, view)

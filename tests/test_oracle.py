@@ -167,6 +167,23 @@ def test_batching_oracle_stride_matches_reference_features(tmp_path):
     assert np.array_equal(f, ref_f) and np.array_equal(mask, ref_mask)
 
 
+@needs_ref
+def test_batching_oracle_mosei_statistics_rows_match_reference_masking():
+    """cmu-mosei/run.py:104-151 (is_bert=False): statistics rows + head / tail views; audio scrub."""
+    from oracle import batching_oracle as BO
+    ns = refload.load("mosei")
+    for is_audio, D, m_len in ((False, 35, 100), (True, 74, 200), (False, 300, 20)):
+        for a in _ragged(7 + D, D, [1, 5, m_len - 4, m_len - 3, m_len - 2, m_len + 40, 3 * m_len]):
+            a = a.astype(np.float64)
+            if not is_audio:        # only the acoustic stream is scrubbed; keep the others finite
+                a = np.nan_to_num(a, nan=0.25, posinf=2.0, neginf=-2.0)
+            ref_f, ref_m = ns.masking(a.copy(), m_len, is_bert=False, is_audio=is_audio)
+            f, m = BO.mosei_masking(a.copy(), m_len, is_audio=is_audio)
+            assert len(f) == len(ref_f) == (2 if len(a) >= m_len - 3 else 1)
+            for x, y in zip(f + m, ref_f + ref_m):
+                assert np.array_equal(x, y)
+
+
 def test_batching_oracle_literal_cases():
     """Runs everywhere (no reference tree needed): hand-checked small cases."""
     from oracle import batching_oracle as BO
@@ -182,6 +199,14 @@ def test_batching_oracle_literal_cases():
     assert f.tolist() == [[0, 0], [0, 0]] and mask.tolist() == [0, 0]
     f, mask = BO.head(np.arange(8, dtype=np.float32).reshape(4, 2), 3)
     assert f.tolist() == [[0, 1], [2, 3], [4, 5]] and mask.tolist() == [1, 1, 1]
+    # cmu-mosei statistics rows: 4 rows, m_len 5 -> two views of 3 stats + 2 body rows
+    a = np.array([[1., 8.], [2., 6.], [3., 4.], [6., 2.]])
+    f, mask = BO.mosei_masking(a, 5)
+    assert f[0].tolist() == [[6, 8], [1, 2], [3, 5], [1, 8], [2, 6]]
+    assert f[1].tolist() == [[6, 8], [1, 2], [3, 5], [3, 4], [6, 2]] and mask[1].tolist() == [1] * 5
+    f, mask = BO.mosei_masking(a[:1], 6)
+    assert f[0].tolist() == [[1, 8], [1, 8], [1, 8], [1, 8], [0, 0], [0, 0]]
+    assert len(f) == 1 and mask[0].tolist() == [1, 1, 1, 1, 0, 0]
 
 
 def test_ragged_batch_pack_host_side():
