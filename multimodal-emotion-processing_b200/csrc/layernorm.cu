@@ -64,8 +64,19 @@ template <> struct Vec<bf16> {
 // ---------------------------------------------------------------------------------------------
 // vector kernels: lane owns chunks c = lane + 32*i (i < NCH) of V consecutive columns
 // ---------------------------------------------------------------------------------------------
-// (bid, nblk): this CTA's index / the number of CTAs that share the rows of this problem
-template <typename T, int NCH>
+// sum over the LPR-lane group a row lives in (LPR = 32: the whole warp)
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// (bid, nblk): this CTA's index / the number of CTAs that share the rows of this problem.
+// LPR = lanes per row: narrow rows (d <= 128 bf16 / 64 fp32) put 2 or 4 rows in a warp so that the
+// lanes are not 60 % idle (d = 96: 12 of 32 lanes busy with one row per warp).  LPR < 32 needs
+// NCH == 1.
+template <typename T, int NCH, int LPR = 32>
 __device__ __forceinline__ void
 ln_fwd_vec_body(const T* __restrict__ res, int64_t ldres, const T* __restrict__ x, int64_t ldx,
                 const float* __restrict__ gate, const float* __restrict__ gamma,
@@ -73,28 +84,32 @@ ln_fwd_vec_body(const T* __restrict__ res, int64_t ldres, const T* __restrict__ 
                 float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t M, int d,
                 float eps, int relu, unsigned bid, unsigned nblk) {
   constexpr int V = Vec<T>::N;
+  constexpr int RPW = 32 / LPR;                 // rows per warp
   const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
   const float g = gate ? gate[0] : 1.f;
   const int nchunk = d / V;
   float gm[NCH][V], bt[NCH][V];
 #pragma unroll
   for (int i = 0; i < NCH; ++i)
-    if (lane + 32 * i < nchunk) {
-      Vec<float>::load(gamma + (lane + 32 * i) * V, gm[i]);
-      Vec<float>::load(beta + (lane + 32 * i) * V, bt[i]);
+    if (l + LPR * i < nchunk) {
+      Vec<float>::load(gamma + (l + LPR * i) * V, gm[i]);
+      Vec<float>::load(beta + (l + LPR * i) * V, bt[i]);
       if (V == 8) {
-        Vec<float>::load(gamma + (lane + 32 * i) * V + 4, gm[i] + 4);
-        Vec<float>::load(beta + (lane + 32 * i) * V + 4, bt[i] + 4);
+        Vec<float>::load(gamma + (l + LPR * i) * V + 4, gm[i] + 4);
+        Vec<float>::load(beta + (l + LPR * i) * V + 4, bt[i] + 4);
       }
     }
-  for (int64_t row = (int64_t)bid * LN_WARPS + (threadIdx.x >> 5); row < M;
-       row += (int64_t)nblk * LN_WARPS) {
+  for (int64_t row0 = ((int64_t)bid * LN_WARPS + (threadIdx.x >> 5)) * RPW; row0 < M;
+       row0 += (int64_t)nblk * LN_WARPS * RPW) {
+  const int64_t row = row0 + sub;
+  const bool live = row < M;
   float z[NCH][V];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunk) {
+    const int c = l + LPR * i;
+    if (live && c < nchunk) {
       float xv[V];
       Vec<T>::load(x + row * ldx + c * V, xv);
       if (res) {
@@ -110,22 +125,22 @@ ln_fwd_vec_body(const T* __restrict__ res, int64_t ldres, const T* __restrict__ 
       for (int j = 0; j < V; ++j) sum += z[i][j];
     }
   }
-  const float mean = warp_sum(sum) / (float)d;
+  const float mean = group_sum<LPR>(sum) / (float)d;
   float var = 0.f;
 #pragma unroll
   for (int i = 0; i < NCH; ++i)
-    if (lane + 32 * i < nchunk) {
+    if (live && l + LPR * i < nchunk) {
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         const float t = z[i][j] - mean;
         var = fmaf(t, t, var);
       }
     }
-  const float rstd = rsqrtf(warp_sum(var) / (float)d + eps);
+  const float rstd = rsqrtf(group_sum<LPR>(var) / (float)d + eps);
 #pragma unroll
   for (int i = 0; i < NCH; ++i) {
-    const int c = lane + 32 * i;
-    if (c < nchunk) {
+    const int c = l + LPR * i;
+    if (live && c < nchunk) {
       float o[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
@@ -135,7 +150,7 @@ ln_fwd_vec_body(const T* __restrict__ res, int64_t ldres, const T* __restrict__ 
       Vec<T>::store(y + row * ldy + c * V, o);
     }
   }
-  if (lane == 0) {
+  if (l == 0 && live) {
     if (mean_out) mean_out[row] = mean;
     if (rstd_out) rstd_out[row] = rstd;
   }
@@ -168,15 +183,15 @@ struct LnProb {
 };
 struct LnTable { LnProb p[LN_MAXP]; };
 
-template <typename T, int NCH>
+template <typename T, int NCH, int LPR>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_vec_grouped(const __grid_constant__ LnTable tb, int d, float eps, int relu) {
   const LnProb& a = tb.p[blockIdx.y];
   pdl_wait();
   pdl_trigger();
-  ln_fwd_vec_body<T, NCH>(static_cast<const T*>(a.res), d, static_cast<const T*>(a.x), d, a.gate,
-                          a.gamma, a.beta, static_cast<T*>(a.y), d, a.mean, a.rstd, a.M, d, eps,
-                          relu, blockIdx.x, gridDim.x);
+  ln_fwd_vec_body<T, NCH, LPR>(static_cast<const T*>(a.res), d, static_cast<const T*>(a.x), d,
+                               a.gate, a.gamma, a.beta, static_cast<T*>(a.y), d, a.mean, a.rstd,
+                               a.M, d, eps, relu, blockIdx.x, gridDim.x);
 }
 
 template <typename T, int NCH>
@@ -267,7 +282,9 @@ ln_bwd_row_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res
 // memory and added to global memory once per CTA.
 constexpr int LNB_WARPS = 16;
 
-template <typename T, int NCH, bool DXSUM>
+// LPR = lanes per row (see ln_fwd_vec_body); LPR < 32 needs NCH == 1 and a staging buffer of
+// LNB_WARPS * (32 / LPR) rows.
+template <typename T, int NCH, bool DXSUM, int LPR = 32>
 __device__ __forceinline__ void
 ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ res, int64_t ldres,
                   const T* __restrict__ x, int64_t ldx, const float* __restrict__ gate,
@@ -281,7 +298,9 @@ ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
   float* sg = ln_sm;
   float* stage = ln_sm + d;
   __shared__ float dgs[LNB_WARPS];
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / LPR, l = lane % LPR;
   for (int i = threadIdx.x; i < d; i += LNB_WARPS * 32) sg[i] = gamma[i];
   __syncthreads();
   const float g = gate ? gate[0] : 1.f;
@@ -298,13 +317,13 @@ ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
     }
   // the row loop is software-pipelined: the 16-byte vectors of the next row are requested (and
   // held packed) before the current row is reduced, so every warp keeps two rows of loads in flight
-  const int64_t rstep = (int64_t)nblk * LNB_WARPS;
-  int64_t row = (int64_t)bid * LNB_WARPS + warp;
+  const int64_t rstep = (int64_t)nblk * LNB_WARPS * RPW;
+  int64_t row = ((int64_t)bid * LNB_WARPS + warp) * RPW + sub;
   uint4 cur[NCH][3], nxt[NCH][3];
   auto fetch = [&](int64_t r, uint4 (&buf)[NCH][3]) {
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
+      const int c = l + LPR * i;
       if (c < nchunk) {
         buf[i][0] = *reinterpret_cast<const uint4*>(x + r * ldx + c * V);
         buf[i][1] = *reinterpret_cast<const uint4*>(dy + r * lddy + c * V);
@@ -313,14 +332,15 @@ ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
     }
   };
   if (row < M) fetch(row, cur);
-  for (; row < M; row += rstep) {
+  for (; row - sub < M; row += rstep) {            // (row - sub: the same trip count for the whole warp)
+    const bool live = row < M;
     if (row + rstep < M) fetch(row + rstep, nxt);
-    const float mean = mean_in[row], rstd = rstd_in[row];
+    const float mean = live ? mean_in[row] : 0.f, rstd = live ? rstd_in[row] : 0.f;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunk) {
+      const int c = l + LPR * i;
+      if (live && c < nchunk) {
         float xv[V], dv[V], rv[V];
         Vec<T>::unpack(cur[i][0], xv);
         Vec<T>::unpack(cur[i][1], dv);
@@ -334,12 +354,12 @@ ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
         }
       }
     }
-    s1 = warp_sum(s1) / (float)d;
-    s2 = warp_sum(s2) / (float)d;
+    s1 = group_sum<LPR>(s1) / (float)d;
+    s2 = group_sum<LPR>(s2) / (float)d;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
-      if (c < nchunk) {
+      const int c = l + LPR * i;
+      if (live && c < nchunk) {
         float xv[V], dv[V], rv[V], dz[V], gx[V];
         Vec<T>::unpack(cur[i][0], xv);
         Vec<T>::unpack(cur[i][1], dv);
@@ -375,9 +395,9 @@ ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
     if (q) __syncthreads();
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      const int c = lane + 32 * i;
+      const int c = l + LPR * i;
       if (c < nchunk) {
-        float* dst = stage + warp * d + c * V;
+        float* dst = stage + (warp * RPW + sub) * d + c * V;
 #pragma unroll
         for (int j = 0; j < V; j += 4) {
           const float* a = q == 0 ? &accg[i][j] : (q == 1 ? &accb[i][j] : &accx[DXSUM ? i : 0][j]);
@@ -390,7 +410,7 @@ ln_bwd_fused_body(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ 
       for (int c = threadIdx.x; c < d; c += LNB_WARPS * 32) {
         float t = 0.f;
 #pragma unroll
-        for (int w2 = 0; w2 < LNB_WARPS; ++w2) t += stage[w2 * d + c];
+        for (int w2 = 0; w2 < LNB_WARPS * RPW; ++w2) t += stage[w2 * d + c];
         atomicAdd(out + c, t);
       }
   }
@@ -418,13 +438,13 @@ ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ r
                                    gridDim.x);
 }
 
-template <typename T, int NCH, bool DXSUM>
+template <typename T, int NCH, bool DXSUM, int LPR>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 ln_bwd_fused_vec_grouped(const __grid_constant__ LnTable tb, int d) {
   const LnProb& a = tb.p[blockIdx.y];
   pdl_wait();
   pdl_trigger();
-  ln_bwd_fused_body<T, NCH, DXSUM>(static_cast<const T*>(a.dy), d, static_cast<const T*>(a.res), d,
+  ln_bwd_fused_body<T, NCH, DXSUM, LPR>(static_cast<const T*>(a.dy), d, static_cast<const T*>(a.res), d,
                                    static_cast<const T*>(a.x), d, a.gate, a.gamma, a.mean, a.rstd,
                                    static_cast<T*>(a.dres), d, static_cast<T*>(a.dx), d, a.dgate,
                                    a.dgamma, a.dbeta, DXSUM ? a.dxsum : nullptr, a.M, d,
@@ -733,14 +753,18 @@ int fwd_grouped(int n, const void* const* res, const void* const* x, const float
     mmax = M[i] > mmax ? M[i] : mmax;
   }
   if (mmax == 0) return MMEMO_OK;
-  // ~6 CTAs (48 warps) per SM over the whole group
-  int64_t gx = cdiv(mmax, LN_WARPS);
+  // ~6 CTAs (48 warps) per SM over the whole group; narrow rows share a warp (LPR lanes per row)
+  const int nchunk = (int)(d / V);
+  const int rpw = nchunk <= 8 ? 4 : (nchunk <= 16 ? 2 : 1);
+  int64_t gx = cdiv(mmax, LN_WARPS * rpw);
   const int64_t cap = cdiv(148 * 6, n);
   if (gx > cap) gx = cap;
   const dim3 grid((unsigned)gx, (unsigned)n);
-  const int nch = (int)cdiv(d / V, 32);
-#define MM_G(NCH_) MM_CUDA_OK(mm_launch(ln_fwd_vec_grouped<T, NCH_>, grid, dim3(LN_WARPS * 32), 0, st, tb, (int)d, eps, relu))
-  if (nch <= 1) MM_G(1); else if (nch <= 2) MM_G(2); else if (nch <= 4) MM_G(4); else MM_G(8);
+  const int nch = (int)cdiv(nchunk, 32);
+#define MM_G(NCH_, LPR_) MM_CUDA_OK(mm_launch(ln_fwd_vec_grouped<T, NCH_, LPR_>, grid, dim3(LN_WARPS * 32), 0, st, tb, (int)d, eps, relu))
+  if (rpw == 4) MM_G(1, 8); else if (rpw == 2) MM_G(1, 16);
+  else if (nch <= 1) MM_G(1, 32); else if (nch <= 2) MM_G(2, 32); else if (nch <= 4) MM_G(4, 32);
+  else MM_G(8, 32);
 #undef MM_G
   return MMEMO_OK;
 }
@@ -773,23 +797,27 @@ int bwd_grouped(int n, const void* const* dy, const void* const* res, const void
     mmax = M[i] > mmax ? M[i] : mmax;
   }
   if (mmax == 0) return MMEMO_OK;
-  // one persistent 16-warp CTA per SM over the whole group (at least one per problem)
-  int64_t gx = cdiv(mmax, LNB_WARPS);
+  // one persistent 16-warp CTA per SM over the whole group (at least one per problem); narrow rows
+  // share a warp (LPR lanes per row)
+  const int nchunk = (int)(d / V);
+  const int rpw = nchunk <= 8 ? 4 : (nchunk <= 16 ? 2 : 1);
+  int64_t gx = cdiv(mmax, LNB_WARPS * rpw);
   const int64_t cap = cdiv(148, n) > 1 ? cdiv(148, n) : 1;
   if (gx > cap) gx = cap;
   const dim3 grid((unsigned)gx, (unsigned)n);
-  const int nch = (int)cdiv(d / V, 32);
-  const size_t sm_bytes = (1 + LNB_WARPS) * (size_t)d * sizeof(float);
-#define MM_G(NCH_)                                                                                \
+  const int nch = (int)cdiv(nchunk, 32);
+  const size_t sm_bytes = (1 + LNB_WARPS * rpw) * (size_t)d * sizeof(float);
+#define MM_G(NCH_, LPR_)                                                                          \
   do {                                                                                            \
     if (any_dxsum)                                                                                \
-      MM_CUDA_OK(mm_launch(ln_bwd_fused_vec_grouped<T, NCH_, true>, grid, dim3(LNB_WARPS * 32),   \
-                           sm_bytes, st, tb, (int)d));                                            \
+      MM_CUDA_OK(mm_launch(ln_bwd_fused_vec_grouped<T, NCH_, true, LPR_>, grid,                   \
+                           dim3(LNB_WARPS * 32), sm_bytes, st, tb, (int)d));                      \
     else                                                                                          \
-      MM_CUDA_OK(mm_launch(ln_bwd_fused_vec_grouped<T, NCH_, false>, grid, dim3(LNB_WARPS * 32),  \
-                           sm_bytes, st, tb, (int)d));                                            \
+      MM_CUDA_OK(mm_launch(ln_bwd_fused_vec_grouped<T, NCH_, false, LPR_>, grid,                  \
+                           dim3(LNB_WARPS * 32), sm_bytes, st, tb, (int)d));                      \
   } while (0)
-  if (nch <= 1) MM_G(1); else if (nch <= 2) MM_G(2); else if (V == 4) MM_G(4);
+  if (rpw == 4) MM_G(1, 8); else if (rpw == 2) MM_G(1, 16);
+  else if (nch <= 1) MM_G(1, 32); else if (nch <= 2) MM_G(2, 32); else if (V == 4) MM_G(4, 32);
 #undef MM_G
   return MMEMO_OK;
 }

@@ -61,6 +61,7 @@ struct Table {
   int n, total;
   float inv_sqrt;
   int kv_blocked;   // backward: K / V are staged one key block at a time (long hd = 64 sequences)
+  int cta_start[MAXP + 1];   // contiguous: the blockIdx -> problem search reads one or two lines
   Prob p[MAXP];
 };
 
@@ -151,11 +152,50 @@ __device__ __forceinline__ void store8(bf16* p, int n_valid, bool vec, const flo
   }
 }
 
+// Lane-constant shared-memory offsets of the ldmatrix operands.  Key rows are addressed as
+// R0 + row with R0 a multiple of 32 and query rows as 16*rt + row: the XOR swizzle term of sw<HD>
+// then depends on `row` only, so the offsets are computed once per kernel and the loops add
+// R0 * row_bytes (keeps the integer / predicate instruction count - 2/3 of the first version's
+// instruction mix - out of the inner loops).
+template <int HD>
+struct LaneOffs {
+  uint32_t a[HD / 16];        // A operand (Q / dO rows 16*rt + ...), per k-tile
+  uint32_t n[2][HD / 16];     // B operand, keys as n (K for QK^T, V for dO V^T): [tile pair][k-tile]
+  uint32_t t[2][HD / 16];     // B operand, keys as k via .trans (V for PV, K for dS K): [pair][2 n-tiles]
+  __device__ __forceinline__ void init(int lane) {
+    const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+    for (int kt = 0; kt < HD / 16; ++kt) {
+      a[kt] = sw<HD>((lane & 7) + ((lane >> 3) & 1) * 8, 2 * kt + (lane >> 4));
+#pragma unroll
+      for (int ip = 0; ip < 2; ++ip) {
+        n[ip][kt] = sw<HD>(perm_key(ip * 2 + (mi >> 1), r), 2 * kt + (mi & 1));
+        t[ip][kt] = sw<HD>(perm_key(2 * ip + (mi & 1), r), 2 * kt + (mi >> 1));
+      }
+    }
+  }
+};
+constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float fast_exp2(float x) {          // MUFU.EX2; 2^(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// blockIdx.x -> (problem, CTA index inside the problem).  The problem's descriptor is COPIED from
+// the kernel-parameter table into shared memory once per CTA: reading it field by field through a
+// dynamically indexed constant-bank reference cost an LDCU miss per access (ncu: 36 % of the
+// backward kernel's stall samples).
 __device__ __forceinline__ const Prob& locate(const Table& T, int& local) {
+  __shared__ Prob sp;
   int p = 0;
-  while (p + 1 < T.n && (int)blockIdx.x >= T.p[p + 1].cta_start) ++p;
-  local = (int)blockIdx.x - T.p[p].cta_start;
-  return T.p[p];
+  while (p + 1 < T.n && (int)blockIdx.x >= T.cta_start[p + 1]) ++p;
+  local = (int)blockIdx.x - T.cta_start[p];
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&T.p[p]);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&sp);
+  for (int i = threadIdx.x; i < (int)(sizeof(Prob) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return sp;
 }
 
 // stage `rows` rows of a (.., ld) bf16 matrix (head slice: HD columns starting at col0) into a
@@ -207,19 +247,25 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
 
   const int r0 = q0 + warp * 16;          // first query row of this warp
   if (r0 >= Lq) return;
-  const bool has_prev = P.s_prev != nullptr;
+  const bool has_prev = P.s_prev != nullptr, has_mask = P.mask != nullptr;
   const float cval = (has_prev && P.c) ? P.c[0] : 0.f;
   const float inv_sqrt = T.inv_sqrt;
   const bool vec = P.vec_s != 0;
+  const int lds = P.lds;
   const int rowA = r0 + g, rowB = r0 + g + 8;
   const bool okA = rowA < Lq, okB = rowB < Lq;
   const size_t sbase = ((size_t)b * H + h) * Lq;
+  const size_t soff[2] = {(sbase + (okA ? rowA : 0)) * lds, (sbase + (okB ? rowB : 0)) * lds};
+  const bf16* __restrict__ sprev = P.s_prev;
+  bf16* __restrict__ sout = P.s_out;
+  constexpr uint32_t RB = HD * 2;
+  LaneOffs<HD> lo;
+  lo.init(lane);
 
   // Q fragments (A operand), all k-tiles
   uint32_t qa[HD / 16][4];
 #pragma unroll
-  for (int kt = 0; kt < HD / 16; ++kt)
-    ldsm4(sQ + sw<HD>(warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * kt + (lane >> 4)), qa[kt]);
+  for (int kt = 0; kt < HD / 16; ++kt) ldsm4(sQ + warp * 16 * RB + lo.a[kt], qa[kt]);
 
   float o[HD / 8][4];
 #pragma unroll
@@ -236,56 +282,73 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
       for (int e = 0; e < 4; ++e) sc[i][e] = 0.f;
     // ---- S = Q K^T : 2 groups of 32 keys x 4 permuted tiles ------------------------------------
 #pragma unroll
-    for (int G = 0; G < 2; ++G)
+    for (int G = 0; G < 2; ++G) {
+      const uint32_t kbase = sK + (uint32_t)(kb + 32 * G) * RB;
 #pragma unroll
       for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
         for (int kt = 0; kt < HD / 16; ++kt) {
-          const int mi = lane >> 3, r = lane & 7;
-          const int tile = ip * 2 + (mi >> 1);
-          const int key = kb + 32 * G + perm_key(tile, r);
           uint32_t kf[4];
-          ldsm4(sK + sw<HD>(key, 2 * kt + (mi & 1)), kf);
+          ldsm4(kbase + lo.n[ip][kt], kf);
           mma16816(sc[G * 4 + ip * 2], qa[kt], kf[0], kf[1]);
           mma16816(sc[G * 4 + ip * 2 + 1], qa[kt], kf[2], kf[3]);
         }
+    }
     // ---- scale, + c*S_prev, - 1e8*(1-mask), bf16 round, store S; block max ----------------------
     float bmax[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int G = 0; G < 2; ++G) {
       const int k0 = kb + 32 * G + 8 * t;             // this lane's 8 contiguous keys
+      const int nvalid = Lk - k0;                     // >= 8: the whole chunk is inside the keys
+      float bias[8];
+      if (has_mask) {
+        const float4 b0 = *reinterpret_cast<const float4*>(sbias + k0);
+        const float4 b1 = *reinterpret_cast<const float4*>(sbias + k0 + 4);
+        bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+        bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        const int row = half ? rowB : rowA;
         const bool row_ok = half ? okB : okA;
+        const bool use_prev = has_prev && row_ok && nvalid > 0;
         float pv[8];
-        if (has_prev && row_ok && k0 < Lk)
-          load8(P.s_prev + (sbase + row) * P.lds + k0, P.lds - k0, vec, pv);
+        if (use_prev) load8(sprev + soff[half] + k0, lds - k0, vec, pv);
         float sv[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int j = 2 * i + e, key = k0 + j;
+            const int j = 2 * i + e;
             float s = sc[G * 4 + i][half * 2 + e] * inv_sqrt;
-            if (has_prev && row_ok && k0 < Lk) s = __fadd_rn(s, __fmul_rn(cval, pv[j]));
-            if (P.mask) s = __fsub_rn(s, sbias[min(key, LkP - 1)]);
-            s = round_bf(s);
-            sv[j] = key < Lk ? s : 0.f;
-            s = key < Lk ? s : -INFINITY;
-            sc[G * 4 + i][half * 2 + e] = s;
-            bmax[half] = fmaxf(bmax[half], s);
+            if (use_prev) s = __fadd_rn(s, __fmul_rn(cval, pv[j]));
+            if (has_mask) s = __fsub_rn(s, bias[j]);
+            sv[j] = round_bf(s);
           }
-        if (P.s_out && row_ok && k0 < P.lds)
-          store8(P.s_out + (sbase + row) * P.lds + k0, P.lds - k0, vec, sv);
+        if (nvalid < 8) {                             // ragged tail of the keys (last block only)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool in = j < nvalid;
+            sc[G * 4 + (j >> 1)][half * 2 + (j & 1)] = in ? sv[j] : -INFINITY;
+            sv[j] = in ? sv[j] : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sc[G * 4 + (j >> 1)][half * 2 + (j & 1)] = sv[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          bmax[half] = fmaxf(bmax[half], fmaxf(sc[G * 4 + i][half * 2], sc[G * 4 + i][half * 2 + 1]));
+        if (sout && row_ok && k0 < lds) store8(sout + soff[half] + k0, lds - k0, vec, sv);
       }
     }
-    // ---- online softmax ----------------------------------------------------------------------
+    // ---- online softmax (base-2 exponentials) ----------------------------------------------------
+    // (s - max is formed FIRST: on a fully masked row s = max = bf16(-1e8), where folding max*log2e
+    // into an FFMA addend would leave its rounding error - up to +-8 - in the exponent)
     float scale[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
       const float m_new = fmaxf(m_run[half], quad_max(bmax[half]));
-      scale[half] = __expf(m_run[half] - m_new);       // first block: exp(-inf) = 0
+      scale[half] = fast_exp2((m_run[half] - m_new) * LOG2E);    // first block: 2^(-inf) = 0
       m_run[half] = m_new;
       l_run[half] *= scale[half];
     }
@@ -293,7 +356,7 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float p = __expf(sc[i][e] - m_run[e >> 1]);
+        const float p = fast_exp2((sc[i][e] - m_run[e >> 1]) * LOG2E);
         sc[i][e] = p;
         l_run[e >> 1] += p;
       }
@@ -304,35 +367,33 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
     }
     // ---- O += P V : P from registers (A operand), V via ldmatrix.trans ---------------------------
 #pragma unroll
-    for (int G = 0; G < 2; ++G)
+    for (int G = 0; G < 2; ++G) {
+      if (kb + 32 * G >= Lk) continue;                 // whole group beyond the keys (warp-uniform)
+      const uint32_t vbase = sV + (uint32_t)(kb + 32 * G) * RB;
 #pragma unroll
       for (int pp = 0; pp < 2; ++pp) {
-        if (kb + 32 * G >= Lk) continue;               // whole group beyond the keys (warp-uniform)
         const int i0 = G * 4 + 2 * pp, i1 = i0 + 1;
         uint32_t pa[4] = {pack2(sc[i0][0], sc[i0][1]), pack2(sc[i0][2], sc[i0][3]),
                           pack2(sc[i1][0], sc[i1][1]), pack2(sc[i1][2], sc[i1][3])};
 #pragma unroll
         for (int c2 = 0; c2 < HD / 8; c2 += 2) {
-          const int mi = lane >> 3, r = lane & 7;
-          const int key = kb + 32 * G + perm_key(2 * pp + (mi & 1), r);
           uint32_t vf[4];
-          ldsm4t(sV + sw<HD>(key, c2 + (mi >> 1)), vf);
+          ldsm4t(vbase + lo.t[pp][c2 >> 1], vf);
           mma16816(o[c2], pa, vf[0], vf[1]);
           mma16816(o[c2 + 1], pa, vf[2], vf[3]);
         }
       }
+    }
   }
   // ---- epilogue: normalise, write O (merged-head layout) and the (max, sum) pair ----------------
   const float lA = quad_sum(l_run[0]), lB = quad_sum(l_run[1]);
   const float iA = 1.f / lA, iB = 1.f / lB;
+  bf16* oA = P.o + ((size_t)b * Lq + rowA) * P.ldo + h * HD + 2 * t;
+  bf16* oB = oA + (size_t)8 * P.ldo;
 #pragma unroll
   for (int n = 0; n < HD / 8; ++n) {
-    if (okA)
-      *reinterpret_cast<uint32_t*>(P.o + ((size_t)b * Lq + rowA) * P.ldo + h * HD + 8 * n + 2 * t) =
-          pack2(o[n][0] * iA, o[n][1] * iA);
-    if (okB)
-      *reinterpret_cast<uint32_t*>(P.o + ((size_t)b * Lq + rowB) * P.ldo + h * HD + 8 * n + 2 * t) =
-          pack2(o[n][2] * iB, o[n][3] * iB);
+    if (okA) *reinterpret_cast<uint32_t*>(oA + 8 * n) = pack2(o[n][0] * iA, o[n][1] * iA);
+    if (okB) *reinterpret_cast<uint32_t*>(oB + 8 * n) = pack2(o[n][2] * iB, o[n][3] * iB);
   }
   if (t == 0 && P.lse) {
     if (okA) { P.lse[2 * (sbase + rowA)] = m_run[0]; P.lse[2 * (sbase + rowA) + 1] = lA; }
@@ -384,12 +445,12 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
   for (int i = threadIdx.x; i < LqP * HD; i += NT) sdQ[i] = 0.f;
   const size_t sbase = ((size_t)b * H + h) * Lq;
-  // per-row statistics: max, 1/sum (saved by the forward), D = rowsum(dO * O)
+  // per-row statistics: max, log2(sum) (saved by the forward), D = rowsum(dO * O)
   for (int r = threadIdx.x; r < LqP; r += NT) {
     float mx = 0.f, inv = 0.f, D = 0.f;
     if (r < Lq) {
       mx = P.lse[2 * (sbase + r)];
-      inv = 1.f / P.lse[2 * (sbase + r) + 1];
+      inv = log2f(P.lse[2 * (sbase + r) + 1]);      // P = 2^((s - max) log2e - log2(sum))
       const bf16* dop = P.d_o + ((size_t)b * Lq + r) * P.lddo + h * HD;
       const bf16* op = P.o_in + ((size_t)b * Lq + r) * P.ldo + h * HD;
 #pragma unroll
@@ -407,12 +468,27 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   cp_commit_wait();
   __syncthreads();
 
-  const bool has_prev = P.s_prev != nullptr;
+  const bool has_prev = P.s_prev != nullptr, has_mask = P.mask != nullptr;
   const bool recompute = P.s == nullptr;
   const float cval = (has_prev && P.c) ? P.c[0] : 0.f;
   const float inv_sqrt = T.inv_sqrt;
   const bool vec = P.vec_s != 0;
+  const int lds = P.lds;
   const int n_rt = LqP / 16;
+  const bf16* __restrict__ gs = P.s;
+  const bf16* __restrict__ gprev = P.s_prev;
+  const bf16* __restrict__ gnext = P.ds_next;
+  bf16* __restrict__ gdsp = P.ds_prev;
+  constexpr uint32_t RB = HD * 2;
+  LaneOffs<HD> lo;
+  lo.init(lane);
+  // shared-memory offsets of this lane's P / dS chunks: row 16*rt + g (+8), chunk 4*G + t
+  uint32_t pofs[NG][2];
+#pragma unroll
+  for (int G = 0; G < NG; ++G) {
+    pofs[G][0] = swp<KB>(g, 4 * G + t);
+    pofs[G][1] = swp<KB>(g + 8, 4 * G + t);
+  }
   float dc_part = 0.f;
 
   for (int kb = 0; kb < Lk; kb += KB) {
@@ -427,12 +503,15 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     // ================= phase A: one warp per 16-row tile ========================================
     for (int rt = warp; rt < n_rt; rt += nwarps) {
       const int rowA = rt * 16 + g, rowB = rowA + 8;
-      const bool okA = rowA < Lq, okB = rowB < Lq;
+      const bool ok[2] = {rowA < Lq, rowB < Lq};
+      const size_t soff[2] = {(sbase + (ok[0] ? rowA : 0)) * lds, (sbase + (ok[1] ? rowB : 0)) * lds};
+      const float st_mx[2] = {sstat[3 * rowA], sstat[3 * rowB]};
+      const float st_l2[2] = {sstat[3 * rowA + 1], sstat[3 * rowB + 1]};
+      const float st_D[2] = {sstat[3 * rowA + 2], sstat[3 * rowB + 2]};
+      const uint32_t abase = (uint32_t)(rt * 16) * RB;
       uint32_t doa[HD / 16][4];
 #pragma unroll
-      for (int kt = 0; kt < HD / 16; ++kt)
-        ldsm4(sdO + sw<HD>(rt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * kt + (lane >> 4)),
-              doa[kt]);
+      for (int kt = 0; kt < HD / 16; ++kt) ldsm4(sdO + abase + lo.a[kt], doa[kt]);
       float sc[NG * 4][4], dp[NG * 4][4];
 #pragma unroll
       for (int i = 0; i < NG * 4; ++i)
@@ -441,87 +520,93 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
       if (recompute) {
         uint32_t qa[HD / 16][4];
 #pragma unroll
-        for (int kt = 0; kt < HD / 16; ++kt)
-          ldsm4(sQ + sw<HD>(rt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, 2 * kt + (lane >> 4)),
-                qa[kt]);
+        for (int kt = 0; kt < HD / 16; ++kt) ldsm4(sQ + abase + lo.a[kt], qa[kt]);
 #pragma unroll
-        for (int G = 0; G < NG; ++G)
+        for (int G = 0; G < NG; ++G) {
+          const uint32_t kbase = sK + (uint32_t)(kb - kofs + 32 * G) * RB;
 #pragma unroll
           for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
             for (int kt = 0; kt < HD / 16; ++kt) {
-              const int mi = lane >> 3, r = lane & 7;
-              const int key = kb + 32 * G + perm_key(ip * 2 + (mi >> 1), r);
               uint32_t kf[4];
-              ldsm4(sK + sw<HD>(key - kofs, 2 * kt + (mi & 1)), kf);
+              ldsm4(kbase + lo.n[ip][kt], kf);
               mma16816(sc[G * 4 + ip * 2], qa[kt], kf[0], kf[1]);
               mma16816(sc[G * 4 + ip * 2 + 1], qa[kt], kf[2], kf[3]);
             }
+        }
       }
       // dP = dO V^T
 #pragma unroll
-      for (int G = 0; G < NG; ++G)
+      for (int G = 0; G < NG; ++G) {
+        const uint32_t vbase = sV + (uint32_t)(kb - kofs + 32 * G) * RB;
 #pragma unroll
         for (int ip = 0; ip < 2; ++ip)
 #pragma unroll
           for (int kt = 0; kt < HD / 16; ++kt) {
-            const int mi = lane >> 3, r = lane & 7;
-            const int key = kb + 32 * G + perm_key(ip * 2 + (mi >> 1), r);
             uint32_t vf[4];
-            ldsm4(sV + sw<HD>(key - kofs, 2 * kt + (mi & 1)), vf);
+            ldsm4(vbase + lo.n[ip][kt], vf);
             mma16816(dp[G * 4 + ip * 2], doa[kt], vf[0], vf[1]);
             mma16816(dp[G * 4 + ip * 2 + 1], doa[kt], vf[2], vf[3]);
           }
+      }
       // elementwise: P, dS, dc, dS_prev; P / dS -> shared memory (bf16, natural key order)
 #pragma unroll
       for (int G = 0; G < NG; ++G) {
         const int k0 = kb + 32 * G + 8 * t;
+        const int nvalid = Lk - k0;                    // >= 8: the whole chunk is inside the keys
+        float bias[8];
+        if (recompute && has_mask) {
+          const float4 b0 = *reinterpret_cast<const float4*>(sbias + k0);
+          const float4 b1 = *reinterpret_cast<const float4*>(sbias + k0 + 4);
+          bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+          bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+        }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-          const int row = half ? rowB : rowA;
-          const bool row_ok = half ? okB : okA;
-          const bool in = row_ok && k0 < Lk;
-          const float mx = sstat[3 * row], inv = sstat[3 * row + 1], D = sstat[3 * row + 2];
+          const bool in = ok[half] && nvalid > 0;
+          const float mx = st_mx[half], l2 = st_l2[half], D = st_D[half];
           float sv[8], pv[8], nv[8], pb[8], dsb[8];
-          if (!recompute && in) load8(P.s + (sbase + row) * P.lds + k0, P.lds - k0, vec, sv);
-          if (has_prev && in) load8(P.s_prev + (sbase + row) * P.lds + k0, P.lds - k0, vec, pv);
-          if (P.ds_next && in) load8(P.ds_next + (sbase + row) * P.lds + k0, P.lds - k0, vec, nv);
+          if (!recompute && in) load8(gs + soff[half] + k0, lds - k0, vec, sv);
+          if (has_prev && in) load8(gprev + soff[half] + k0, lds - k0, vec, pv);
+          if (gnext && in) load8(gnext + soff[half] + k0, lds - k0, vec, nv);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = 2 * i + e, key = k0 + j;
-              float p = 0.f, ds = 0.f;
-              if (in && key < Lk) {
-                float s;
-                if (recompute) {
-                  s = sc[G * 4 + i][half * 2 + e] * inv_sqrt;
-                  if (has_prev) s = __fadd_rn(s, __fmul_rn(cval, pv[j]));
-                  if (P.mask) s = __fsub_rn(s, sbias[key]);
-                  s = round_bf(s);
-                } else {
-                  s = sv[j];
-                }
-                p = __expf(s - mx) * inv;
-                ds = p * (dp[G * 4 + i][half * 2 + e] - D);
-                if (P.ds_next) ds += nv[j];
-                if (has_prev) dc_part = fmaf(ds, pv[j], dc_part);
-              }
-              pb[j] = p;
-              dsb[j] = ds;
-              sc[G * 4 + i][half * 2 + e] = ds;        // reused as the A operand of dQ += dS K
+          for (int j = 0; j < 8; ++j) {
+            float s;
+            if (recompute) {
+              s = sc[G * 4 + (j >> 1)][half * 2 + (j & 1)] * inv_sqrt;
+              if (has_prev) s = __fadd_rn(s, __fmul_rn(cval, pv[j]));
+              if (has_mask) s = __fsub_rn(s, bias[j]);
+              s = round_bf(s);
+            } else {
+              s = sv[j];
             }
-          if (has_prev && P.ds_prev && in) {
+            const float p = fast_exp2(fmaf(s - mx, LOG2E, -l2));
+            float ds = p * (dp[G * 4 + (j >> 1)][half * 2 + (j & 1)] - D);
+            if (gnext) ds += nv[j];
+            pb[j] = p;
+            dsb[j] = ds;
+          }
+          if (!in || nvalid < 8) {                     // rows beyond Lq / ragged tail of the keys
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (!in || j >= nvalid) { pb[j] = 0.f; dsb[j] = 0.f; pv[j] = 0.f; }   // (padding may hold anything)
+          }
+          if (has_prev && in) {
             float o8[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o8[j] = cval * dsb[j];
-            store8(P.ds_prev + (sbase + row) * P.lds + k0, P.lds - k0, vec, o8);
+            for (int j = 0; j < 8; ++j) {
+              dc_part = fmaf(dsb[j], pv[j], dc_part);
+              o8[j] = cval * dsb[j];
+            }
+            if (gdsp) store8(gdsp + soff[half] + k0, lds - k0, vec, o8);
           }
-          const uint32_t ch = (uint32_t)(4 * G + t);
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sP + swp<KB>(row, ch)),
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sc[G * 4 + (j >> 1)][half * 2 + (j & 1)] = dsb[j];   // A of dQ += dS K
+          const uint32_t rb = (uint32_t)(rt * 16) * (KB * 2) + pofs[G][half];
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sP + rb),
                        "r"(pack2(pb[0], pb[1])), "r"(pack2(pb[2], pb[3])), "r"(pack2(pb[4], pb[5])),
                        "r"(pack2(pb[6], pb[7])) : "memory");
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sdS + swp<KB>(row, ch)),
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sdS + rb),
                        "r"(pack2(dsb[0], dsb[1])), "r"(pack2(dsb[2], dsb[3])),
                        "r"(pack2(dsb[4], dsb[5])), "r"(pack2(dsb[6], dsb[7])) : "memory");
         }
@@ -533,27 +618,28 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) dq[n][e] = 0.f;
 #pragma unroll
-      for (int G = 0; G < NG; ++G)
+      for (int G = 0; G < NG; ++G) {
+        if (kb + 32 * G >= Lk) continue;
+        const uint32_t kbase = sK + (uint32_t)(kb - kofs + 32 * G) * RB;
 #pragma unroll
         for (int pp = 0; pp < 2; ++pp) {
-          if (kb + 32 * G >= Lk) continue;
           const int i0 = G * 4 + 2 * pp, i1 = i0 + 1;
           uint32_t da[4] = {pack2(sc[i0][0], sc[i0][1]), pack2(sc[i0][2], sc[i0][3]),
                             pack2(sc[i1][0], sc[i1][1]), pack2(sc[i1][2], sc[i1][3])};
 #pragma unroll
           for (int c2 = 0; c2 < HD / 8; c2 += 2) {
-            const int mi = lane >> 3, r = lane & 7;
-            const int key = kb + 32 * G + perm_key(2 * pp + (mi & 1), r);
             uint32_t kf[4];
-            ldsm4t(sK + sw<HD>(key - kofs, c2 + (mi >> 1)), kf);
+            ldsm4t(kbase + lo.t[pp][c2 >> 1], kf);
             mma16816(dq[c2], da, kf[0], kf[1]);
             mma16816(dq[c2 + 1], da, kf[2], kf[3]);
           }
         }
+      }
+      float* qA = sdQ + rowA * HD + 2 * t;
 #pragma unroll
       for (int n = 0; n < HD / 8; ++n) {
-        float2* pa = reinterpret_cast<float2*>(sdQ + rowA * HD + 8 * n + 2 * t);
-        float2* pb2 = reinterpret_cast<float2*>(sdQ + rowB * HD + 8 * n + 2 * t);
+        float2* pa = reinterpret_cast<float2*>(qA + 8 * n);
+        float2* pb2 = reinterpret_cast<float2*>(qA + 8 * HD + 8 * n);
         float2 a = *pa, b2 = *pb2;
         a.x += dq[n][0]; a.y += dq[n][1]; b2.x += dq[n][2]; b2.y += dq[n][3];
         *pa = a; *pb2 = b2;
@@ -706,11 +792,13 @@ int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
     if (ps[i].hd != hd || !resattn_mma_supported(ps[i], false)) return MMEMO_ERR_SHAPE;
     fill(T.p[i], ps[i]);
     T.p[i].cta_start = ctas;
+    T.cta_start[i] = ctas;
     ctas += (int)(ps[i].B * ps[i].H * cdiv(ps[i].Lq, FWD_ROWS));
     const size_t s = fwd_smem(hd, (int)ps[i].Lk, ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv);
     smem = s > smem ? s : smem;
   }
   T.total = ctas;
+  T.cta_start[n] = ctas;
   T.inv_sqrt = (float)(1.0 / sqrt((double)hd));
 #define MM_FWD(HD)                                                                               \
   {                                                                                              \
@@ -745,6 +833,7 @@ int bwd_launch(const mmemo_attn_problem* const* ps, int n, int warps, cudaStream
   for (int i = 0; i < n; ++i) {
     fill(T.p[i], *ps[i]);
     T.p[i].cta_start = ctas;
+    T.cta_start[i] = ctas;
     ctas += (int)(ps[i]->B * ps[i]->H);
     const bool same = ps[i]->k == ps[i]->v && ps[i]->ldk == ps[i]->ldv;
     const size_t f32_ = bwd_smem(hd, 32, (int)ps[i]->Lq, (int)ps[i]->Lk, same, false);
@@ -762,6 +851,7 @@ int bwd_launch(const mmemo_attn_problem* const* ps, int n, int warps, cudaStream
     smem32 = s32 > smem32 ? s32 : smem32;
   }
   T.total = ctas;
+  T.cta_start[n] = ctas;
   T.inv_sqrt = (float)(1.0 / sqrt((double)hd));
   // Key block: the 64-key instantiation needs ~155 registers, the 32-key one ~110: prefer 32
   // whenever two or more CTAs fit (measured 2x faster on cfg 1a and cfg 4), 64 when only one CTA
