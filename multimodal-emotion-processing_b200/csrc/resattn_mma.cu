@@ -36,7 +36,7 @@ namespace {
 
 constexpr int MAXP = 40;          // problems per launch
 constexpr int FWD_WARPS = 4, FWD_ROWS = 64;
-constexpr int BWD_WARPS = 8;
+constexpr int BWD_WARPS = 6;
 constexpr size_t SMEM_MAX = 226 * 1024;   // dynamic part (227 KB per CTA minus static + reserve)
 
 struct Prob {
@@ -215,8 +215,9 @@ __device__ __forceinline__ void stage(uint32_t dst, const bf16* src, int ld, int
 // =============================================================================================
 // forward
 // =============================================================================================
+// (register caps keep 5 / 4 / 3 CTAs of 4 warps resident per SM for hd = 16 / 32 / 64)
 template <int HD>
-__global__ void __launch_bounds__(FWD_WARPS * 32)
+__global__ void __launch_bounds__(FWD_WARPS * 32, HD == 16 ? 5 : (HD == 32 ? 4 : 3))
 resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
   extern __shared__ __align__(128) uint8_t smem[];
   int local;
@@ -404,8 +405,10 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
 // =============================================================================================
 // backward
 // =============================================================================================
+// (<= 6 warps per CTA; the 32-key instantiations are capped at 113 registers so that three
+// 6-warp CTAs - or four 4-warp ones - stay resident per SM)
 template <int HD, int KB>
-__global__ void __launch_bounds__(BWD_WARPS * 32)
+__global__ void __launch_bounds__(BWD_WARPS * 32, (KB == 32 && HD <= 32) ? 3 : 1)
 resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   const int NT = blockDim.x, nwarps = blockDim.x >> 5;   // 2..8 warps, chosen per launch (host)
   constexpr int NG = KB / 32;              // 32-key groups per block
@@ -815,7 +818,7 @@ int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
 namespace {
 // Warps per backward CTA: phase A hands one 16-row tile to a warp per round, so the CTA is sized
 // to the number of tiles split evenly over the rounds (18 tiles -> 3 rounds of 6 warps instead of
-// 8 + 8 + 2 on eight; 4 tiles -> 4 warps, twice as many CTAs per SM) - idle warps only add
+// 6 + 6 + 6 + 0; 4 tiles -> 4 warps, more CTAs per SM) - idle warps only add
 // barrier stalls (ncu: 7 of 10 issue slots stalled on the barrier with 4 of 8 warps working).
 int bwd_warps(int64_t Lq) {
   const int n_rt = (int)cdiv(Lq, 16);
