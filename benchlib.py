@@ -327,6 +327,47 @@ class GraphedStep:
         torch.cuda.current_stream().synchronize()
         return float(self.host_loss)
 
+    def run_e2e_pipelined(self, n: int) -> float:
+        """n steps driven like a real input pipeline: the H2D copy of step i+1 (pinned host ->
+        one of two device staging sets, on a copy stream) overlaps the compute of step i; the
+        compute stream copies the staged batch into the graph's static inputs, replays, and sends
+        the loss to the host, where it is read one step later.  Every step's inputs cross PCIe and
+        every step's loss reaches the host inside the timed region."""
+        if not hasattr(self, "_pipe"):
+            self._pipe = dict(
+                copy=torch.cuda.Stream(),
+                stage=[{k: torch.empty_like(v) for k, v in self.static.items()} for _ in range(2)],
+                h2d=[torch.cuda.Event() for _ in range(2)], free=[torch.cuda.Event() for _ in range(2)],
+                done=[torch.cuda.Event() for _ in range(2)],
+                loss=[torch.zeros((), pin_memory=True) for _ in range(2)])
+        P = self._pipe
+        cur = torch.cuda.current_stream()
+
+        def issue(i):
+            s_ = i % 2
+            with torch.cuda.stream(P["copy"]):
+                P["copy"].wait_event(P["free"][s_])         # compute no longer reads this stage
+                for k, v in self.host.items():
+                    P["stage"][s_][k].copy_(v, non_blocking=True)
+                P["h2d"][s_].record(P["copy"])
+
+        issue(0)
+        for i in range(n):
+            s_ = i % 2
+            if i + 1 < n:
+                issue(i + 1)
+            cur.wait_event(P["h2d"][s_])
+            torch._foreach_copy_(list(self.static.values()), list(P["stage"][s_].values()))
+            P["free"][s_].record(cur)
+            self.run()
+            P["loss"][s_].copy_(self.loss_dev, non_blocking=True)
+            P["done"][s_].record(cur)
+            if i >= 1:
+                P["done"][1 - s_].synchronize()
+                float(P["loss"][1 - s_])
+        P["done"][(n - 1) % 2].synchronize()
+        return float(P["loss"][(n - 1) % 2])
+
 
 def time_events(fn: Callable, steps: int, warmup: int, barrier: Callable) -> float:
     """ms for `steps` calls of fn, CUDA events on the current stream, barrier+sync on both sides."""

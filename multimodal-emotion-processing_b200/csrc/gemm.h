@@ -32,8 +32,3 @@ int gemm_tc(const GemmArgs& g, int c_bf16, int family, cudaStream_t st);
 constexpr int GEMM_TC_MAX_GROUP = 48;
 int gemm_tc_grouped(const GemmArgs* gs, const int* c_bf16s, int n, int family, cudaStream_t st);
 
-// Skinny path (gemm_skinny.cu): bf16, N and K <= 384 (the d = 96 / 128 / 192 models): weight resident
-// in shared memory, rows streamed through mma.sync; HBM-bound shapes where the 128 x 128 tcgen05
-// tiles are dominated by per-tile latency.  Grouped like gemm_tc_grouped.
-bool gemm_skinny_supported(const GemmArgs& g, int c_bf16);
-int gemm_skinny_grouped(const GemmArgs* gs, int n, cudaStream_t st);

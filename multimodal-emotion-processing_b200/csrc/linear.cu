@@ -11,8 +11,6 @@ int mmemo_rowsum_dispatch(int bf16_mode, const void* x, int64_t ldx, float* out,
 namespace {
 
 int run(const GemmArgs& g, int a_bf16, int b_bf16, int c_bf16, int family, cudaStream_t st) {
-  if (a_bf16 && b_bf16 && c_bf16 && gemm_skinny_supported(g, c_bf16))
-    return gemm_skinny_grouped(&g, 1, st);
   if (a_bf16 && b_bf16 && gemm_tc_supported(g, c_bf16)) return gemm_tc(g, c_bf16, family, st);
   return gemm_simt(g, a_bf16, b_bf16, c_bf16, st);
 }
@@ -96,7 +94,7 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
   if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
   GemmArgs g[GEMM_TC_MAX_GROUP] = {};
   int cb[GEMM_TC_MAX_GROUP];
-  bool tc_ok = true, sk_ok = true;
+  bool tc_ok = true;
   for (int i = 0; i < n; ++i) {
     MM_REQUIRE(x[i] && w[i] && y[i]);
     g[i].A = x[i]; g[i].sAm = ldx[i]; g[i].sAk = 1;
@@ -112,9 +110,7 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
     }
     cb[i] = 1;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 1, n > 1);
-    sk_ok = sk_ok && gemm_skinny_supported(g[i], 1);
   }
-  if (sk_ok) return gemm_skinny_grouped(g, n, mm_stream(s));
   if (tc_ok) return gemm_tc_grouped(g, cb, n, 0, mm_stream(s));
   for (int i = 0; i < n; ++i) {
     const int rc = run(g[i], 1, 1, 1, 0, mm_stream(s));
@@ -130,7 +126,7 @@ int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t*
   if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
   GemmArgs g[GEMM_TC_MAX_GROUP] = {};
   int cb[GEMM_TC_MAX_GROUP];
-  bool tc_ok = true, sk_ok = true;
+  bool tc_ok = true;
   for (int i = 0; i < n; ++i) {
     MM_REQUIRE(dy[i] && w[i] && dx[i]);
     g[i].A = dy[i]; g[i].sAm = lddy[i]; g[i].sAk = 1;
@@ -144,9 +140,7 @@ int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t*
     }
     cb[i] = 1;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 1, n > 1);
-    sk_ok = sk_ok && gemm_skinny_supported(g[i], 1);
   }
-  if (sk_ok) return gemm_skinny_grouped(g, n, mm_stream(s));
   if (tc_ok) return gemm_tc_grouped(g, cb, n, 1, mm_stream(s));
   for (int i = 0; i < n; ++i) {
     const int rc = run(g[i], 1, 1, 1, 1, mm_stream(s));

@@ -36,7 +36,7 @@ namespace {
 
 constexpr int MAXP = 40;          // problems per launch
 constexpr int FWD_WARPS = 4, FWD_ROWS = 64;
-constexpr int BWD_WARPS = 6;
+constexpr int BWD_WARPS = 8;
 constexpr size_t SMEM_MAX = 226 * 1024;   // dynamic part (227 KB per CTA minus static + reserve)
 
 struct Prob {
@@ -405,10 +405,10 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
 // =============================================================================================
 // backward
 // =============================================================================================
-// (<= 6 warps per CTA; the 32-key instantiations are capped at 113 registers so that three
-// 6-warp CTAs - or four 4-warp ones - stay resident per SM)
+// (no register cap: forcing three 6-warp CTAs per SM (<= 96 registers) spilled and measured 8 %
+// slower on Ren-MME's shapes than two CTAs at 121 registers)
 template <int HD, int KB>
-__global__ void __launch_bounds__(BWD_WARPS * 32, (KB == 32 && HD <= 32) ? 3 : 1)
+__global__ void __launch_bounds__(BWD_WARPS * 32)
 resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   const int NT = blockDim.x, nwarps = blockDim.x >> 5;   // 2..8 warps, chosen per launch (host)
   constexpr int NG = KB / 32;              // 32-key groups per block
@@ -818,7 +818,7 @@ int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
 namespace {
 // Warps per backward CTA: phase A hands one 16-row tile to a warp per round, so the CTA is sized
 // to the number of tiles split evenly over the rounds (18 tiles -> 3 rounds of 6 warps instead of
-// 6 + 6 + 6 + 0; 4 tiles -> 4 warps, more CTAs per SM) - idle warps only add
+// 8 + 8 + 2 on eight; 4 tiles -> 4 warps, twice as many CTAs per SM) - idle warps only add
 // barrier stalls (ncu: 7 of 10 issue slots stalled on the barrier with 4 of 8 warps working).
 int bwd_warps(int64_t Lq) {
   const int n_rt = (int)cdiv(Lq, 16);
