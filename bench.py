@@ -262,7 +262,10 @@ def ncu_traffic():
     try:
         with open(NCU_TRAFFIC_FILE) as fh:
             d = json.load(fh)
-        return d.get("families", {}), d.get("source")
+        src = d.get("source")
+        if isinstance(src, dict):
+            src = src.get("cfg2")
+        return d.get("families", {}), src
     except Exception:
         return {}, None
 
@@ -657,6 +660,61 @@ def measure_robot_ensemble(dev, n_requests: int = 200, baselines: bool = True):
     return res
 
 
+def ncu_step(which: str, dev, precision: str):
+    """One eager step of a workload with an NVTX range (named like bench's kernel families) around
+    every libmmemo launch; the profiled region is bracketed by cudaProfilerStart/Stop."""
+    import benchlib
+    import mmemo_b200
+    from mmemo_b200 import ops, synth
+    mmemo_b200.set_precision(precision)
+    if which == "cfg2":
+        torch.manual_seed(0)
+        model = mmemo_b200.ResidualEncoder(CFG["dim"], CFG["n_heads"], CFG["n_layers"], CFG["ffn"])
+        model.load_state_dict(synth.randomize_gates(
+            {k: v.detach().clone() for k, v in model.state_dict().items()}))
+        model = model.to(dev).train()
+        b = synth.encoder_batch(seed=1234, B=CFG["batch_per_gpu"], L=CFG["seq_len"], d=CFG["dim"])
+        x, m = b["x"].to(dev), b["mask"].to(dev)
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            (model(x, m).float() ** 2).mean().backward()
+    else:
+        bsz = {"cfg1a": 32, "cfg1b": 32, "cfg3": 128, "cfg3c": 64, "cfg4": 256}[which]
+        gs = benchlib.GraphedStep(benchlib.WORKLOADS[which](bsz), dev, seed=1234, use_graph=False)
+        step = gs._step
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    real, real_try = ops._call, ops._try_call
+
+    def key_of(name, args):
+        _, _, tag = _algorithmic(name, args)
+        return name.replace("mmemo_", "") + (":" + tag if tag else "")
+
+    def call(name, *a):
+        torch.cuda.nvtx.range_push(key_of(name, a))
+        try:
+            real(name, *a)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def try_call(name, *a):
+        torch.cuda.nvtx.range_push(key_of(name, a))
+        try:
+            return real_try(name, *a)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    ops._call, ops._try_call = call, try_call
+    torch.cuda.profiler.start()
+    step()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+    ops._call, ops._try_call = real, real_try
+    print(f"ncu-step {which}: done", file=sys.stderr)
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -667,6 +725,11 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", default=None, metavar="WORKLOAD",
+                    help="profiling driver (no JSON line): run ONE eager step of cfg2 | cfg1a | cfg1b | "
+                         "cfg3c | cfg4 between cudaProfilerStart/Stop with every libmmemo launch "
+                         "inside an NVTX range named after its kernel family, for "
+                         "`ncu --nvtx --print-nvtx-rename kernel --profile-from-start off`")
     ap.add_argument("--configs", default="all",
                     help="comma list of the extra BASELINE configs to measure "
                          "(cfg1a,cfg1b,cfg3,cfg3c,cfg4,cfg5), 'all' or 'none'")
@@ -682,8 +745,17 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.ncu_step:
+        ncu_step(args.ncu_step, dev, args.precision)
+        return
     import torch.distributed as dist
+    stdout_fd = None
     if world > 1:
+        # stdout carries exactly ONE JSON line: native libraries (NCCL's version banner) that write
+        # to file descriptor 1 during initialisation are sent to stderr until the line is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         # the gradient all-reduce moves ~50 MB per 2 ms step: a few CTAs are plenty (measured on 2
@@ -883,7 +955,8 @@ def main():
             g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
                 step()
-        except Exception:
+        except Exception as ex:
+            print(f"[bench] no-comm graph capture failed ({type(ex).__name__}: {ex})", file=sys.stderr)
             g2 = None
             torch.cuda.synchronize()
         run2 = g2.replay if g2 is not None else step
@@ -1012,6 +1085,9 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": gpu_eager, "dp": dp_info,
             "kernels": kernels[:12], "configs": configs,
         }
+        if stdout_fd is not None:
+            sys.stdout.flush()
+            os.dup2(stdout_fd, 1)
         print(json.dumps(out), flush=True)
     if world > 1:
         # Tear down in a fixed order: drain the device, meet the other ranks, then leave without

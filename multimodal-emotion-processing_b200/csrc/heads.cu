@@ -243,7 +243,8 @@ bilinear_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ th
   }
 }
 
-// dW[n][i] += sum_b dy[b][n] cat[b][i]: thread per (n, i), loop over the batch (recomputes LN(z)).
+// dW[n][i] += sum_b dy[b][n] cat[b][i]: thread per (n, i); blockIdx.y splits the batch into strips
+// of 16 samples (one atomic per weight per strip) so that B = 256 is not one serial loop.
 __global__ void bilinear_dw_kernel(const float* __restrict__ dout, const float* __restrict__ th,
                                    const float* __restrict__ zsave, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ dW, int B,
@@ -251,8 +252,9 @@ __global__ void bilinear_dw_kernel(const float* __restrict__ dout, const float* 
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 2 * C * C) return;
   const int n = idx / (2 * C), i = idx - n * 2 * C;
+  const int b0 = blockIdx.y * 16, b1 = min(B, b0 + 16);
   float acc = 0.f;
-  for (int b = 0; b < B; ++b) {
+  for (int b = b0; b < b1; ++b) {
     float cat;
     if (i < C) {
       cat = th[b * C + i];
@@ -413,7 +415,8 @@ int mmemo_bilinear_head_bwd(const float* dout, const float* this_feat, const flo
       (int)B, (int)C, eps, copies);
   MM_LAUNCH_OK();
   if (dw) {  // dW needs the full concat value LN(z)+beta: thread per weight, loop over the batch
-    bilinear_dw_kernel<<<(unsigned)cdiv(2 * C * C, 128), 128, 0, mm_stream(s)>>>(
+    bilinear_dw_kernel<<<dim3((unsigned)cdiv(2 * C * C, 128), (unsigned)cdiv(B, 16)), 128, 0,
+                         mm_stream(s)>>>(
         dout, this_feat, z, gamma, beta, dw, (int)B, (int)C, eps);
     MM_LAUNCH_OK();
   }

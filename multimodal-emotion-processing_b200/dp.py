@@ -334,7 +334,7 @@ class GradReducer:
             if b.work is not None:
                 b.work.wait()
                 b.work = None
-        if self._symm is not None:
+        if self._symm is not None and not self.no_comm:
             torch.cuda.current_stream().wait_stream(self._symm[1])
 
     def remove(self) -> None:
