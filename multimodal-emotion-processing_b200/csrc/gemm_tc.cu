@@ -96,9 +96,10 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
   const int units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int total = G.item_start[G.n];
 
-  // global work item -> (problem, item within the problem)
+  // global work item -> (problem, item within the problem).  Every role walks its items in
+  // increasing order, so the search resumes from the caller's previous problem (`g` is a cursor
+  // the caller keeps): O(1) amortised instead of a scan over up to 48 table entries per tile.
   auto locate = [&](int w, int& g, int& lw) {
-    g = 0;
     while (g + 1 < G.n && w >= G.item_start[g + 1]) ++g;
     lw = w - G.item_start[g];
   };
@@ -140,8 +141,9 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     // ================= TMA producer (every CTA stages its own rows of A and columns of B) =========
     if (lane == 0) {
       uint32_t it = 0;
+      int g = 0;
       for (int w = unit; w < total; w += units) {
-        int g, lw, m0, n0, sp, tile;
+        int lw, m0, n0, sp, tile;
         locate(w, g, lw);
         const TcArgs& a = G.p[g];
         const CUtensorMap* tmA = &TMS.a[g];
@@ -179,8 +181,9 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     // ================= MMA issuer (leader CTA only) =================
     if (lane == 0 && rank == 0) {
       uint32_t it = 0, ti = 0;
+      int g = 0;
       for (int w = unit; w < total; w += units, ++ti) {
-        int g, lw;
+        int lw;
         locate(w, g, lw);
         const TcArgs& a = G.p[g];
         const int sp = lw % a.splits;
@@ -219,9 +222,11 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     const int te = threadIdx.x - 64;
     // step = (work item, 128-column half); aux tile of a step: old C (accumulate) or the saved
     // activation (ReLU mask), bf16, prefetched one step ahead (issue order == consumption order)
+    int g_aux = 0;                 // cursor of the aux prefetches (they run one step ahead)
     auto issue_aux = [&](int w, int half) {
-      int g, lw, m0, n0, sp, tile;
-      locate(w, g, lw);
+      int lw, m0, n0, sp, tile;
+      locate(w, g_aux, lw);
+      const int g = g_aux;
       if (!G.p[g].aux) return;
       decode(G.p[g], lw, m0, n0, sp, tile);
       tc::mbar_expect_tx(bar_aux, 32 * 1024);
@@ -230,8 +235,9 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     };
     if (te == 0 && unit < total) issue_aux(unit, 0);
     uint32_t ti = 0, aux_ctr = 0;
+    int g = 0;
     for (int w = unit; w < total; w += units, ++ti) {
-      int g, lw, m0, n0, sp, tile;
+      int lw, m0, n0, sp, tile;
       locate(w, g, lw);
       const TcArgs& a = G.p[g];
       const CUtensorMap* tmC = &TMS.c[g];
