@@ -269,6 +269,14 @@ int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_
  * whole trunk layer */
 int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const* dst,
                                  const int64_t* n, mmemo_stream_t stream);
+/* out[i] = sum of n_in[i] (<= 8) equally sized contiguous tensors, for n_out <= 16 outputs in one
+ * launch (`in` = the inputs of all outputs, concatenated; out[i] may alias its first input): the
+ * gradients reaching one modality stream from the chains that read it (others/realformer.py:232-257),
+ * which autograd would add pairwise.  16-byte aligned pointers. */
+int mmemo_sum_grouped_f32(int n_out, void* const* out, const int* n_in, const void* const* in,
+                          const int64_t* numel, mmemo_stream_t stream);
+int mmemo_sum_grouped_bf16(int n_out, void* const* out, const int* n_in, const void* const* in,
+                           const int64_t* numel, mmemo_stream_t stream);
 /* `count` <= 16 float32 (M, K) matrices (row stride lds) -> bf16 (M, ldd) with ldd % 8 == 0 and
  * zero-filled padding columns, in one launch: raw input features (the float tensors built at
  * others/realformer.py:307-309, Ren-MME/run.py:316-327) and their projection weights become

@@ -112,8 +112,10 @@ int gemm_simt(const GemmArgs& g, int a_bf16, int b_bf16, int c_bf16, cudaStream_
   // non-linear epilogue
   int splitk = 1;
   const int64_t tiles = cdiv(g.M, BM) * cdiv(g.N, BN);
-  if (!c_bf16 && !g.relu && !g.relu_src && tiles < 148 && g.K >= 1024) {
-    const int64_t want = cdiv(296, tiles), cap = g.K / 256;
+  // (also the small float32 head GEMMs: (B, 576..2304) x (9..96 outputs) are 3-8 tiles whose serial
+  // K loop took 30-76 us on a handful of CTAs)
+  if (!c_bf16 && !g.relu && !g.relu_src && tiles < 148 && g.K >= 128) {
+    const int64_t want = cdiv(296, tiles), cap = g.K / 64;
     splitk = (int)(want < cap ? want : cap);
     if (splitk < 1) splitk = 1;
   }

@@ -237,6 +237,80 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const __grid_constant__ P
   }
 }
 
+// out_i = sum of up to 8 equally shaped tensors, for up to 16 outputs in one launch: the gradients
+// that flow into ONE activation from several consumers (a modality stream feeds three chains as
+// query and three as key/value source: others/realformer.py:232-257) - autograd would add them
+// pairwise, one launch per pair.  out may alias its first input.
+constexpr int SG_MAXO = 16, SG_MAXI = 8;
+struct SumTable {
+  void* out[SG_MAXO];
+  const void* in[SG_MAXO][SG_MAXI];
+  long long n[SG_MAXO];
+  int n_in[SG_MAXO];
+};
+template <typename T>
+__global__ void __launch_bounds__(256) sum_grouped_kernel(const __grid_constant__ SumTable t) {
+  constexpr int V = 16 / sizeof(T);
+  const int w = blockIdx.y;
+  pdl_wait();
+  pdl_trigger();
+  const long long n = t.n[w];
+  const int k = t.n_in[w];
+  T* __restrict__ out = static_cast<T*>(t.out[w]);
+  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * 256 * V) {
+    float acc[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.f;
+    if (i + V <= n) {
+      for (int q = 0; q < k; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(static_cast<const T*>(t.in[w][q]) + i);
+        const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] += to_f(e[j]);
+      }
+      uint4 o;
+      T* e = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int j = 0; j < V; ++j) e[j] = from_f<T>(acc[j]);
+      *reinterpret_cast<uint4*>(out + i) = o;
+    } else {
+      for (long long j = i; j < n; ++j) {
+        float a = 0.f;
+        for (int q = 0; q < k; ++q) a += to_f(static_cast<const T*>(t.in[w][q])[j]);
+        out[j] = from_f<T>(a);
+      }
+    }
+  }
+}
+
+template <typename T>
+int sum_grouped(int n_out, void* const* out, const int* n_in, const void* const* in,
+                const int64_t* numel, cudaStream_t st) {
+  if (n_out <= 0) return MMEMO_OK;
+  if (n_out > SG_MAXO) return MMEMO_ERR_ARG;
+  static thread_local SumTable t;
+  long long most = 0;
+  int pos = 0;
+  for (int i = 0; i < n_out; ++i) {
+    MM_REQUIRE(out[i] && n_in[i] >= 1 && n_in[i] <= SG_MAXI && numel[i] >= 0);
+    MM_REQUIRE((reinterpret_cast<uintptr_t>(out[i]) & 15) == 0);
+    t.out[i] = out[i]; t.n[i] = numel[i]; t.n_in[i] = n_in[i];
+    for (int q = 0; q < n_in[i]; ++q) {
+      MM_REQUIRE(in[pos] && (reinterpret_cast<uintptr_t>(in[pos]) & 15) == 0);
+      t.in[i][q] = in[pos++];
+    }
+    most = numel[i] > most ? numel[i] : most;
+  }
+  if (most == 0) return MMEMO_OK;
+  long long bx = cdiv(most, 256 * (16 / (long long)sizeof(T)));
+  const long long cap = cdiv(148 * 8, n_out);
+  if (bx > cap) bx = cap;
+  MM_CUDA_OK(mm_launch(sum_grouped_kernel<T>, dim3((unsigned)bx, (unsigned)n_out), dim3(256), 0, st,
+                       t));
+  return MMEMO_OK;
+}
+
 template <typename T>
 int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
            cudaStream_t st) {
@@ -321,6 +395,14 @@ int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const
   MM_CUDA_OK(mm_launch(cast_multi_kernel, dim3((unsigned)bx, (unsigned)count), dim3(256), 0,
                        mm_stream(s), t));
   return MMEMO_OK;
+}
+int mmemo_sum_grouped_f32(int n_out, void* const* out, const int* n_in, const void* const* in,
+                          const int64_t* numel, mmemo_stream_t s) {
+  return sum_grouped<float>(n_out, out, n_in, in, numel, mm_stream(s));
+}
+int mmemo_sum_grouped_bf16(int n_out, void* const* out, const int* n_in, const void* const* in,
+                           const int64_t* numel, mmemo_stream_t s) {
+  return sum_grouped<bf16>(n_out, out, n_in, in, numel, mm_stream(s));
 }
 int mmemo_cast_pad_f32_to_bf16_multi(int count, const float* const* src, const int64_t* lds,
                                      void* const* dst, const int64_t* ldd, const int64_t* M,

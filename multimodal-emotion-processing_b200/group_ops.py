@@ -107,6 +107,40 @@ def colsum_group(bf16: bool, xs, outs):
         ops._rowsum(bf16, x.reshape(-1, N), o)
 
 
+def merge_shared_grads(bf16: bool, inputs, grads):
+    """``grads[i]`` is the gradient of ``inputs[i]`` (None = undefined).  Entries whose inputs are
+    the SAME tensor (a modality stream is the query of three chains and the source of three) are
+    summed into the first one's buffer with one grouped launch; the other entries become None, so
+    autograd receives one gradient per distinct tensor instead of adding them pairwise."""
+    groups = {}
+    for i, (x, gx) in enumerate(zip(inputs, grads)):
+        if gx is not None:
+            groups.setdefault((x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype), []).append(i)
+    multi = [ix for ix in groups.values() if len(ix) > 1]
+    if not multi:
+        return list(grads)
+    out = list(grads)
+    todo = []
+    for ix in multi:
+        gs = [grads[i] for i in ix]
+        if len(ix) > 8 or not all(g_.is_contiguous() and g_.dtype == gs[0].dtype and
+                                  g_.data_ptr() % 16 == 0 for g_ in gs):
+            tot = gs[0]
+            for g_ in gs[1:]:
+                tot = tot + g_
+            out[ix[0]] = tot
+        else:
+            todo.append(gs)
+        for i in ix[1:]:
+            out[i] = None
+    for part in [todo[i:i + 16] for i in range(0, len(todo), 16)]:
+        name = f"mmemo_sum_grouped_{'bf16' if part[0][0].dtype == BF else 'f32'}"
+        _call(name, len(part), _vpa([gs[0] for gs in part]), _arr(C.c_int, [len(gs) for gs in part]),
+              _vpa([g_ for gs in part for g_ in gs]), _arr(C.c_int64, [gs[0].numel() for gs in part]),
+              _stream())
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # grouped attention core
 # ------------------------------------------------------------------------------------------------
@@ -339,9 +373,12 @@ def trunk_full_bwd_op(dh2s: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Se
                   (dqps[g].view(-1, d), qs[g].view(-1, d), w[0]),
                   (dkvps[g].view(-1, 2 * d), kvs[g].view(-1, d), w[1])]
     ops._linear_bwd_w_group(bf16, items, zeroed=True)
+    # one gradient per distinct input tensor (shared modality streams): grouped sum, not autograd adds
+    merged = merge_shared_grads(bf16, list(qs) + list(kvs), list(dqs) + list(dkvs))
+    dqs, dkvs = merged[:G], merged[G:]
     out = []
     for g in range(G):
-        out += [dqs[g], dkvs[g] if dkvs[g] is not None else _e(dev),
+        out += [dqs[g] if dqs[g] is not None else _e(dev), dkvs[g] if dkvs[g] is not None else _e(dev),
                 dsps[g] if dsps[g] is not None else _e(dev)]
     return out + [zall]
 
@@ -383,7 +420,7 @@ def _trunk_full_backward(ctx, grads):
     dqs, dkvs, dsps, pgrads = [], [], [], []
     for g in range(G):
         dq, dkv, dsp = res[3 * g:3 * g + 3]
-        dqs.append(dq)
+        dqs.append(dq if dq.numel() else None)
         dkvs.append(dkv if dkv.numel() else None)
         dsps.append(dsp if dsp.numel() else None)
         dp2, dp1, db_f2, db_f1, dc, ws = _full_zviews(zall[g * zlen:(g + 1) * zlen], d, dff)
@@ -518,9 +555,13 @@ def trunk_lite_bwd_op(douts: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: S
                   (dys[g].view(-1, d), qs[g].view(-1, d), dwm[:, :d]),
                   (dys[g].view(-1, d), xs[g].view(-1, d), dwm[:, d:])]
     ops._linear_bwd_w_group(bf16, items, zeroed=True)
+    merged = merge_shared_grads(bf16, list(qs) + list(kvs),
+                                list(dqs) + [t if t.numel() else None for t in dkv_out])
+    dqs, dkvs = merged[:G], merged[G:]
     out = []
     for g in range(G):
-        out += [dqs[g], dkv_out[g], dsps[g] if dsps[g] is not None else _e(dev)]
+        out += [dqs[g] if dqs[g] is not None else _e(dev), dkvs[g] if dkvs[g] is not None else _e(dev),
+                dsps[g] if dsps[g] is not None else _e(dev)]
     return out + [zall]
 
 
@@ -559,7 +600,7 @@ def _trunk_lite_backward(ctx, grads):
     dqs, dkvs, dsps, pgrads = [], [], [], []
     for g in range(G):
         dq, dkv, dsp = res[3 * g:3 * g + 3]
-        dqs.append(dq)
+        dqs.append(dq if dq.numel() else None)
         dkvs.append(dkv if dkv.numel() else None)
         dsps.append(dsp if dsp.numel() else None)
         dpn, dc, dwo, dwm = _lite_zviews(zall[g * zlen:(g + 1) * zlen], d)

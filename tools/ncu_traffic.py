@@ -38,8 +38,13 @@ def main(path, workload):
              "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}
     fam = {}
     for (_, name), m in per.items():
-        f = fam.setdefault(name, dict(n=0, us=0.0, rd=0.0, wr=0.0))
-        f["n"] += 1
+        # "family/kernel name" when the launch ran inside an NVTX range (every libmmemo launch does)
+        family, _, kern = name.partition("/")
+        f = fam.setdefault(family, dict(n=0, us=0.0, rd=0.0, wr=0.0, kernels={}))
+        kern = kern.split("(")[0].split("<")[0] if "<unnamed>::" in kern.split("<")[0] + "<" else kern
+        kern = kern.replace("void ", "").replace("<unnamed>::", "").split("<")[0]   # instantiations count together
+        f["kernels"][kern] = f["kernels"].get(kern, 0) + 1
+        f["n"] = max(f["kernels"].values())        # C-ABI calls = launches of the family's main kernel
         v, u = m.get("gpu__time_duration.sum", (0.0, "us"))
         f["us"] += v * scale.get(u, 1.0)
         v, u = m.get("dram__bytes_read.sum", (0.0, "byte"))
@@ -51,11 +56,12 @@ def main(path, workload):
     with open(out, "w") as fh:
         fh.write(f"# {workload}: one eager step under ncu (cold caches, serialised launches: compare "
                  f"SHARES, not absolute times); source {os.path.basename(path)}\n")
-        fh.write(f"# kernel family (NVTX range of the launching C-ABI call)   launches   us/launch   "
-                 f"share   DRAM read MB/launch   DRAM write MB/launch\n")
+        fh.write(f"# kernel family (NVTX range of the launching C-ABI call; unnamed = torch kernels)   calls   "
+                 f"us/call   share   DRAM read MB/call   DRAM write MB/call   kernels in the range\n")
         for name, f in sorted(fam.items(), key=lambda kv: -kv[1]["us"]):
-            fh.write(f"{name[:110]:110s} {f['n']:4d} {f['us'] / f['n']:9.1f} {f['us'] / total:7.3f} "
-                     f"{f['rd'] / f['n'] / 1e6:9.2f} {f['wr'] / f['n'] / 1e6:9.2f}\n")
+            kern = ", ".join(k[:48] for k in f["kernels"] if k)
+            fh.write(f"{name[:96]:96s} {f['n']:4d} {f['us'] / f['n']:9.1f} {f['us'] / total:7.3f} "
+                     f"{f['rd'] / f['n'] / 1e6:9.2f} {f['wr'] / f['n'] / 1e6:9.2f}   {kern}\n")
         fh.write(f"# total device time of the step's kernels: {total:.1f} us\n")
     tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     data = json.load(open(tj)) if os.path.isfile(tj) else {"families": {}, "source": {}}
