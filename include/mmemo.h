@@ -269,6 +269,15 @@ int mmemo_cast_bf16_to_f32(const void* src, float* dst, int64_t n, mmemo_stream_
  * whole trunk layer */
 int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const* dst,
                                  const int64_t* n, mmemo_stream_t stream);
+/* *out (float32 device scalar, zero-initialised by the caller) += mean(x^2) over n contiguous
+ * elements; dx = dloss[0] * 2 x / n.  The synthetic loss of the encoder benchmark (BASELINE config 2
+ * has no head of its own) as one launch per direction instead of six eager ATen kernels. */
+int mmemo_sqmean_fwd_f32(const void* x, int64_t n, float* out, mmemo_stream_t stream);
+int mmemo_sqmean_fwd_bf16(const void* x, int64_t n, float* out, mmemo_stream_t stream);
+int mmemo_sqmean_bwd_f32(const void* x, const float* dloss, int64_t n, void* dx,
+                         mmemo_stream_t stream);
+int mmemo_sqmean_bwd_bf16(const void* x, const float* dloss, int64_t n, void* dx,
+                          mmemo_stream_t stream);
 /* out[i] = sum of n_in[i] (<= 8) equally sized contiguous tensors, for n_out <= 16 outputs in one
  * launch (`in` = the inputs of all outputs, concatenated; out[i] may alias its first input): the
  * gradients reaching one modality stream from the chains that read it (others/realformer.py:232-257),

@@ -70,6 +70,9 @@ SIGNATURES = {
     "mmemo_cast_f32_to_bf16": [_vp, _vp, _i64, _vp],
     "mmemo_cast_bf16_to_f32": [_vp, _vp, _i64, _vp],
     "mmemo_cast_f32_to_bf16_multi": [_i32, _vp, _vp, _vp, _vp],
+    "mmemo_sqmean_fwd_f32": [_vp, _i64, _vp, _vp], "mmemo_sqmean_fwd_bf16": [_vp, _i64, _vp, _vp],
+    "mmemo_sqmean_bwd_f32": [_vp, _vp, _i64, _vp, _vp],
+    "mmemo_sqmean_bwd_bf16": [_vp, _vp, _i64, _vp, _vp],
     "mmemo_sum_grouped_f32": [_i32, _vp, _vp, _vp, _vp, _vp],
     "mmemo_sum_grouped_bf16": [_i32, _vp, _vp, _vp, _vp, _vp],
     "mmemo_cast_pad_f32_to_bf16_multi": [_i32] + [_vp] * 6 + [_vp],

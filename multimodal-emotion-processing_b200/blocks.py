@@ -44,7 +44,11 @@ def is_bf16() -> bool:
 def as_act(x: torch.Tensor) -> torch.Tensor:
     """Cast an activation to the compute dtype of the current precision mode."""
     want = torch.bfloat16 if _STATE["bf16"] else torch.float32
-    return x if x.dtype == want else x.to(want)
+    if x.dtype == want:
+        return x
+    if want == torch.bfloat16 and x.dtype == torch.float32 and x.is_cuda and not x.requires_grad:
+        return ops.cast_bf16(x)          # raw inputs: libmmemo's vector cast
+    return x.to(want)
 
 
 def as_mask(m: Optional[torch.Tensor]) -> Optional[torch.Tensor]:

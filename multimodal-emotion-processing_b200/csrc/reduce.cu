@@ -311,6 +311,62 @@ int sum_grouped(int n_out, void* const* out, const int* n_in, const void* const*
   return MMEMO_OK;
 }
 
+// mean(x^2) and its gradient (the loss of the encoder benchmark / a plain L2 activation penalty):
+// one launch each instead of a cast, a pow, a reduction and their three autograd kernels.
+template <typename T>
+__global__ void __launch_bounds__(256) sqmean_fwd_kernel(const T* __restrict__ x, long long n,
+                                                         float scale, float* __restrict__ out) {
+  constexpr int V = 16 / sizeof(T);
+  __shared__ float red[8];
+  pdl_wait();
+  pdl_trigger();
+  float acc = 0.f;
+  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * 256 * V) {
+    if (i + V <= n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + i);
+      const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc = fmaf(to_f(e[j]), to_f(e[j]), acc);
+    } else {
+      for (long long j = i; j < n; ++j) acc = fmaf(to_f(x[j]), to_f(x[j]), acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t * scale);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) sqmean_bwd_kernel(const T* __restrict__ x,
+                                                         const float* __restrict__ dloss,
+                                                         long long n, float scale,
+                                                         T* __restrict__ dx) {
+  constexpr int V = 16 / sizeof(T);
+  pdl_wait();
+  pdl_trigger();
+  const float g = dloss[0] * scale;
+  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * 256 * V) {
+    if (i + V <= n) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + i);
+      const T* e = reinterpret_cast<const T*>(&v);
+      uint4 o;
+      T* d = reinterpret_cast<T*>(&o);
+#pragma unroll
+      for (int j = 0; j < V; ++j) d[j] = from_f<T>(g * to_f(e[j]));
+      *reinterpret_cast<uint4*>(dx + i) = o;
+    } else {
+      for (long long j = i; j < n; ++j) dx[j] = from_f<T>(g * to_f(x[j]));
+    }
+  }
+}
+
 template <typename T>
 int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t period,
            cudaStream_t st) {
@@ -394,6 +450,47 @@ int mmemo_cast_f32_to_bf16_multi(int count, const float* const* src, void* const
   if (bx < 1) bx = 1;
   MM_CUDA_OK(mm_launch(cast_multi_kernel, dim3((unsigned)bx, (unsigned)count), dim3(256), 0,
                        mm_stream(s), t));
+  return MMEMO_OK;
+}
+/* *out (float32, zero-initialised by the caller) += mean(x^2);  dx = dloss * 2 x / n */
+int mmemo_sqmean_fwd_bf16(const void* x, int64_t n, float* out, mmemo_stream_t s) {
+  if (n <= 0) return MMEMO_OK;
+  MM_REQUIRE(x && out && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  int64_t bx = cdiv(n, 256 * 8);
+  if (bx > 148 * 4) bx = 148 * 4;
+  MM_CUDA_OK(mm_launch(sqmean_fwd_kernel<bf16>, dim3((unsigned)bx), dim3(256), 0, mm_stream(s),
+                       static_cast<const bf16*>(x), (long long)n, 1.0f / (float)n, out));
+  return MMEMO_OK;
+}
+int mmemo_sqmean_fwd_f32(const void* x, int64_t n, float* out, mmemo_stream_t s) {
+  if (n <= 0) return MMEMO_OK;
+  MM_REQUIRE(x && out && (reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  int64_t bx = cdiv(n, 256 * 4);
+  if (bx > 148 * 4) bx = 148 * 4;
+  MM_CUDA_OK(mm_launch(sqmean_fwd_kernel<float>, dim3((unsigned)bx), dim3(256), 0, mm_stream(s),
+                       static_cast<const float*>(x), (long long)n, 1.0f / (float)n, out));
+  return MMEMO_OK;
+}
+int mmemo_sqmean_bwd_bf16(const void* x, const float* dloss, int64_t n, void* dx, mmemo_stream_t s) {
+  if (n <= 0) return MMEMO_OK;
+  MM_REQUIRE(x && dloss && dx && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  int64_t bx = cdiv(n, 256 * 8);
+  if (bx > 148 * 8) bx = 148 * 8;
+  MM_CUDA_OK(mm_launch(sqmean_bwd_kernel<bf16>, dim3((unsigned)bx), dim3(256), 0, mm_stream(s),
+                       static_cast<const bf16*>(x), dloss, (long long)n, 2.0f / (float)n,
+                       static_cast<bf16*>(dx)));
+  return MMEMO_OK;
+}
+int mmemo_sqmean_bwd_f32(const void* x, const float* dloss, int64_t n, void* dx, mmemo_stream_t s) {
+  if (n <= 0) return MMEMO_OK;
+  MM_REQUIRE(x && dloss && dx && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(dx) & 15) == 0);
+  int64_t bx = cdiv(n, 256 * 4);
+  if (bx > 148 * 8) bx = 148 * 8;
+  MM_CUDA_OK(mm_launch(sqmean_bwd_kernel<float>, dim3((unsigned)bx), dim3(256), 0, mm_stream(s),
+                       static_cast<const float*>(x), dloss, (long long)n, 2.0f / (float)n,
+                       static_cast<float*>(dx)));
   return MMEMO_OK;
 }
 int mmemo_sum_grouped_f32(int n_out, void* const* out, const int* n_in, const void* const* in,

@@ -1168,6 +1168,49 @@ rdrop_kl_op.register_autograd(_rk_backward, setup_context=_rk_setup)
 
 
 # ------------------------------------------------------------------------------------------------
+# mean(x^2) (the encoder benchmark's synthetic loss) — one launch per direction
+# ------------------------------------------------------------------------------------------------
+@torch.library.custom_op("mmemo::sq_mean", mutates_args=())
+def sq_mean_op(x: Tensor) -> Tensor:
+    _need_cuda(x)
+    x = x.contiguous()
+    out = torch.zeros((), dtype=F32, device=x.device)
+    _call(f"mmemo_sqmean_fwd_{_sfx(x.dtype == BF)}", x.data_ptr(), x.numel(), out.data_ptr(),
+          _stream())
+    return out
+
+
+@torch.library.custom_op("mmemo::sq_mean_bwd", mutates_args=())
+def sq_mean_bwd_op(dloss: Tensor, x: Tensor) -> Tensor:
+    x = x.contiguous()
+    dx = torch.empty_like(x)
+    _call(f"mmemo_sqmean_bwd_{_sfx(x.dtype == BF)}", x.data_ptr(),
+          dloss.to(F32).contiguous().data_ptr(), x.numel(), dx.data_ptr(), _stream())
+    return dx
+
+
+def _sq_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+
+
+def _sq_backward(ctx, dloss):
+    (x,) = ctx.saved_tensors
+    return sq_mean_bwd_op(dloss, x)
+
+
+sq_mean_op.register_autograd(_sq_backward, setup_context=_sq_setup)
+
+
+def cast_bf16(x: Tensor) -> Tensor:
+    """float32 -> bf16 copy of a tensor that needs no gradient (raw inputs), libmmemo's vector
+    cast instead of ATen's generic copy kernel."""
+    x = x.contiguous()
+    y = torch.empty(x.shape, dtype=BF, device=x.device)
+    _call("mmemo_cast_f32_to_bf16", x.data_ptr(), y.data_ptr(), x.numel(), _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
 # dropout (counter-based; forward and backward are the same kernel with the same seed)
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("mmemo::dropout", mutates_args=())

@@ -100,3 +100,32 @@ def test_shard_batch_nested():
     b = {"inputs": [torch.arange(8), torch.arange(16).view(8, 2)], "label": torch.arange(8)}
     s = dp.shard_batch(b, 1, 2, align=2)
     assert s["inputs"][0].tolist() == [4, 5, 6, 7] and s["inputs"][1].shape == (4, 2)
+
+
+def test_grad_reducer_refuses_gradient_accumulation():
+    """after a step p.grad is a view of its all-reduce bucket (already averaged); a
+    second backward() without zero_grad(set_to_none=True) would re-reduce the old contribution.
+    The reducer raises instead of training on silently wrong gradients."""
+    import socket
+    import pytest
+    import torch
+    import torch.distributed as dist
+    from mmemo_b200 import dp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        model = torch.nn.Linear(4, 3)
+        red = dp.GradReducer(model, world_size=2, bucket_bytes=1 << 10)
+        x = torch.randn(5, 4)
+        red.backward(model(x).sum())              # first step: discovers the buckets
+        model.zero_grad(set_to_none=True)
+        red.backward(model(x).sum())
+        with pytest.raises(RuntimeError, match="zero_grad"):
+            red.backward(model(x).sum())          # grads of the previous step still attached
+        model.zero_grad(set_to_none=True)
+        red.backward(model(x).sum())              # fine again
+    finally:
+        dist.destroy_process_group()

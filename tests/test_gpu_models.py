@@ -245,8 +245,9 @@ def test_cfg4_renmme_full_batch_256_with_rdrop_loss():
     assert set(grads) == set(ref_grads)
     worst = max((rel_err(grads[k], v), k) for k, v in ref_grads.items())
     assert worst[0] < TOL32, worst
-    # R-Drop pairs carry identical inputs and dropout is off -> identical logits
-    assert torch.equal(logits[0::2], logits[1::2])
+    # R-Drop pairs carry identical inputs and dropout is off -> the same logits (to the fp32
+    # summation order of the split-K classifier GEMM, whose slices are added by atomics)
+    assert torch.allclose(logits[0::2], logits[1::2], rtol=0, atol=2e-6)
     with mmemo_b200.precision("bf16"):
         logits_bf, _, grads_bf, _ = cases.run_module_with_grads(m, c, to_dev(b), Loss)
     assert rel_err(logits_bf.float(), ref_logits) < TOLBF

@@ -347,3 +347,20 @@ def test_unsupported_shape_fails_loudly():
     q = torch.zeros(1, 4, 2 * 200, device=DEV)
     with pytest.raises(RuntimeError):
         ops.resattn_op(q, q, q, None, None, None, 2)   # hd = 200 > 128
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(64, 128, 512), (3, 7, 5), (1,)])
+def test_sq_mean_loss(shape, dt):
+    """mean(x^2) and its gradient (bench.py's synthetic loss) vs torch."""
+    x = rnd(g(9), *shape).to(dt)
+    xr = x.float().requires_grad_(True)
+    ref = (xr ** 2).mean()
+    (ref * 1.7).backward()
+    xc = x.to(DEV).requires_grad_(True)
+    out = ops.sq_mean_op(xc)
+    (out * 1.7).backward()
+    tol = 1e-5 if dt == torch.float32 else 1e-2
+    assert abs(out.item() - ref.item()) <= tol * max(1.0, abs(ref.item()))
+    assert xc.grad.dtype == dt
+    assert rel_err(xc.grad.float(), xr.grad) < tol
