@@ -194,6 +194,9 @@ int mmemo_resattn_bwd_grouped_bf16(int n, const mmemo_attn_problem* problems, mm
 /* 1 if the problem shape (pointers may be dummy non-null, 16-byte aligned) is served by the
  * mma.sync kernels; bwd != 0 asks about the backward */
 int mmemo_resattn_uses_mma(int64_t Lq, int64_t Lk, int64_t hd, int64_t ld, int same_kv, int bwd);
+/* Which bf16 kernel family a shape runs on: 3 = tcgen05 single tile (L = 128), 2 = tcgen05 tiled
+ * (Lk = 256), 1 = mma.sync, 0 = SIMT.  Used by the benchmarks' tables and the routing tests. */
+int mmemo_resattn_kernel_path(int64_t Lq, int64_t Lk, int64_t hd, int64_t ld, int bwd);
 
 /* ---------------------------------------------------------------------------------------------
  * Gated residual + LayerNorm (+ReLU).  y = act( LN( res + gate * x ) * gamma + beta ), eps 1e-5.

@@ -59,6 +59,7 @@ SIGNATURES = {
     "mmemo_resattn_fwd_grouped_bf16": [_i32, _vp, _vp],
     "mmemo_resattn_bwd_grouped_bf16": [_i32, _vp, _vp],
     "mmemo_resattn_uses_mma": [_i64, _i64, _i64, _i64, _i32, _i32],
+    "mmemo_resattn_kernel_path": [_i64, _i64, _i64, _i64, _i32],
     "mmemo_add_ln_fwd_f32": _LN_FWD, "mmemo_add_ln_fwd_bf16": _LN_FWD,
     "mmemo_add_ln_bwd_f32": _LN_BWD, "mmemo_add_ln_bwd_bf16": _LN_BWD,
     "mmemo_add_ln_fwd_grouped_f32": [_i32] + [_vp] * 9 + [_i64, _f32, _i32, _vp],

@@ -27,6 +27,8 @@
 // persistent grid; work items are numbered problem by problem.  The kernel is launched with
 // programmatic stream serialization: its prologue runs while the previous kernel drains
 // (griddepcontrol.wait before the first global access).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm.h"
 #include "tc_common.cuh"
@@ -508,6 +510,20 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
   // CTA pairs (256 x 256 tiles) when every output is wide and tall enough to fill them
   bool cta2 = true;
   for (int i = 0; i < n; ++i) cta2 = cta2 && gs[i].N >= 256 && gs[i].M >= 256;
+  {
+    // experiment hook: MMEMO_GEMM_CTA2=0 forces single-CTA 128 x 128 tiles, =N (> 1) uses them
+    // when the launch has fewer than N pair tiles per CTA pair
+    const char* env = getenv("MMEMO_GEMM_CTA2");
+    if (env && cta2) {
+      const int v = atoi(env);
+      if (v == 0) cta2 = false;
+      else if (v > 1) {
+        long pt = 0;
+        for (int i = 0; i < n; ++i) pt += cdiv(gs[i].M, 256) * cdiv(gs[i].N, 256);
+        if (pt * 100 < (long)v * (num_sms() / 2)) cta2 = false;   // v = percent of one pair wave
+      }
+    }
+  }
   const int TM = cta2 ? 256 : 128, BN = cta2 ? 256 : 128;
   const int sms = num_sms();
   const int units_max = cta2 ? sms / 2 : sms;      // schedulable work units (pairs or CTAs)

@@ -31,6 +31,13 @@ int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const
                    const float* c, void* s_out, void* o, int64_t ldo, float* lse, int64_t B,
                    int64_t H, int64_t Lq, int64_t Lk, int64_t hd, cudaStream_t st);
 
+// tcgen05 / TMA path for the long-sequence shapes (bf16, hd == 64, Lk == 256, Lq in {128, 256})
+bool resattn_tc2_supported(const mmemo_attn_problem& a, bool bwd);
+int resattn_fwd_tc2(const mmemo_attn_problem& a, cudaStream_t st);
+int resattn_bwd_tc2(const mmemo_attn_problem& a, cudaStream_t st);
+// L2 prefetch distance (CTAs) for the one-CTA-per-SM attention kernels: the SM count, or MMEMO_ATTN_PF
+int resattn_pf_distance();
+
 // mma.sync (m16n8k16 bf16) path: hd in {16, 32, 64}, any L that fits shared memory; grouped
 bool resattn_mma_supported(const mmemo_attn_problem& a, bool bwd);
 int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st);

@@ -42,6 +42,7 @@ struct FwdArgs {
   float* stat;         // (B, H, Lq, 2)
   int H;
   int has_prev, write_s;
+  int pf_dist;   // L2-prefetch the tile of CTA (linear id + pf_dist); 0 = off
   float sqrt_hd;
   uint32_t idesc_qk, idesc_pv;
 };
@@ -114,6 +115,18 @@ resattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
       tc::mbar_expect_tx(bar_v, TILE_QKV);
       tc::tma_load_2d(base + OFF_V, &tmV, h * HD, row0, bar_v);
+      // pull the tile of the CTA that follows on this SM (about one wave ahead) into L2
+      const int nxt = blockIdx.y * gridDim.x + blockIdx.x + a.pf_dist;
+      if (a.pf_dist > 0 && nxt < (int)(gridDim.x * gridDim.y)) {
+        const int h2 = nxt % gridDim.x, b2 = nxt / gridDim.x;
+        if (a.has_prev) {
+          tc::tma_prefetch_2d(&tmSprev, 0, (b2 * a.H + h2) * L);
+          tc::tma_prefetch_2d(&tmSprev, 64, (b2 * a.H + h2) * L);
+        }
+        tc::tma_prefetch_2d(&tmQ, h2 * HD, b2 * L);
+        tc::tma_prefetch_2d(&tmK, h2 * HD, b2 * L);
+        tc::tma_prefetch_2d(&tmV, h2 * HD, b2 * L);
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -301,6 +314,7 @@ int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const
   a.mask = mask; a.mask_bs = mask_bs; a.c = c; a.stat = lse; a.H = (int)H;
   a.has_prev = s_prev != nullptr; a.write_s = s_out != nullptr;
   a.sqrt_hd = (float)sqrt((double)hd);
+  a.pf_dist = 2 * resattn_pf_distance();   // two CTAs per SM
   a.idesc_qk = tc::idesc_bf16(L, L, 0, 0);
   a.idesc_pv = tc::idesc_bf16(L, HD, 0, 1);
   dim3 grid((unsigned)H, (unsigned)B);
@@ -338,6 +352,7 @@ struct BwdArgs {
   float* dc;
   int H;
   int has_s, has_prev, has_dsn, write_dsp;
+  int pf_dist;
   float sqrt_hd;
   uint32_t idesc_nn128, idesc_tt64, idesc_nt64;
 };
@@ -425,6 +440,26 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tc::mbar_expect_tx(bar_dsn, TILE_S);
         tc::tma_load_2d(base + B_OFF_B, &tmDSn, 0, srow0, bar_dsn);
         tc::tma_load_2d(base + B_OFF_B + TILE_S / 2, &tmDSn, 64, srow0, bar_dsn);
+      }
+      const int nxt = blockIdx.y * gridDim.x + blockIdx.x + a.pf_dist;
+      if (a.pf_dist > 0 && nxt < (int)(gridDim.x * gridDim.y)) {
+        const int h2 = nxt % gridDim.x, b2 = nxt / gridDim.x, sr2 = (b2 * a.H + h2) * L;
+        tc::tma_prefetch_2d(&tmDO, h2 * HD, b2 * L);
+        tc::tma_prefetch_2d(&tmV, h2 * HD, b2 * L);
+        tc::tma_prefetch_2d(&tmQ, h2 * HD, b2 * L);
+        tc::tma_prefetch_2d(&tmK, h2 * HD, b2 * L);
+        if (a.has_s) {
+          tc::tma_prefetch_2d(&tmS, 0, sr2);
+          tc::tma_prefetch_2d(&tmS, 64, sr2);
+        }
+        if (a.has_prev) {
+          tc::tma_prefetch_2d(&tmSprev, 0, sr2);
+          tc::tma_prefetch_2d(&tmSprev, 64, sr2);
+        }
+        if (a.has_dsn) {
+          tc::tma_prefetch_2d(&tmDSn, 0, sr2);
+          tc::tma_prefetch_2d(&tmDSn, 64, sr2);
+        }
       }
     }
   } else if (warp == 1) {
@@ -643,6 +678,7 @@ int resattn_bwd_tc(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
   a.has_s = s != nullptr; a.has_prev = s_prev != nullptr; a.has_dsn = ds_next != nullptr;
   a.write_dsp = ds_prev != nullptr;
   a.sqrt_hd = 8.0f;
+  a.pf_dist = resattn_pf_distance();
   a.idesc_nn128 = tc::idesc_bf16(L, L, 0, 0);
   a.idesc_tt64 = tc::idesc_bf16(L, HD, 1, 1);
   a.idesc_nt64 = tc::idesc_bf16(L, HD, 0, 1);

@@ -354,10 +354,10 @@ def test_unsupported_shape_fails_loudly():
 def test_sq_mean_loss(shape, dt):
     """mean(x^2) and its gradient (bench.py's synthetic loss) vs torch."""
     x = rnd(g(9), *shape).to(dt)
-    xr = x.float().requires_grad_(True)
+    xr = x.float().clone().requires_grad_(True)
     ref = (xr ** 2).mean()
     (ref * 1.7).backward()
-    xc = x.to(DEV).requires_grad_(True)
+    xc = x.detach().clone().to(DEV).requires_grad_(True)
     out = ops.sq_mean_op(xc)
     (out * 1.7).backward()
     tol = 1e-5 if dt == torch.float32 else 1e-2
