@@ -39,7 +39,7 @@ constexpr int BM = 128, BK = 64, STAGES = 5;
 constexpr uint32_t A_TILE = BM * BK * 2, B_TILE = 128 * BK * 2;   // per CTA per stage: 16 KB + 16 KB
 constexpr uint32_t RING = STAGES * (A_TILE + B_TILE);             // 160 KB
 constexpr uint32_t OUT_BYTES = 64 * 1024;    // fp32 staging (128x128), or bf16 staging + aux tile
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;   // TMA warp, MMA warp, two epilogue warpgroups
 constexpr uint32_t SMEM_BYTES = RING + OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
 constexpr int AUX_NONE = 0, AUX_ACC = 1, AUX_RELU = 2;
 
@@ -69,6 +69,7 @@ constexpr int MAXG_SMALL = 6, MAXG = 48;
 template <int NG> struct TmapGroup { CUtensorMap a[NG], b[NG], c[NG], aux[NG]; };
 template <int NG> struct GroupArgs {
   int n;
+  int any_aux;             // some problem of the launch prefetches an aux tile (owns the second 32 KB)
   int item_start[NG + 1];
   TcArgs p[NG];
 };
@@ -218,8 +219,10 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
       }
     }
   } else {
-    // ================= epilogue: warps 2..5, TMEM lane quarter = warp % 4 =================
+    // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4; the two warpgroups split every
+    // 128-column half (64 columns = one bf16 staging panel each), so thread = (row, column half) =====
     const int quarter = warp & 3;
+    const int cgp = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;
     const int te = threadIdx.x - 64;
     // step = (work item, 128-column half); aux tile of a step: old C (accumulate) or the saved
@@ -236,7 +239,8 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
       tc::tma_load_2d(sAux + 16384, &TMS.aux[g], n0 + half * 128 + 64, m0, bar_aux);
     };
     if (te == 0 && unit < total) issue_aux(unit, 0);
-    uint32_t ti = 0, aux_ctr = 0;
+    uint32_t ti = 0, aux_ctr = 0, step = 0;
+    bool prev_f32 = true;          // the previous step's store may span both staging buffers
     int g = 0;
     for (int w = unit; w < total; w += units, ++ti) {
       int lw, m0, n0, sp, tile;
@@ -252,16 +256,26 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
       tc::mbar_wait(bar_accf + 8 * buf, aph);
       tc::tc_fence_after();
 #pragma unroll 1
-      for (int half = 0; half < NHALF; ++half) {
+      for (int half = 0; half < NHALF; ++half, ++step) {
         const int nh = n0 + half * 128;                  // first column of this half
-        if (te == 0) tc::tma_store_wait_read();          // previous store has left the staging tile
-        if (a.bias) sbias[te] = (nh + te < a.N) ? __ldg(a.bias + nh + te) : 0.f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // bf16 tiles (32 KB) alternate between the two 32 KB staging buffers when no problem of
+        // the launch needs the second one for aux tiles: the store of the previous step may then
+        // still be reading its buffer while this step fills the other one
+        const bool alt = !out_f32 && !G.any_aux;
+        const uint32_t sO = sOut + ((alt && (step & 1)) ? 32 * 1024 : 0);
+        if (te == 0) {
+          if (alt && !prev_f32) tc::tma_store_wait_read1();
+          else tc::tma_store_wait_read();                // previous store has left the staging tile
+        }
+        prev_f32 = out_f32;
+        if (a.bias && te < 128) sbias[te] = (nh + te < a.N) ? __ldg(a.bias + nh + te) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (a.aux) { tc::mbar_wait(bar_aux, aux_ctr & 1); ++aux_ctr; }
         const uint32_t taddr =
             tmem_base + buf * BN + half * 128 + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int ch = cgp * 2 + c2;
           uint32_t r[32];
           tc::tmem_ld32(taddr + ch * 32, r);
           tc::tmem_ld_wait();
@@ -307,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
 #pragma unroll
             for (int c = 0; c < 8; ++c)
               asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(
-                               sOut + ch * 16384 + tc::sw128_offset(row, c)),
+                               sO + ch * 16384 + tc::sw128_offset(row, c)),
                            "r"(r[4 * c]), "r"(r[4 * c + 1]), "r"(r[4 * c + 2]), "r"(r[4 * c + 3])
                            : "memory");
           } else {            // 2 panels of 64 bf16 columns
@@ -321,7 +335,7 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
                 pk[e] = *reinterpret_cast<uint32_t*>(&t);
               }
               asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(
-                               sOut + (ch >> 1) * 16384 + tc::sw128_offset(row, (ch & 1) * 4 + c)),
+                               sO + (ch >> 1) * 16384 + tc::sw128_offset(row, (ch & 1) * 4 + c)),
                            "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                            : "memory");
             }
@@ -329,7 +343,7 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
         }
         tc::tc_fence_before();
         tc::fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (te == 0) {
           if (half == NHALF - 1) {   // whole accumulator drained by this CTA -> tell the MMA issuer
             if (CTA2) tc::mbar_arrive_cta(bar_acce + 8 * buf, 0); else tc::mbar_arrive(bar_acce + 8 * buf);
@@ -337,19 +351,19 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
           if (partial && a.reduce_add) {   // C += slice, summed by the L2
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              if (nh + p * 32 < a.N) tc::tma_reduce_add_2d(tmC, sOut + p * 16384, nh + p * 32, m0);
+              if (nh + p * 32 < a.N) tc::tma_reduce_add_2d(tmC, sO + p * 16384, nh + p * 32, m0);
           } else if (partial) {   // workspace: [(tile*splits + split)*TM rows][BN fp32 columns]
             const int prow = (tile * a.splits + sp) * TM + (int)rank * BM;
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              tc::tma_store_2d(tmC, sOut + p * 16384, half * 128 + p * 32, prow);
+              tc::tma_store_2d(tmC, sO + p * 16384, half * 128 + p * 32, prow);
           } else if (out_f32) {
 #pragma unroll
             for (int p = 0; p < 4; ++p)
-              if (nh + p * 32 < a.N) tc::tma_store_2d(tmC, sOut + p * 16384, nh + p * 32, m0);
+              if (nh + p * 32 < a.N) tc::tma_store_2d(tmC, sO + p * 16384, nh + p * 32, m0);
           } else {
-            if (nh < a.N) tc::tma_store_2d(tmC, sOut, nh, m0);
-            if (nh + 64 < a.N) tc::tma_store_2d(tmC, sOut + 16384, nh + 64, m0);
+            if (nh < a.N) tc::tma_store_2d(tmC, sO, nh, m0);
+            if (nh + 64 < a.N) tc::tma_store_2d(tmC, sO + 16384, nh + 64, m0);
           }
           tc::tma_store_commit();
           // prefetch the aux tile of the next step (if that step has one)
@@ -603,6 +617,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     a.bias = partial ? nullptr : g.bias;
     a.pos = g.pos; a.pos_period = (int)g.pos_period;
     a.relu = g.relu; a.aux = aux;
+    if (aux != AUX_NONE) G.any_aux = 1;
     a.a_mn = a_mn; a.b_mn = b_mn;
     a.idesc = tc::idesc_bf16(TM, BN, a_mn, b_mn);
     a.splits = sp; a.kb_per = kb_per; a.kb_total = kb_total;

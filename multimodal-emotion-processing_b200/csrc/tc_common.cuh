@@ -103,6 +103,10 @@ __device__ __forceinline__ void tma_store_wait_all() {
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+// all but the most recent bulk group have finished reading shared memory
+__device__ __forceinline__ void tma_store_wait_read1() {
+  asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (TMA store / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
