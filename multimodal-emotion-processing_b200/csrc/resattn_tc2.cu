@@ -198,14 +198,15 @@ resattn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = col + q4 * 8 + e * 2;
+          const float2 mk = *reinterpret_cast<const float2*>(mask_s + j);
           float s0 = __uint_as_float(r[q4 * 8 + e * 2]) * 0.125f;       // == / sqrt(64), exact
           float s1 = __uint_as_float(r[q4 * 8 + e * 2 + 1]) * 0.125f;
           if (a.has_prev) {
             s0 = __fadd_rn(s0, __fmul_rn(cval, bf16_lo(pv[e])));
             s1 = __fadd_rn(s1, __fmul_rn(cval, bf16_hi(pv[e])));
           }
-          s0 = __fsub_rn(s0, mask_s[j]);
-          s1 = __fsub_rn(s1, mask_s[j + 1]);
+          s0 = __fsub_rn(s0, mk.x);
+          s1 = __fsub_rn(s1, mk.y);
           out[e] = pack_bf16(s0, s1);
           mx = fmaxf(mx, fmaxf(bf16_lo(out[e]), bf16_hi(out[e])));
         }
@@ -224,8 +225,8 @@ resattn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       lds128(base + F_OFF_S + off, sv);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const float e0 = exp2f((bf16_lo(sv[e]) - mx) * kLog2e);
-        const float e1 = exp2f((bf16_hi(sv[e]) - mx) * kLog2e);
+        const float e0 = tc::ex2((bf16_lo(sv[e]) - mx) * kLog2e);
+        const float e1 = tc::ex2((bf16_hi(sv[e]) - mx) * kLog2e);
         pe[e] = pack_bf16(e0, e1);
         sum += bf16_lo(pe[e]) + bf16_hi(pe[e]);
       }
@@ -554,6 +555,7 @@ resattn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int i0 = q4 * 8 + e * 2, j = kt * TL + col + i0;
+              const float2 mk = *reinterpret_cast<const float2*>(mask_s + j);
               float s0, s1;
               if (a.has_s) {
                 s0 = bf16_lo(sv[e]);
@@ -565,13 +567,13 @@ resattn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                   s0 = __fadd_rn(s0, __fmul_rn(cval, bf16_lo(sp[e])));
                   s1 = __fadd_rn(s1, __fmul_rn(cval, bf16_hi(sp[e])));
                 }
-                s0 = __fsub_rn(s0, mask_s[j]);
-                s1 = __fsub_rn(s1, mask_s[j + 1]);
+                s0 = __fsub_rn(s0, mk.x);
+                s1 = __fsub_rn(s1, mk.y);
                 const uint32_t rr = pack_bf16(s0, s1);   // the forward softmax saw bf16 scores
                 s0 = bf16_lo(rr);
                 s1 = bf16_hi(rr);
               }
-              const float p0 = exp2f((s0 - mx) * kLog2e) * inv, p1 = exp2f((s1 - mx) * kLog2e) * inv;
+              const float p0 = tc::ex2((s0 - mx) * kLog2e) * inv, p1 = tc::ex2((s1 - mx) * kLog2e) * inv;
               outp[e] = pack_bf16(p0, p1);
               float d0 = bf16_lo(outp[e]) * (__uint_as_float(dp[i0]) - Dq);
               float d1 = bf16_hi(outp[e]) * (__uint_as_float(dp[i0 + 1]) - Dq);

@@ -260,6 +260,14 @@ __host__ __device__ inline uint32_t idesc_bf16(int M, int N, int a_mn_major, int
   return d;
 }
 
+// 2^x as one MUFU.EX2 (exp2f() wraps it in a denormal-range rescale: a compare and two predicated
+// multiplies per call); results below 2^-126 flush to zero, 2^(-inf) = 0
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // byte offset of logical (row, 16-byte chunk) inside a [rows][128 B] SWIZZLE_128B tile whose base
 // is 1024-byte aligned (the layout TMA writes / reads and UMMA descriptors address)
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {
