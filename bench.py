@@ -620,9 +620,11 @@ def measure_robot_ensemble(dev, n_requests: int = 200, baselines: bool = True):
             pred = ens(*stat)
             out_host.copy_(pred, non_blocking=True)
             torch.cuda.current_stream().synchronize()
+        request()                                 # builds the request graph (warm-up + capture)
         n0 = ops.launch_count
-        request()
-        launches = ops.launch_count - n0          # launches captured into the request graph
+        with torch.no_grad():
+            ens._forward(stat)                    # one eager pass = what one graph replay launches
+        launches = ops.launch_count - n0
         ts = sorted(benchlib.time_wall(request, n_requests, 10))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()

@@ -91,14 +91,17 @@ int mmemo_linear_bwd_w_bf16(const void* dy, int64_t lddy, const void* x, int x_i
  * tensor-core launch (the Q and K|V projections of a block; its five weight gradients; the same
  * for all nine chains of a fusion-trunk layer at once), so that GEMMs too small to fill 148 SMs
  * share a wave.  All arrays are HOST arrays of length n.  Falls
- * back to n single launches when a problem does not meet the tensor-core kernel's constraints. */
+ * back to n single launches when a problem does not meet the tensor-core kernel's constraints.
+ * ldpos (nullable, entries 0 = N): row stride of pos[i], so that a problem can add a COLUMN SLICE
+ * of a wider position table (the reference concatenates three visual projections and then adds
+ * one table, robot_demo.py:304-311); y[i] / ldy[i] can address the matching slice of the output. */
 int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ldx,
                                   const void* const* w, const int64_t* ldw,
                                   const float* const* bias, void* const* y, const int64_t* ldy,
                                   const int64_t* M, const int64_t* N, const int64_t* K,
                                   const int* relu, const int* accumulate,
                                   const float* const* pos, const int64_t* pos_period,
-                                  mmemo_stream_t stream);
+                                  const int64_t* ldpos, mmemo_stream_t stream);
 int mmemo_linear_bwd_x_grouped_bf16(int n, const void* const* dy, const int64_t* lddy,
                                     const void* const* w, const int64_t* ldw, void* const* dx,
                                     const int64_t* lddx, const void* const* relu_src,

@@ -11,8 +11,9 @@ struct GemmArgs {
   int64_t sAm, sAk, sBn, sBk, ldc;
   int64_t M, N, K;
   const float* bias;       // [N] or null
-  const float* pos;        // [pos_period, N] or null
+  const float* pos;        // [pos_period, N] (row stride ldpos, 0 = N) or null
   int64_t pos_period;
+  int64_t ldpos;
   const void* relu_src;    // [M, N] (ldrelu) or null: C *= (relu_src > 0)
   int64_t ldrelu;
   int relu_src_bf16;

@@ -75,13 +75,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs g) {
       if (gridDim.z > 1) {  // split-K: linear epilogue terms once, atomics into a float32 C
         if (first_split) {
           if (g.bias) v += g.bias[n];
-          if (g.pos) v += g.pos[(m % g.pos_period) * g.N + n];
+          if (g.pos) v += g.pos[(m % g.pos_period) * (g.ldpos ? g.ldpos : g.N) + n];
         }
         atomicAdd(reinterpret_cast<float*>(C) + m * g.ldc + n, v);
         continue;
       }
       if (g.bias) v += g.bias[n];
-      if (g.pos) v += g.pos[(m % g.pos_period) * g.N + n];
+      if (g.pos) v += g.pos[(m % g.pos_period) * (g.ldpos ? g.ldpos : g.N) + n];
       if (g.relu) v = fmaxf(v, 0.f);
       if (g.relu_src) {
         const float r = g.relu_src_bf16

@@ -48,7 +48,7 @@ struct TcArgs {
   int c_bf16;              // output element type of the TMA store (0: fp32)
   const float* bias;
   const float* pos;
-  int pos_period;
+  int pos_period, pos_ld;
   int relu, aux;
   int a_mn, b_mn;
   uint32_t idesc;
@@ -286,7 +286,7 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
               r[i] = __float_as_uint(__uint_as_float(r[i]) + sbias[ch * 32 + i]);
           }
           if (a.pos && m < a.M) {   // position table row of this output row (period = seq length)
-            const float* prow = a.pos + (int64_t)pos_row * a.N + nh + ch * 32;
+            const float* prow = a.pos + (int64_t)pos_row * a.pos_ld + nh + ch * 32;
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (nh + ch * 32 + i < a.N)
@@ -616,6 +616,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     a.M = (int)g.M; a.N = (int)g.N; a.K = (int)g.K; a.c_bf16 = c_bf16;
     a.bias = partial ? nullptr : g.bias;
     a.pos = g.pos; a.pos_period = (int)g.pos_period;
+    a.pos_ld = (int)(g.ldpos ? g.ldpos : g.N);
     a.relu = g.relu; a.aux = aux;
     if (aux != AUX_NONE) G.any_aux = 1;
     a.a_mn = a_mn; a.b_mn = b_mn;

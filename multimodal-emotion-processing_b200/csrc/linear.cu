@@ -90,7 +90,7 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
                                   const int64_t* M, const int64_t* N, const int64_t* K,
                                   const int* relu, const int* accumulate,
                                   const float* const* pos, const int64_t* pos_period,
-                                  mmemo_stream_t s) {
+                                  const int64_t* ldpos, mmemo_stream_t s) {
   if (n < 1 || n > GEMM_TC_MAX_GROUP) return MMEMO_ERR_ARG;
   GemmArgs g[GEMM_TC_MAX_GROUP] = {};
   int cb[GEMM_TC_MAX_GROUP];
@@ -107,6 +107,10 @@ int mmemo_linear_fwd_grouped_bf16(int n, const void* const* x, const int64_t* ld
     if (pos && pos[i]) {
       MM_REQUIRE(pos_period && pos_period[i] > 0);
       g[i].pos = pos[i]; g[i].pos_period = pos_period[i];
+      if (ldpos && ldpos[i]) {
+        MM_REQUIRE(ldpos[i] >= N[i]);
+        g[i].ldpos = ldpos[i];
+      }
     }
     cb[i] = 1;
     tc_ok = tc_ok && gemm_tc_supported(g[i], 1, n > 1);

@@ -789,6 +789,39 @@ def _proj_backward(ctx, grads):
 proj_group_op.register_autograd(_proj_backward, setup_context=_proj_setup)
 
 
+@torch.no_grad()
+def project_into(xs, ws, biases, outs, poss=None) -> None:
+    """Inference-only (no autograd) form of the grouped projection, bf16 mode with float32 inputs:
+    problem g writes ``x_g w_g^T + b_g (+ pos_g)`` into ``outs[g]``, a (rows, N_g) bf16 2-D view
+    that may be a COLUMN SLICE of a wider buffer — the reference's ``cat`` of several projections
+    (robot_demo.py:304-311) without the concat kernel — and ``pos_g`` may likewise be a column
+    slice of the (L, d) table added after that concat (robot_demo.py:415-417).  One cast launch
+    per 16 inputs and ONE tensor-core launch for all problems (up to 48)."""
+    ops._need_cuda(*xs)
+    G = len(xs)
+    poss = poss if poss is not None else [None] * G
+    todo, xbs, wps = [], [], []
+    for x in xs:
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        x2 = x2 if x2.stride(1) == 1 else x2.contiguous()
+        xb = torch.empty(x2.shape[0], _pad8(K), dtype=BF, device=x.device)
+        todo.append((x2, xb))
+        xbs.append(xb)
+    for w in ws:
+        wps.append(_padded_shadow(w, todo))
+    _cast_pad(todo)
+    items = []
+    for g in range(G):
+        pos = poss[g]
+        if pos is not None:
+            assert xs[g].dim() == 3 and pos.shape[0] == xs[g].shape[1] and pos.stride(1) == 1, \
+                "position table length != seq length"
+        assert outs[g].dim() == 2 and outs[g].shape == (xbs[g].shape[0], wps[g].shape[0])
+        items.append((xbs[g], wps[g], biases[g], outs[g], False, False, pos))
+    ops._linear_fwd_group(True, items)
+
+
 def project(xs, ws, biases=None, poss=None, bf16: bool = False) -> List[Tensor]:
     """Modality projections of one or several towers.  bf16 mode with float32 inputs: the grouped
     cast + tensor-core path above; otherwise the per-problem ``ops.linear`` (float32 parity mode,

@@ -315,10 +315,12 @@ def _chunks(items, n=MAX_GEMM_GROUP):
 def _linear_fwd_group(bf16, items):
     """items: [(x, w, bias, out2d, relu[, accumulate[, pos]])].  One grouped tensor-core launch (per
     48 problems) in bf16 mode; N, K and the weight's leading dimension come from ``w`` (a 2-D view,
-    e.g. one half of a concat weight); ``pos`` = (L, N) position table added with period L."""
+    e.g. one half of a concat weight); ``pos`` = (L, N) position table added with period L (may be a
+    column slice of a wider table: its row stride is passed along)."""
     items = [tuple(it) + (False, None)[len(it) - 5:] for it in items]
     if not bf16 or len(items) == 1:
         for x, w, b, out, relu, acc, pos in items:
+            assert pos is None or pos.is_contiguous(), "a sliced position table needs the grouped path"
             _linear_fwd(bf16, x, w, b, pos, out, relu=relu, accumulate=acc, ldw=w.stride(0),
                         N=w.shape[0], K=w.shape[1])
         return
@@ -335,7 +337,8 @@ def _linear_fwd_group(bf16, items):
               _arr(C.c_int64, [it[1].shape[1] for it in part]),
               _arr(C.c_int, [int(it[4]) for it in part]), _arr(C.c_int, [int(it[5]) for it in part]),
               _arr(C.c_void_p, [_p(it[6]) for it in part]),
-              _arr(C.c_int64, [0 if it[6] is None else it[6].shape[0] for it in part]), _stream())
+              _arr(C.c_int64, [0 if it[6] is None else it[6].shape[0] for it in part]),
+              _arr(C.c_int64, [0 if it[6] is None else it[6].stride(0) for it in part]), _stream())
 
 
 def _linear_bwd_x_group(bf16, items):

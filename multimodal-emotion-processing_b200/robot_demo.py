@@ -141,7 +141,9 @@ class Ensemble:
         ms = self.models
         if all(isinstance(m, Multi_class) for m in ms) and \
                 len({(m.n_layers, len(m.multimodal_blocks)) for m in ms}) == 1:
-            pooled = fusion_trunk_multi([m._tower(*args) for m in ms], ms[0].n_layers, keep_all=True)
+            towers = self._towers_joint(args) if is_bf16() and args[0].dtype == torch.float32 \
+                else [m._tower(*args) for m in ms]
+            pooled = fusion_trunk_multi(towers, ms[0].n_layers, keep_all=True)
             preds = [ops.linear(x, m.classifier.weight, m.classifier.bias)
                      for m, x in zip(ms, pooled)]
         else:
@@ -159,6 +161,38 @@ class Ensemble:
         for p in preds[1:]:            # same summation order as robot_demo.py:614
             pred = pred + p
         return pred / len(preds)
+
+    def _towers_joint(self, args):
+        """``Multi_class._tower`` of every member from ONE grouped projection launch (bf16 mode):
+        the 5 input projections of all members are problems of one tensor-core launch whose
+        epilogue adds bias and position table; the three visual projections write the column
+        thirds of one (B, L, d) buffer and add the matching thirds of the visual table, so the
+        reference's ``cat`` + three ``x + position`` kernels per member disappear."""
+        from .group_ops import project_into
+        l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask = args
+        masks = {"l": as_mask(l_mask), "v": as_mask(v_mask), "a": as_mask(a_mask)}
+        xs, ws, bs, outs, poss, towers = [], [], [], [], [], []
+        for m in self.models:
+            u = m.unify_dimension
+            d = u.linguistic.weight.shape[0]
+            t = d // 3
+            pl, pv, pa = (e.position_embeddings.weight.detach() for e in
+                          (m.linguistic_position, m.visual_position, m.acoustic_position))
+            yl = torch.empty(*l.shape[:2], d, dtype=torch.bfloat16, device=l.device)
+            yv = torch.empty(*v_256.shape[:2], 3 * t, dtype=torch.bfloat16, device=l.device)
+            ya = torch.empty(*a.shape[:2], d, dtype=torch.bfloat16, device=l.device)
+            yv2 = yv.view(-1, 3 * t)
+            for x, conv, out, pos in (
+                    (l, u.linguistic, yl.view(-1, d), pl),
+                    (v_256, u.visual_256, yv2[:, 0:t], pv[:, 0:t]),
+                    (v_512, u.visual_512, yv2[:, t:2 * t], pv[:, t:2 * t]),
+                    (v_1024, u.visual_1024, yv2[:, 2 * t:3 * t], pv[:, 2 * t:3 * t]),
+                    (a, u.acoustic, ya.view(-1, d), pa)):
+                xs.append(x); ws.append(conv.weight); bs.append(conv.bias.detach())
+                outs.append(out); poss.append(pos)
+            towers.append((m.multimodal_blocks, {"l": yl, "v": yv, "a": ya}, masks))
+        project_into(xs, ws, bs, outs, poss)
+        return towers
 
     @torch.no_grad()
     def __call__(self, l, v_256, v_512, v_1024, a, l_mask, v_mask, a_mask):

@@ -36,9 +36,9 @@ def test_linear_formulas_and_positions():
 
 def test_grouped_linear_formulas():
     Ms, Ns, Ks = [8192, 8192], [512, 1024], [512, 512]
-    name = "mmemo_linear_fwd_grouped_bf16"       # ..., M, N, K, relu, accumulate, pos, period, stream
-    assert len(_lib.SIGNATURES[name]) == 16
-    a = [2] + [None] * 15
+    name = "mmemo_linear_fwd_grouped_bf16"   # ..., M, N, K, relu, accumulate, pos, period, ldpos, stream
+    assert len(_lib.SIGNATURES[name]) == 17
+    a = [2] + [None] * 16
     a[8], a[9], a[10] = Ms, Ns, Ks
     fl, by, tag = bench._algorithmic(name, tuple(a))
     assert fl == sum(2 * m * n * k for m, n, k in zip(Ms, Ns, Ks))
