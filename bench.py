@@ -248,6 +248,9 @@ def _algorithmic(name: str, a: tuple):
         return M * N, e * M * N, f"{M}x{N}"
     if name.startswith("mmemo_cast"):
         return 0, 6 * a[2], f"{a[2]}"
+    if name.startswith("mmemo_dropout_multi"):      # read + write of every tensor
+        ns = [int(v) for v in list(a[3])[:a[0]]]
+        return 0, 2 * e * sum(ns), f"G{a[0]}:{sum(ns)}"
     return 0, 0, ""
 
 

@@ -190,10 +190,13 @@ class Cfg3Composite(Workload):
 class Cfg4(Workload):
     name, cfg = "cfg4_renmme_base_model", "configs[3] (Ren-MME/run.py defaults, global batch 256)"
     description = ("Base_model(d=128,L=40/76/275,8 heads,1 layer), dims 768/640/205, R-Drop pairs, "
-                   "loss=multi_loss + symmetric sigmoid-KL; dropout off")
+                   "loss=multi_loss + symmetric sigmoid-KL; training dropout 0.1 as in the reference "
+                   "(Ren-MME/run.py:36; grouped counter-based masks, new on every step) - the CPU / "
+                   "eager baselines run the same model without dropout")
+    dropout = 0.1
 
     def model(self):
-        mmemo_b200.ren_mme.DROP = 0.0
+        mmemo_b200.ren_mme.DROP = self.dropout
         return mmemo_b200.ren_mme.Base_model()
 
     def host_batch(self, seed):
@@ -302,6 +305,8 @@ class GraphedStep:
 
     def _step(self):
         self.model.zero_grad(set_to_none=True)
+        if getattr(self.wl, "dropout", 0.0) > 0:
+            ops.advance_dropout_step(self.dev)     # captured: every graph replay draws new masks
         loss = self.wl.loss(self.model, self.static)
         if self.reducer is not None:
             self.reducer.backward(loss)

@@ -305,6 +305,17 @@ int mmemo_dropout_f32(const void* x, void* y, int64_t n, float p, uint64_t seed,
                       mmemo_stream_t stream);
 int mmemo_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed,
                        mmemo_stream_t stream);
+/* The same for n <= 64 tensors in ONE launch (the dropout sites of a fusion-trunk layer over all
+ * of its chains: Ren-MME/run.py:208,212  robot_demo.py:333,368).  x[i] == y[i] is allowed (in
+ * place); 16-byte aligned pointers.  x, y, numel, seeds: HOST arrays of length n.  step: nullable
+ * DEVICE scalar mixed into every seed when the kernel runs, so that a captured CUDA graph draws
+ * new masks on every replay (the caller increments it once per training step). */
+int mmemo_dropout_multi_f32(int n, const void* const* x, void* const* y, const int64_t* numel,
+                            const uint64_t* seeds, float p, const uint64_t* step,
+                            mmemo_stream_t stream);
+int mmemo_dropout_multi_bf16(int n, const void* const* x, void* const* y, const int64_t* numel,
+                             const uint64_t* seeds, float p, const uint64_t* step,
+                             mmemo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fusion pooling: concat on features, concat on positions (l, a, v), mean || max over ALL

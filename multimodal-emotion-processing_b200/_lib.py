@@ -78,6 +78,8 @@ SIGNATURES = {
     "mmemo_sum_grouped_bf16": [_i32, _vp, _vp, _vp, _vp, _vp],
     "mmemo_cast_pad_f32_to_bf16_multi": [_i32] + [_vp] * 6 + [_vp],
     "mmemo_dropout_f32": _DROPOUT, "mmemo_dropout_bf16": _DROPOUT,
+    "mmemo_dropout_multi_f32": [_i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp],
+    "mmemo_dropout_multi_bf16": [_i32, _vp, _vp, _vp, _vp, _f32, _vp, _vp],
     "mmemo_pool_fwd_f32": _POOL_FWD, "mmemo_pool_fwd_bf16": _POOL_FWD,
     "mmemo_pool_bwd_f32": _POOL_BWD, "mmemo_pool_bwd_bf16": _POOL_BWD,
     "mmemo_state_transfer_fwd": [_vp, _vp, _vp, _i64, _i64, _i64, _vp],

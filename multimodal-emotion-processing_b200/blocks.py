@@ -199,10 +199,12 @@ def fusion_trunk_multi(towers, n_layers: int, keep_all: bool) -> List[torch.Tens
     ``Concat_Trans`` / ``Base_model`` (cmu-mosei/run.py:330-331, Ren-MME/run.py:283-284), the
     members of an ensemble (robot_demo.py:610-614).  ``towers`` = [(blocks, feats, masks), ...];
     returns one pooled tensor per tower.  Layer i of every chain of every tower is one grouped op
-    (``group_ops``) unless dropout is active in training (no fused dropout in the grouped path)."""
+    (``group_ops``); training dropout (Ren-MME and robot_demo train with p = 0.1) runs inside it as
+    one grouped launch per dropout site."""
     blk0 = towers[0][0][0]
-    if not GROUPED_TRUNK or (blk0.training and blk0.drop.p > 0):
+    if not GROUPED_TRUNK:
         return [_fusion_trunk_per_block(b, n_layers, f, m, keep_all) for b, f, m in towers]
+    drop_p = float(blk0.drop.p) if blk0.training else 0.0
     from . import group_ops
     bf = is_bf16()
     full = isinstance(blk0, FullAttentionBlock)
@@ -222,7 +224,8 @@ def fusion_trunk_multi(towers, n_layers: int, keep_all: bool) -> List[torch.Tens
         params = [p for blocks, _, _ in towers for ci in range(len(CHAINS))
                   for p in blocks[n_layers * ci + i]._params()]
         emit = i + 1 < n_layers                 # the last layer's scores feed nothing
-        res = op(qs, kvs, ms, s_prev, params, blk0.n_heads, bf, emit)
+        res = op(qs, kvs, ms, s_prev, params, blk0.n_heads, bf, emit, drop_p,
+                 ops.next_dropout_seed() if drop_p > 0 else 0)
         qs = [res[n_out * g] for g in range(G)]
         s_prev = [res[n_out * g + 1] for g in range(G)] if emit else []
         for g in range(G):

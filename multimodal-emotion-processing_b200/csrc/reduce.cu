@@ -58,19 +58,72 @@ __global__ void cast_b2f_kernel(const bf16* __restrict__ s, float* __restrict__ 
   if (i < n) d[i] = __bfloat162float(s[i]);
 }
 
-// splitmix64-style hash of (seed, element index) -> uniform in [0,1)
-__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i) {
+// splitmix64-style hash of (seed, index) -> 64 well-mixed bits / a uniform in [0,1)
+__device__ __forceinline__ uint64_t hash_bits(uint64_t seed, uint64_t i) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t i) {
+  return (float)(hash_bits(seed, i) >> 40) * (1.0f / 16777216.0f);
 }
 template <typename T>
 __global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p,
                                float scale, uint64_t seed) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = from_f<T>(hash_uniform(seed, (uint64_t)i) >= p ? to_f(x[i]) * scale : 0.f);
+}
+
+// dropout of several tensors in ONE launch (the two dropout sites of a fusion-trunk layer over all
+// of its chains), in place or out of place.  Per-tensor seeds; `step` (device scalar, nullable) is
+// mixed into every seed at run time so that a captured CUDA graph draws new masks on every replay.
+constexpr int DROP_MAXT = 64;
+struct DropTable {
+  const void* x[DROP_MAXT];
+  void* y[DROP_MAXT];
+  long long n[DROP_MAXT];
+  unsigned long long seed[DROP_MAXT];
+  int count;
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+dropout_multi_kernel(const __grid_constant__ DropTable t, float p, float scale,
+                     const unsigned long long* __restrict__ step) {
+  const int which = blockIdx.y;
+  pdl_wait();
+  pdl_trigger();
+  if (which >= t.count) return;
+  const T* __restrict__ x = static_cast<const T*>(t.x[which]);
+  T* __restrict__ y = static_cast<T*>(t.y[which]);
+  const long long n = t.n[which];
+  const uint64_t seed = t.seed[which] + (step ? step[0] * 0xD6E8FEB86659FD93ull : 0ull);
+  // one 64-bit hash per FOUR consecutive elements, 16 bits each (p is resolved to 1/65536): the
+  // per-element hash of dropout_kernel made this kernel ALU-bound (0.49 of HBM on cfg 4)
+  const uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
+  constexpr int V = 16 / sizeof(T);            // elements per 16-byte access (4 or 8)
+  for (long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * V; i < n;
+       i += (long long)gridDim.x * 256 * V) {
+    if (i + V <= n) {
+      uint4 raw = *reinterpret_cast<const uint4*>(x + i);
+      T* e = reinterpret_cast<T*>(&raw);
+#pragma unroll
+      for (int q = 0; q < V / 4; ++q) {
+        const uint64_t h = hash_bits(seed, (uint64_t)(i >> 2) + q);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          e[4 * q + k] = from_f<T>(((uint32_t)(h >> (16 * k)) & 0xFFFFu) >= thr
+                                       ? to_f(e[4 * q + k]) * scale : 0.f);
+      }
+      *reinterpret_cast<uint4*>(y + i) = raw;
+    } else {
+      for (long long j = i; j < n; ++j) {
+        const uint64_t h = hash_bits(seed, (uint64_t)(j >> 2));
+        y[j] = from_f<T>(((uint32_t)(h >> (16 * (j & 3))) & 0xFFFFu) >= thr ? to_f(x[j]) * scale
+                                                                             : 0.f);
+      }
+    }
+  }
 }
 
 // several float32 tensors -> bf16 in ONE launch (all bf16 weight shadows of a block)
@@ -399,6 +452,31 @@ int rowsum(const void* x, int64_t ldx, float* out, int64_t M, int64_t N, int64_t
 }
 
 template <typename T>
+int dropout_multi(int n, const void* const* x, void* const* y, const int64_t* numel,
+                  const uint64_t* seeds, float p, const uint64_t* step, cudaStream_t st) {
+  if (n < 1 || n > DROP_MAXT) return MMEMO_ERR_ARG;
+  MM_REQUIRE(x && y && numel && seeds && p >= 0.f && p < 1.f);
+  DropTable t = {};
+  long long nmax = 0;
+  for (int i = 0; i < n; ++i) {
+    MM_REQUIRE(x[i] && y[i] && numel[i] >= 0);
+    if ((reinterpret_cast<uintptr_t>(x[i]) | reinterpret_cast<uintptr_t>(y[i])) & 15)
+      return MMEMO_ERR_ARG;
+    t.x[i] = x[i]; t.y[i] = y[i]; t.n[i] = numel[i]; t.seed[i] = seeds[i];
+    nmax = numel[i] > nmax ? numel[i] : nmax;
+  }
+  t.count = n;
+  if (nmax == 0) return MMEMO_OK;
+  const long long per_block = 256 * (16 / sizeof(T)) * 4;      // four 16-byte accesses per thread
+  long long gx = cdiv(nmax, per_block);
+  gx = gx > 1184 ? 1184 : gx;                                  // 8 CTAs per SM at most
+  MM_CUDA_OK(mm_launch(dropout_multi_kernel<T>, dim3((unsigned)gx, (unsigned)n), dim3(256), 0, st, t,
+                       p, 1.0f / (1.0f - p),
+                       reinterpret_cast<const unsigned long long*>(step)));
+  return MMEMO_OK;
+}
+
+template <typename T>
 int dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, cudaStream_t st) {
   if (n <= 0) return MMEMO_OK;
   MM_REQUIRE(x && y && p >= 0.f && p < 1.f);
@@ -563,6 +641,16 @@ int mmemo_dropout_f32(const void* x, void* y, int64_t n, float p, uint64_t seed,
 int mmemo_dropout_bf16(const void* x, void* y, int64_t n, float p, uint64_t seed,
                        mmemo_stream_t s) {
   return dropout<bf16>(x, y, n, p, seed, mm_stream(s));
+}
+int mmemo_dropout_multi_f32(int n, const void* const* x, void* const* y, const int64_t* numel,
+                            const uint64_t* seeds, float p, const uint64_t* step,
+                            mmemo_stream_t s) {
+  return dropout_multi<float>(n, x, y, numel, seeds, p, step, mm_stream(s));
+}
+int mmemo_dropout_multi_bf16(int n, const void* const* x, void* const* y, const int64_t* numel,
+                             const uint64_t* seeds, float p, const uint64_t* step,
+                             mmemo_stream_t s) {
+  return dropout_multi<bf16>(n, x, y, numel, seeds, p, step, mm_stream(s));
 }
 }
 

@@ -28,7 +28,15 @@ import torch
 from torch import Tensor
 
 from . import _lib, ops
-from .ops import BF, F32, LN_EPS, _act_dtype, _arr, _call, _p, _stream, _weight
+from .ops import BF, F32, LN_EPS, _act_dtype, _arr, _p, _weight
+
+
+def _call(name, *args):          # late-bound: tests stub ops._call / ops._stream
+    return ops._call(name, *args)
+
+
+def _stream():
+    return ops._stream()
 
 N_FULL = 15      # wq wk wv wo  n1w n1b n2w n2b  f1w f1b f2w f2b  a b c
 N_LITE = 5       # wo(proj) wm(minus, (d,2d)) nw nb c
@@ -229,7 +237,10 @@ FULL_OUT = 12
 @torch.library.custom_op("mmemo::trunk_full", mutates_args=())
 def trunk_full_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[Tensor],
                   s_prevs: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
-                  emit_s: bool) -> List[Tensor]:
+                  emit_s: bool, drop_p: float, drop_seed: int) -> List[Tensor]:
+    """``drop_p`` > 0: the block's two training dropouts — on the projected attention output
+    (others/realformer.py:203  robot_demo.py:368) and at the end of the FFN (:167 / :333) — as one
+    in-place grouped launch each, masks regenerated from ``drop_seed`` in the backward."""
     ops._need_cuda(*qs, *kvs)
     G = len(qs)
     dt, dev = _act_dtype(bf16), qs[0].device
@@ -261,6 +272,7 @@ def trunk_full_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[T
     xs = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
     ops._linear_fwd_group(bf16, [(os_[g], _weight(bf16, P[g][3]), None, xs[g].view(-1, d), False)
                                  for g in range(G)])
+    ops._dropout_group(xs, xs, drop_p, ops.site_seeds(drop_seed, G, 0))
     h1s, st1s = ln_fwd_group(bf16, qs, xs, [p[12] for p in P], [p[4] for p in P],
                              [p[5] for p in P])
     # FFN (bias + ReLU fused in the first GEMM's epilogue), gated residual + LN2
@@ -270,6 +282,7 @@ def trunk_full_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[T
                                  for g in range(G)])
     ops._linear_fwd_group(bf16, [(f1s[g], _weight(bf16, P[g][10]), P[g][11], f2s[g].view(-1, d), False)
                                  for g in range(G)])
+    ops._dropout_group(f2s, f2s, drop_p, ops.site_seeds(drop_seed, G, 1))
     h2s, st2s = ln_fwd_group(bf16, h1s, f2s, [p[13] for p in P], [p[6] for p in P],
                              [p[7] for p in P])
     out = []
@@ -303,7 +316,7 @@ def _full_zviews(z: Tensor, d: int, dff: int):
 def trunk_full_bwd_op(dh2s: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Sequence[Tensor],
                       kvs: Sequence[Tensor], masks: Sequence[Tensor], s_prevs: Sequence[Tensor],
                       saved: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
-                      need_dsprev: bool) -> List[Tensor]:
+                      need_dsprev: bool, drop_p: float, drop_seed: int) -> List[Tensor]:
     """Returns per problem [dq, dkv, ds_prev] (empty placeholders where undefined) followed by ONE
     float32 buffer holding every parameter gradient of the group (layout: _full_zlayout)."""
     G = len(qs)
@@ -328,8 +341,14 @@ def trunk_full_bwd_op(dh2s: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Se
     zall = torch.zeros(G * zlen, dtype=F32, device=dev)      # ONE fill for every "+=" output
     Z = [_full_zviews(zall[g * zlen:(g + 1) * zlen], d, dff) for g in range(G)]
     # LN2: h2 = LN(h1 + b*f2); colsum(df2) = the FFN-2 bias gradient comes out of the same pass
-    dh1s, df2s = ln_bwd_group(bf16, dh2s, h1s, f2s, [p[13] for p in P], [p[6] for p in P], st2s,
-                              True, [z[0] for z in Z], [z[2] for z in Z])
+    if drop_p > 0:   # the FFN-2 bias sees the gradient BEFORE the dropout: mask first, then column sums
+        dh1s, df2s = ln_bwd_group(bf16, dh2s, h1s, f2s, [p[13] for p in P], [p[6] for p in P], st2s,
+                                  True, [z[0] for z in Z])
+        ops._dropout_group(df2s, df2s, drop_p, ops.site_seeds(drop_seed, G, 1))
+        colsum_group(bf16, [t.view(-1, d) for t in df2s], [z[2] for z in Z])
+    else:
+        dh1s, df2s = ln_bwd_group(bf16, dh2s, h1s, f2s, [p[13] for p in P], [p[6] for p in P], st2s,
+                                  True, [z[0] for z in Z], [z[2] for z in Z])
     # FFN backward: df1 = (df2 W2) * (f1 > 0) fused in the epilogue; dh1 += df1 W1
     df1s = [torch.empty(f.shape, dtype=dt, device=dev) for f in f1s]
     ops._linear_bwd_x_group(bf16, [(df2s[g], _weight(bf16, P[g][10]), df1s[g].view(-1, dff), False,
@@ -340,6 +359,7 @@ def trunk_full_bwd_op(dh2s: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Se
     # LN1: h1 = LN(q + a*x)
     dqs, dxs = ln_bwd_group(bf16, dh1s, qs, xs, [p[12] for p in P], [p[4] for p in P], st1s, True,
                             [z[1] for z in Z])
+    ops._dropout_group(dxs, dxs, drop_p, ops.site_seeds(drop_seed, G, 0))
     # output projection
     dos = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
     ops._linear_bwd_x_group(bf16, [(dxs[g], _weight(bf16, P[g][3]), dos[g].view(-1, d), False)
@@ -384,9 +404,10 @@ def trunk_full_bwd_op(dh2s: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Se
 
 
 def _trunk_full_setup(ctx, inputs, output):
-    qs, kvs, masks, s_prevs, params, H, bf16, emit_s = inputs
+    qs, kvs, masks, s_prevs, params, H, bf16, emit_s, drop_p, drop_seed = inputs
     G = len(qs)
     ctx.G, ctx.cfg, ctx.has_prev = G, (H, bf16), len(s_prevs) > 0
+    ctx.drop = (drop_p, drop_seed)
     ctx.n_params = len(params)
     saved = []
     for g in range(G):
@@ -412,7 +433,8 @@ def _trunk_full_backward(ctx, grads):
         dh2s.append(gh if gh is not None else torch.zeros_like(qs[g]))
         dsn.append(gs if gs is not None else _e(dev))
     need_dsprev = ctx.has_prev and any(ctx.needs_input_grad[3])
-    res = trunk_full_bwd_op(dh2s, dsn, qs, kvs, masks, s_prevs, saved, params, H, bf16, need_dsprev)
+    res = trunk_full_bwd_op(dh2s, dsn, qs, kvs, masks, s_prevs, saved, params, H, bf16, need_dsprev,
+                            *ctx.drop)
     zall = res[-1]
     d = qs[0].shape[-1]
     dff = params[8].shape[0]
@@ -429,7 +451,7 @@ def _trunk_full_backward(ctx, grads):
                    dc if ctx.has_prev else None]
     n_prev = G if ctx.has_prev else 0
     return (dqs, dkvs, [None] * G, dsps if need_dsprev else [None] * n_prev, pgrads, None, None,
-            None)
+            None, None, None)
 
 
 trunk_full_op.register_autograd(_trunk_full_backward, setup_context=_trunk_full_setup)
@@ -446,7 +468,10 @@ LITE_OUT = 7
 @torch.library.custom_op("mmemo::trunk_lite", mutates_args=())
 def trunk_lite_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[Tensor],
                   s_prevs: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
-                  emit_s: bool) -> List[Tensor]:
+                  emit_s: bool, drop_p: float, drop_seed: int) -> List[Tensor]:
+    """``drop_p`` > 0: the lite block's two training dropouts — ``drop(proj(att))`` and
+    ``drop(norm(minus(..)))`` (Ren-MME/run.py:208,212  cmu-mosei/run.py:256,260) — one in-place
+    grouped launch each."""
     ops._need_cuda(*qs, *kvs)
     G = len(qs)
     dt, dev = _act_dtype(bf16), qs[0].device
@@ -465,6 +490,7 @@ def trunk_lite_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[T
     xs = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
     ops._linear_fwd_group(bf16, [(os_[g], _weight(bf16, P[g][0]), None, xs[g].view(-1, d), False)
                                  for g in range(G)])
+    ops._dropout_group(xs, xs, drop_p, ops.site_seeds(drop_seed, G, 0))
     # y = [q | x] Wm^T as two accumulating grouped GEMMs over the halves of Wm (no concat copy)
     ys = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
     wms = [_weight(bf16, P[g][1]) for g in range(G)]
@@ -473,6 +499,7 @@ def trunk_lite_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[T
     ops._linear_fwd_group(bf16, [(xs[g], wms[g][:, d:], None, ys[g].view(-1, d), False, True)
                                  for g in range(G)])
     outs, sts = ln_fwd_group(bf16, [None] * G, ys, [None] * G, [p[2] for p in P], [p[3] for p in P])
+    ops._dropout_group(outs, outs, drop_p, ops.site_seeds(drop_seed, G, 1))
     out = []
     for g in range(G):
         out += [outs[g], ss[g] if ss[g] is not None else _e(dev), os_[g], stats[g], xs[g], ys[g],
@@ -498,7 +525,7 @@ def _lite_zviews(z: Tensor, d: int):
 def trunk_lite_bwd_op(douts: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Sequence[Tensor],
                       kvs: Sequence[Tensor], masks: Sequence[Tensor], s_prevs: Sequence[Tensor],
                       saved: Sequence[Tensor], params: Sequence[Tensor], n_heads: int, bf16: bool,
-                      need_dsprev: bool) -> List[Tensor]:
+                      need_dsprev: bool, drop_p: float, drop_seed: int) -> List[Tensor]:
     G = len(qs)
     dt, dev = _act_dtype(bf16), qs[0].device
     d = qs[0].shape[-1]
@@ -514,6 +541,10 @@ def trunk_lite_bwd_op(douts: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: S
     sp = [s_prevs[g] if len(s_prevs) else None for g in range(G)]
     dsn = [_opt(t) for t in ds_nexts]
     douts = [t.contiguous() for t in douts]
+    if drop_p > 0:   # gradient through the output dropout (out of place: douts belong to autograd)
+        masked = [torch.empty_like(t) for t in douts]
+        ops._dropout_group(douts, masked, drop_p, ops.site_seeds(drop_seed, G, 1))
+        douts = masked
     _, zlen = _lite_zlayout(d)
     zall = torch.zeros(G * zlen, dtype=F32, device=dev)
     Z = [_lite_zviews(zall[g * zlen:(g + 1) * zlen], d) for g in range(G)]
@@ -524,6 +555,7 @@ def trunk_lite_bwd_op(douts: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: S
     dxs = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
     ops._linear_bwd_x_group(bf16, [(dys[g], wms[g][:, d:], dxs[g].view(-1, d), False)
                                    for g in range(G)])
+    ops._dropout_group(dxs, dxs, drop_p, ops.site_seeds(drop_seed, G, 0))
     dos = [torch.empty(q.shape, dtype=dt, device=dev) for q in qs]
     ops._linear_bwd_x_group(bf16, [(dxs[g], _weight(bf16, P[g][0]), dos[g].view(-1, d), False)
                                    for g in range(G)])
@@ -566,9 +598,10 @@ def trunk_lite_bwd_op(douts: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: S
 
 
 def _trunk_lite_setup(ctx, inputs, output):
-    qs, kvs, masks, s_prevs, params, H, bf16, emit_s = inputs
+    qs, kvs, masks, s_prevs, params, H, bf16, emit_s, drop_p, drop_seed = inputs
     G = len(qs)
     ctx.G, ctx.cfg, ctx.has_prev = G, (H, bf16), len(s_prevs) > 0
+    ctx.drop = (drop_p, drop_seed)
     saved = []
     for g in range(G):
         saved += list(output[LITE_OUT * g + 1:LITE_OUT * (g + 1)])
@@ -593,7 +626,8 @@ def _trunk_lite_backward(ctx, grads):
         douts.append(gh if gh is not None else torch.zeros_like(qs[g]))
         dsn.append(gs if gs is not None else _e(dev))
     need_dsprev = ctx.has_prev and any(ctx.needs_input_grad[3])
-    res = trunk_lite_bwd_op(douts, dsn, qs, kvs, masks, s_prevs, saved, params, H, bf16, need_dsprev)
+    res = trunk_lite_bwd_op(douts, dsn, qs, kvs, masks, s_prevs, saved, params, H, bf16, need_dsprev,
+                            *ctx.drop)
     zall = res[-1]
     d = qs[0].shape[-1]
     _, zlen = _lite_zlayout(d)
@@ -607,7 +641,7 @@ def _trunk_lite_backward(ctx, grads):
         pgrads += [dwo, dwm, dpn[1:1 + d], dpn[1 + d:], dc if ctx.has_prev else None]
     n_prev = G if ctx.has_prev else 0
     return (dqs, dkvs, [None] * G, dsps if need_dsprev else [None] * n_prev, pgrads, None, None,
-            None)
+            None, None, None)
 
 
 trunk_lite_op.register_autograd(_trunk_lite_backward, setup_context=_trunk_lite_setup)

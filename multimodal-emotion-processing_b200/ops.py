@@ -1237,11 +1237,56 @@ def _do_backward(ctx, dy):
 dropout_op.register_autograd(_do_backward, setup_context=_do_setup)
 
 _dropout_counter = [0]
+_dropout_step = {}     # device -> int64 scalar mixed into the grouped-dropout seeds at run time
+
+
+def next_dropout_seed() -> int:
+    """A fresh 63-bit seed per call, derived from torch's seed (``torch.manual_seed`` controls it)."""
+    _dropout_counter[0] += 1
+    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _dropout_counter[0] * 0xD1B54A32D192ED03)
+    return seed & 0x7FFFFFFFFFFFFFFF
 
 
 def dropout(x: Tensor, p: float, training: bool) -> Tensor:
     if not training or p <= 0.0:
         return x
-    _dropout_counter[0] += 1
-    seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + _dropout_counter[0] * 0xD1B54A32D192ED03)
-    return dropout_op(x, float(p), seed & 0x7FFFFFFFFFFFFFFF)
+    return dropout_op(x, float(p), next_dropout_seed())
+
+
+def dropout_step(dev) -> Tensor:
+    """Device scalar added to every grouped-dropout seed when the kernel RUNS.  Python-side seeds
+    are frozen when a training step is captured into a CUDA graph; a captured ``advance_dropout_step``
+    (one increment per replay) makes every replay draw new masks."""
+    dev = torch.device(dev)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    t = _dropout_step.get(dev)
+    if t is None:
+        t = _dropout_step[dev] = torch.zeros(1, dtype=torch.int64, device=dev)
+    return t
+
+
+def advance_dropout_step(dev="cuda") -> None:
+    dropout_step(dev).add_(1)
+
+
+def site_seeds(seed: int, G: int, site: int, n_sites: int = 2) -> List[int]:
+    """One seed per (problem, dropout site) of a grouped layer."""
+    return [(seed + (n_sites * g + site + 1) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
+            for g in range(G)]
+
+
+def _dropout_group(xs, ys, p: float, seeds) -> None:
+    """ys[i] = dropout(xs[i]) for up to 64 tensors per launch; xs[i] is ys[i] = in place.  Forward
+    and backward use the same seeds (same masks)."""
+    if p <= 0.0 or not xs:
+        return
+    bf16 = xs[0].dtype == BF
+    step = dropout_step(xs[0].device)
+    for i in range(0, len(xs), 64):
+        px, py, ps = xs[i:i + 64], ys[i:i + 64], seeds[i:i + 64]
+        assert all(t.is_contiguous() for t in px) and all(t.is_contiguous() for t in py)
+        _call(f"mmemo_dropout_multi_{_sfx(bf16)}", len(px),
+              _arr(C.c_void_p, [t.data_ptr() for t in px]), _arr(C.c_void_p, [t.data_ptr() for t in py]),
+              _arr(C.c_int64, [t.numel() for t in px]), _arr(C.c_uint64, list(ps)), float(p),
+              step.data_ptr(), _stream())

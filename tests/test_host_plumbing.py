@@ -96,9 +96,9 @@ def test_trunk_skips_unused_score_writes(stub, monkeypatch):
         emitted.append(emit_s)
         return real(q, kv, mask, s_prev, params, H, bf16, emit_s)
 
-    def spy_g(qs, kvs, masks, s_prevs, params, H, bf16, emit_s):
+    def spy_g(qs, kvs, masks, s_prevs, params, H, bf16, emit_s, drop_p, drop_seed):
         groups.append((len(qs), len(s_prevs), emit_s))
-        return real_g(qs, kvs, masks, s_prevs, params, H, bf16, emit_s)
+        return real_g(qs, kvs, masks, s_prevs, params, H, bf16, emit_s, drop_p, drop_seed)
 
     monkeypatch.setattr(ops, "block_lite_op", spy)
     monkeypatch.setattr(group_ops, "trunk_lite_op", spy_g)
@@ -277,3 +277,23 @@ def test_bucket_length_is_sliceable_for_any_world():
         assert n % (4 * world) == 0 and n >= offs[-1] + 33 and all(o % 32 == 0 for o in offs)
         if world in (1, 2, 4, 8, 16):
             assert n == dp._Bucket.layout(ps)[1] and n % 1024 == 0
+
+
+def test_training_dropout_stays_on_the_grouped_path(stub, monkeypatch):
+    """Ren-MME trains with dropout 0.1 (Ren-MME/run.py:36).  The grouped trunk keeps its launch
+    count: the two dropout sites of the 18 chains are ONE grouped launch each per direction, not
+    36 per-tensor kernels (and not the per-op fallback path)."""
+    monkeypatch.setattr(mmemo_b200.ren_mme, "DROP", 0.1)
+    m = mmemo_b200.ren_mme.Base_model(16, 4, 5, 6, 2, 1, 1, l_dim=8, v_dim=6, a_dim=7).train()
+    g = torch.Generator().manual_seed(0)
+    inputs = []
+    for L, D in ((4, 8), (5, 6), (6, 7)):
+        for _ in range(2):
+            inputs += [torch.randn(2, L, D, generator=g), torch.ones(2, L)]
+    with mmemo_b200.precision("bf16"):
+        out = m(*inputs)
+        ops.circle_loss_op(out, torch.zeros(2, 9)).mean().backward()
+    assert sum(n == "mmemo_dropout_multi_bf16" for n in stub) == 4     # 2 sites x (fwd + bwd)
+    assert not any(n in ("mmemo_dropout_bf16", "mmemo_dropout_f32") for n in stub)
+    assert sum(n.startswith("mmemo_resattn") for n in stub) == 2
+    assert len(stub) <= 60, (len(stub), stub)
