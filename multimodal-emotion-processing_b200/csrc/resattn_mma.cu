@@ -35,6 +35,17 @@
 namespace {
 
 constexpr int MAXP = 40;          // problems per launch
+// Kernel instantiations by the role of a layer in its chain.  The flags of a problem (previous
+// scores? scores written / stored? score gradients in / out?) are runtime data in M_GEN; the other
+// modes fix them at compile time, which removes the per-chunk pointer tests, the scalar fall-back
+// of the score-tensor accesses and (M_PLAIN) all score-tensor code from the inner loops.
+//            forward                         backward
+//  M_PLAIN   no S_prev, S not written        recompute, no S_prev / dS_next / dS_prev   (1-layer chain)
+//  M_FIRST   no S_prev, S written            S stored, no S_prev, dS_next, no dS_prev   (first of n)
+//  M_MID     S_prev, S written               S stored, S_prev, dS_next, dS_prev
+//  M_LAST    S_prev, S not written           recompute, S_prev, no dS_next, dS_prev      (last of n)
+// M_FIRST..M_LAST additionally require 16-byte accessible score rows (vec_s).
+constexpr int M_GEN = 0, M_PLAIN = 1, M_FIRST = 2, M_MID = 3, M_LAST = 4;
 constexpr int FWD_WARPS = 4, FWD_ROWS = 64;
 constexpr int BWD_WARPS = 8;
 constexpr size_t SMEM_MAX = 226 * 1024;   // dynamic part (227 KB per CTA minus static + reserve)
@@ -215,10 +226,19 @@ __device__ __forceinline__ void stage(uint32_t dst, const bf16* src, int ld, int
 // =============================================================================================
 // forward
 // =============================================================================================
-// (register caps keep 5 / 4 / 3 CTAs of 4 warps resident per SM for hd = 16 / 32 / 64)
-template <int HD>
-__global__ void __launch_bounds__(FWD_WARPS * 32, HD == 16 ? 5 : (HD == 32 ? 4 : 3))
+// (register caps keep 5 / 4 / 3 CTAs of 4 warps resident per SM for hd = 16 / 32 / 64; the PLAIN
+// hd = 16 instantiation fits 72 registers without spills: 7 CTAs)
+// PLAIN = no previous scores and no score output: the single layer of a one-layer trunk (Ren-MME's
+// default, cmu-mosei with n_layers = 1: any chain of length one).  The scores
+// then never leave the registers, so they are not rounded to bf16 (the backward's PLAIN recompute
+// does the same), key padding is handled by a +inf entry in the additive-mask row instead of
+// per-element selects, and none of the global score-tensor address / predicate code is compiled
+// in: 24 -> ~10 instructions per score (ncu source counters, profiles/).
+template <int HD, int MODE>
+__global__ void __launch_bounds__(FWD_WARPS * 32,
+                                  HD == 16 ? (MODE == M_PLAIN ? 7 : 5) : (HD == 32 ? 4 : 3))
 resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
+  constexpr bool PLAIN = MODE == M_PLAIN, SPEC = MODE >= M_FIRST;
   extern __shared__ __align__(128) uint8_t smem[];
   int local;
   const Prob& P = locate(T, local);
@@ -241,17 +261,21 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
                             min(FWD_ROWS, Lq - q0), FWD_ROWS);
   stage<HD>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
   if (!same_kv) stage<HD>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
-  for (int j = threadIdx.x; j < LkP; j += FWD_WARPS * 32)
-    sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
+  for (int j = threadIdx.x; j < LkP; j += FWD_WARPS * 32) {
+    float bias = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
+    if (PLAIN && j >= Lk) bias = INFINITY;   // padded keys: s = 0 - inf, p = 2^(-inf) = 0
+    sbias[j] = bias;
+  }
   cp_commit_wait();
   __syncthreads();
 
   const int r0 = q0 + warp * 16;          // first query row of this warp
   if (r0 >= Lq) return;
-  const bool has_prev = P.s_prev != nullptr, has_mask = P.mask != nullptr;
+  const bool has_prev = SPEC ? (MODE != M_FIRST) : (!PLAIN && P.s_prev != nullptr);
+  const bool has_mask = P.mask != nullptr;
   const float cval = (has_prev && P.c) ? P.c[0] : 0.f;
   const float inv_sqrt = T.inv_sqrt;
-  const bool vec = P.vec_s != 0;
+  const bool vec = SPEC ? true : P.vec_s != 0;
   const int lds = P.lds;
   const int rowA = r0 + g, rowB = r0 + g + 8;
   const bool okA = rowA < Lq, okB = rowB < Lq;
@@ -259,6 +283,7 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
   const size_t soff[2] = {(sbase + (okA ? rowA : 0)) * lds, (sbase + (okB ? rowB : 0)) * lds};
   const bf16* __restrict__ sprev = P.s_prev;
   bf16* __restrict__ sout = P.s_out;
+  const bool has_sout = SPEC ? (MODE != M_LAST) : (!PLAIN && sout != nullptr);
   constexpr uint32_t RB = HD * 2;
   LaneOffs<HD> lo;
   lo.init(lane);
@@ -297,6 +322,23 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
     }
     // ---- scale, + c*S_prev, - 1e8*(1-mask), bf16 round, store S; block max ----------------------
     float bmax[2] = {-INFINITY, -INFINITY};
+    if constexpr (PLAIN) {
+#pragma unroll
+      for (int G = 0; G < 2; ++G) {
+        const float* bp = sbias + kb + 32 * G + 8 * t;
+        const float4 b0 = *reinterpret_cast<const float4*>(bp);
+        const float4 b1 = *reinterpret_cast<const float4*>(bp + 4);
+        const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {               // e >> 1 = row half, key = 2 i + (e & 1)
+            const float sx = __fsub_rn(__fmul_rn(sc[G * 4 + i][e], inv_sqrt), bias[2 * i + (e & 1)]);
+            sc[G * 4 + i][e] = sx;
+            bmax[e >> 1] = fmaxf(bmax[e >> 1], sx);
+          }
+      }
+    } else {
 #pragma unroll
     for (int G = 0; G < 2; ++G) {
       const int k0 = kb + 32 * G + 8 * t;             // this lane's 8 contiguous keys
@@ -339,8 +381,9 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           bmax[half] = fmaxf(bmax[half], fmaxf(sc[G * 4 + i][half * 2], sc[G * 4 + i][half * 2 + 1]));
-        if (sout && row_ok && k0 < lds) store8(sout + soff[half] + k0, lds - k0, vec, sv);
+        if (has_sout && row_ok && k0 < lds) store8(sout + soff[half] + k0, lds - k0, vec, sv);
       }
+    }
     }
     // ---- online softmax (base-2 exponentials) ----------------------------------------------------
     // (s - max is formed FIRST: on a fully masked row s = max = bf16(-1e8), where folding max*log2e
@@ -407,9 +450,17 @@ resattn_mma_fwd_kernel(const __grid_constant__ Table T) {
 // =============================================================================================
 // (no register cap: forcing three 6-warp CTAs per SM (<= 96 registers) spilled and measured 8 %
 // slower on Ren-MME's shapes than two CTAs at 121 registers)
-template <int HD, int KB>
+// PLAIN = scores recomputed, no previous scores, no score gradients in or out (the backward of the
+// PLAIN forward): unrounded scores, +inf mask entries for the key padding, no per-element selects
+// and none of the global score-tensor code.
+// DQREG: every warp owns at most three 16-row tiles (Lq <= 384 with the CTA sizing below) and
+// keeps their dQ accumulators in registers across the key blocks instead of a read-modify-write
+// fp32 tile in shared memory: 18 KB less per CTA at Lq = 275 (87 -> 69 KB: three CTAs per SM).
+template <int HD, int KB, int MODE, bool DQREG>
 __global__ void __launch_bounds__(BWD_WARPS * 32)
 resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
+  constexpr bool PLAIN = MODE == M_PLAIN, SPEC = MODE >= M_FIRST;
+  constexpr int MAXR = DQREG ? 3 : 1;
   const int NT = blockDim.x, nwarps = blockDim.x >> 5;   // 2..8 warps, chosen per launch (host)
   constexpr int NG = KB / 32;              // 32-key groups per block
   extern __shared__ __align__(128) uint8_t smem[];
@@ -430,7 +481,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   if (!same_kv) { sV = s_u32(smem) + off;  off += kv_rows * HD * 2; }
   const uint32_t sP = s_u32(smem) + off;   off += LqP * KB * 2;
   const uint32_t sdS = s_u32(smem) + off;  off += LqP * KB * 2;
-  float* sdQ = reinterpret_cast<float*>(smem + off);    off += LqP * HD * 4;
+  float* sdQ = reinterpret_cast<float*>(smem + off);    off += DQREG ? 0 : LqP * HD * 4;
   float* sstat = reinterpret_cast<float*>(smem + off);  off += LqP * 3 * 4;
   float* sbias = reinterpret_cast<float*>(smem + off);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -444,9 +495,13 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     stage<HD>(sK, P.k + (size_t)b * Lk * P.ldk + h * HD, P.ldk, Lk, LkP);
     if (!same_kv) stage<HD>(sV, P.v + (size_t)b * Lk * P.ldv + h * HD, P.ldv, Lk, LkP);
   }
-  for (int j = threadIdx.x; j < LkP; j += NT)
-    sbias[j] = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
-  for (int i = threadIdx.x; i < LqP * HD; i += NT) sdQ[i] = 0.f;
+  for (int j = threadIdx.x; j < LkP; j += NT) {
+    float bias = (P.mask && j < Lk) ? 1.0e8f * (1.0f - P.mask[(size_t)b * P.mask_bs + j]) : 0.f;
+    if (PLAIN && j >= Lk) bias = INFINITY;   // padded keys: s = -inf, p = 0, dS = 0
+    sbias[j] = bias;
+  }
+  if (!DQREG)
+    for (int i = threadIdx.x; i < LqP * HD; i += NT) sdQ[i] = 0.f;
   const size_t sbase = ((size_t)b * H + h) * Lq;
   // per-row statistics: max, log2(sum) (saved by the forward), D = rowsum(dO * O)
   for (int r = threadIdx.x; r < LqP; r += NT) {
@@ -471,11 +526,14 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
   cp_commit_wait();
   __syncthreads();
 
-  const bool has_prev = P.s_prev != nullptr, has_mask = P.mask != nullptr;
-  const bool recompute = P.s == nullptr;
+  const bool has_mask = P.mask != nullptr;
+  const bool has_prev = SPEC ? (MODE != M_FIRST) : (!PLAIN && P.s_prev != nullptr);
+  const bool recompute = SPEC ? (MODE == M_LAST) : (PLAIN || P.s == nullptr);
+  const bool has_next = SPEC ? (MODE != M_LAST) : (!PLAIN && P.ds_next != nullptr);
+  const bool has_dsp = SPEC ? (MODE != M_FIRST) : (!PLAIN && P.ds_prev != nullptr);
   const float cval = (has_prev && P.c) ? P.c[0] : 0.f;
   const float inv_sqrt = T.inv_sqrt;
-  const bool vec = P.vec_s != 0;
+  const bool vec = SPEC ? true : P.vec_s != 0;
   const int lds = P.lds;
   const int n_rt = LqP / 16;
   const bf16* __restrict__ gs = P.s;
@@ -493,6 +551,13 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     pofs[G][1] = swp<KB>(g + 8, 4 * G + t);
   }
   float dc_part = 0.f;
+  float dqa[MAXR][HD / 8][4];                        // DQREG: dQ of this warp's row tiles
+#pragma unroll
+  for (int ri = 0; ri < MAXR; ++ri)
+#pragma unroll
+    for (int n = 0; n < HD / 8; ++n)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) dqa[ri][n][e] = 0.f;
 
   for (int kb = 0; kb < Lk; kb += KB) {
     const int kofs = kv_blocked ? kb : 0;            // first key held in the K / V tiles
@@ -504,7 +569,10 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
       __syncthreads();
     }
     // ================= phase A: one warp per 16-row tile ========================================
-    for (int rt = warp; rt < n_rt; rt += nwarps) {
+    // (DQREG: tile ri of this warp, statically indexed accumulators; else the plain tile loop)
+#pragma unroll
+    for (int ri = 0; ri < MAXR; ++ri)
+    for (int rt = warp + ri * nwarps; rt < n_rt; rt += (DQREG ? n_rt : nwarps)) {
       const int rowA = rt * 16 + g, rowB = rowA + 8;
       const bool ok[2] = {rowA < Lq, rowB < Lq};
       const size_t soff[2] = {(sbase + (ok[0] ? rowA : 0)) * lds, (sbase + (ok[1] ? rowB : 0)) * lds};
@@ -553,6 +621,39 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
           }
       }
       // elementwise: P, dS, dc, dS_prev; P / dS -> shared memory (bf16, natural key order)
+      if constexpr (PLAIN) {
+        // rows >= Lq carry zero Q / dO rows and zero statistics, keys >= Lk a +inf mask entry and
+        // zero K / V rows: their P / dS come out as finite values times zero operands or exact
+        // zeros, so no element needs a guard
+#pragma unroll
+        for (int G = 0; G < NG; ++G) {
+          const float* bp = sbias + kb + 32 * G + 8 * t;
+          const float4 b0 = *reinterpret_cast<const float4*>(bp);
+          const float4 b1 = *reinterpret_cast<const float4*>(bp + 4);
+          const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const float mx = st_mx[half], l2 = st_l2[half], D = st_D[half];
+            float pb[8], dsb[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int i = G * 4 + (j >> 1), e = half * 2 + (j & 1);
+              const float sx = __fsub_rn(__fmul_rn(sc[i][e], inv_sqrt), bias[j]);
+              const float pj = fast_exp2(fmaf(sx - mx, LOG2E, -l2));
+              pb[j] = pj;
+              dsb[j] = pj * (dp[i][e] - D);
+              sc[i][e] = dsb[j];                         // A operand of dQ += dS K
+            }
+            const uint32_t rb = (uint32_t)(rt * 16) * (KB * 2) + pofs[G][half];
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sP + rb),
+                         "r"(pack2(pb[0], pb[1])), "r"(pack2(pb[2], pb[3])),
+                         "r"(pack2(pb[4], pb[5])), "r"(pack2(pb[6], pb[7])) : "memory");
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(sdS + rb),
+                         "r"(pack2(dsb[0], dsb[1])), "r"(pack2(dsb[2], dsb[3])),
+                         "r"(pack2(dsb[4], dsb[5])), "r"(pack2(dsb[6], dsb[7])) : "memory");
+          }
+        }
+      } else {
 #pragma unroll
       for (int G = 0; G < NG; ++G) {
         const int k0 = kb + 32 * G + 8 * t;
@@ -571,7 +672,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
           float sv[8], pv[8], nv[8], pb[8], dsb[8];
           if (!recompute && in) load8(gs + soff[half] + k0, lds - k0, vec, sv);
           if (has_prev && in) load8(gprev + soff[half] + k0, lds - k0, vec, pv);
-          if (gnext && in) load8(gnext + soff[half] + k0, lds - k0, vec, nv);
+          if (has_next && in) load8(gnext + soff[half] + k0, lds - k0, vec, nv);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float s;
@@ -585,7 +686,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
             }
             const float p = fast_exp2(fmaf(s - mx, LOG2E, -l2));
             float ds = p * (dp[G * 4 + (j >> 1)][half * 2 + (j & 1)] - D);
-            if (gnext) ds += nv[j];
+            if (has_next) ds += nv[j];
             pb[j] = p;
             dsb[j] = ds;
           }
@@ -601,7 +702,7 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
               dc_part = fmaf(dsb[j], pv[j], dc_part);
               o8[j] = cval * dsb[j];
             }
-            if (gdsp) store8(gdsp + soff[half] + k0, lds - k0, vec, o8);
+            if (has_dsp) store8(gdsp + soff[half] + k0, lds - k0, vec, o8);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) sc[G * 4 + (j >> 1)][half * 2 + (j & 1)] = dsb[j];   // A of dQ += dS K
@@ -614,12 +715,16 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
                        "r"(pack2(dsb[4], dsb[5])), "r"(pack2(dsb[6], dsb[7])) : "memory");
         }
       }
+      }
       // dQ tile += dS K  (A = dS from registers, B = K via ldmatrix.trans), fp32 in shared memory
-      float dq[HD / 8][4];
+      float dq_blk[HD / 8][4];
+      float (&dq)[HD / 8][4] = DQREG ? dqa[ri] : dq_blk;
+      if (!DQREG) {
 #pragma unroll
-      for (int n = 0; n < HD / 8; ++n)
+        for (int n = 0; n < HD / 8; ++n)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) dq[n][e] = 0.f;
+          for (int e = 0; e < 4; ++e) dq_blk[n][e] = 0.f;
+      }
 #pragma unroll
       for (int G = 0; G < NG; ++G) {
         if (kb + 32 * G >= Lk) continue;
@@ -638,14 +743,16 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
           }
         }
       }
-      float* qA = sdQ + rowA * HD + 2 * t;
+      if (!DQREG) {
+        float* qA = sdQ + rowA * HD + 2 * t;
 #pragma unroll
-      for (int n = 0; n < HD / 8; ++n) {
-        float2* pa = reinterpret_cast<float2*>(qA + 8 * n);
-        float2* pb2 = reinterpret_cast<float2*>(qA + 8 * HD + 8 * n);
-        float2 a = *pa, b2 = *pb2;
-        a.x += dq[n][0]; a.y += dq[n][1]; b2.x += dq[n][2]; b2.y += dq[n][3];
-        *pa = a; *pb2 = b2;
+        for (int n = 0; n < HD / 8; ++n) {
+          float2* pa = reinterpret_cast<float2*>(qA + 8 * n);
+          float2* pb2 = reinterpret_cast<float2*>(qA + 8 * HD + 8 * n);
+          float2 a = *pa, b2 = *pb2;
+          a.x += dq[n][0]; a.y += dq[n][1]; b2.x += dq[n][2]; b2.y += dq[n][3];
+          *pa = a; *pb2 = b2;
+        }
       }
     }
     __syncthreads();
@@ -701,8 +808,27 @@ resattn_mma_bwd_kernel(const __grid_constant__ Table T) {
     }
     __syncthreads();
   }
-  // ---- dQ: fp32 tile -> bf16, 16-byte stores --------------------------------------------------
-  for (int i = threadIdx.x; i < Lq * (HD / 8); i += NT) {
+  // ---- dQ: registers (DQREG) or the fp32 tile -> bf16 -----------------------------------------
+  if (DQREG) {
+#pragma unroll
+    for (int ri = 0; ri < MAXR; ++ri) {
+      const int rt = warp + ri * nwarps;
+      if (rt >= n_rt) continue;
+      const int rowA = rt * 16 + g, rowB = rowA + 8;
+      bf16* qa_ = P.dq + ((size_t)b * Lq + rowA) * P.lddq + h * HD + 2 * t;
+      bf16* qb_ = qa_ + (size_t)8 * P.lddq;
+#pragma unroll
+      for (int n = 0; n < HD / 8; ++n) {
+        if (rowA < Lq)
+          *reinterpret_cast<uint32_t*>(qa_ + 8 * n) =
+              pack2(dqa[ri][n][0] * inv_sqrt, dqa[ri][n][1] * inv_sqrt);
+        if (rowB < Lq)
+          *reinterpret_cast<uint32_t*>(qb_ + 8 * n) =
+              pack2(dqa[ri][n][2] * inv_sqrt, dqa[ri][n][3] * inv_sqrt);
+      }
+    }
+  }
+  for (int i = threadIdx.x; !DQREG && i < Lq * (HD / 8); i += NT) {
     const int r = i / (HD / 8), c8 = i - r * (HD / 8);
     const float* s = sdQ + r * HD + c8 * 8;
     *reinterpret_cast<uint4*>(P.dq + ((size_t)b * Lq + r) * P.lddq + h * HD + c8 * 8) =
@@ -730,11 +856,13 @@ size_t fwd_smem(int hd, int Lk, bool same_kv) {
   const int LkP = (Lk + 63) & ~63;
   return (size_t)FWD_ROWS * hd * 2 + (size_t)(same_kv ? 1 : 2) * LkP * hd * 2 + (size_t)LkP * 4;
 }
-size_t bwd_smem(int hd, int kbk, int Lq, int Lk, bool same_kv, bool kv_blocked = false) {
+size_t bwd_smem(int hd, int kbk, int Lq, int Lk, bool same_kv, bool kv_blocked = false,
+                bool dqreg = false) {
   const int LqP = (Lq + 15) & ~15, LkP = (Lk + kbk - 1) / kbk * kbk;
   const int kv_rows = kv_blocked ? kbk : LkP;
   return (size_t)2 * LqP * hd * 2 + (size_t)(same_kv ? 1 : 2) * kv_rows * hd * 2 +
-         (size_t)2 * LqP * kbk * 2 + (size_t)LqP * hd * 4 + (size_t)LqP * 12 + (size_t)LkP * 4;
+         (size_t)2 * LqP * kbk * 2 + (dqreg ? 0 : (size_t)LqP * hd * 4) + (size_t)LqP * 12 +
+         (size_t)LkP * 4;
 }
 
 bool operands_ok(const mmemo_attn_problem& a, bool bwd) {
@@ -784,34 +912,80 @@ bool resattn_mma_supported(const mmemo_attn_problem& a, bool bwd) {
   return bwd_smem((int)a.hd, 32, (int)a.Lq, (int)a.Lk, same, true) <= SMEM_MAX;
 }
 
-int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
-  if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
+namespace {
+bool vec_ok(const mmemo_attn_problem& p) {
+  auto al = [](const void* x) { return (reinterpret_cast<uintptr_t>(x) & 15) == 0; };
+  return p.lds % 8 == 0 && al(p.s_prev) && al(p.s_out) && al(p.s) && al(p.ds_next) && al(p.ds_prev);
+}
+int fwd_mode(const mmemo_attn_problem& p) {
+  if (getenv("MMEMO_ATTN_GENERIC")) return M_GEN;          // A/B switch (tools/prof_attn.py)
+  if (!p.s_prev && !p.s_out) return M_PLAIN;
+  if (!vec_ok(p)) return M_GEN;
+  return p.s_prev ? (p.s_out ? M_MID : M_LAST) : M_FIRST;
+}
+int bwd_mode(const mmemo_attn_problem& p) {
+  if (getenv("MMEMO_ATTN_GENERIC")) return M_GEN;
+  if (!p.s && !p.s_prev && !p.ds_next && !p.ds_prev) return M_PLAIN;
+  if (!vec_ok(p)) return M_GEN;
+  if (p.s && !p.s_prev && p.ds_next && !p.ds_prev) return M_FIRST;
+  if (p.s && p.s_prev && p.ds_next && p.ds_prev) return M_MID;
+  if (!p.s && p.s_prev && !p.ds_next && p.ds_prev) return M_LAST;
+  return M_GEN;
+}
+
+// the problems of `ps` that run in `mode`, as one launch of that instantiation
+int fwd_launch(const mmemo_attn_problem* ps, int n, int mode, cudaStream_t st) {
   static thread_local Table T;      // host staging (copied by value into the launch)
-  T.n = n;
   const int hd = (int)ps[0].hd;
   size_t smem = 0;
-  int ctas = 0;
+  int ctas = 0, m = 0;
   for (int i = 0; i < n; ++i) {
-    if (ps[i].hd != hd || !resattn_mma_supported(ps[i], false)) return MMEMO_ERR_SHAPE;
-    fill(T.p[i], ps[i]);
-    T.p[i].cta_start = ctas;
-    T.cta_start[i] = ctas;
+    if (fwd_mode(ps[i]) != mode) continue;
+    fill(T.p[m], ps[i]);
+    T.p[m].cta_start = ctas;
+    T.cta_start[m] = ctas;
     ctas += (int)(ps[i].B * ps[i].H * cdiv(ps[i].Lq, FWD_ROWS));
     const size_t s = fwd_smem(hd, (int)ps[i].Lk, ps[i].k == ps[i].v && ps[i].ldk == ps[i].ldv);
     smem = s > smem ? s : smem;
+    ++m;
   }
+  if (m == 0) return MMEMO_OK;
+  T.n = m;
   T.total = ctas;
-  T.cta_start[n] = ctas;
+  T.cta_start[m] = ctas;
   T.inv_sqrt = (float)(1.0 / sqrt((double)hd));
+#define MM_FWD1(HD, MD)                                                                          \
+  {                                                                                              \
+    MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_fwd_kernel<HD, MD>,                              \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+    MM_CUDA_OK(mm_launch(resattn_mma_fwd_kernel<HD, MD>, dim3((unsigned)ctas),                   \
+                         dim3(FWD_WARPS * 32), smem, st, T));                                    \
+  }
 #define MM_FWD(HD)                                                                               \
   {                                                                                              \
-    MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_fwd_kernel<HD>,                                  \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-    MM_CUDA_OK(mm_launch(resattn_mma_fwd_kernel<HD>, dim3((unsigned)ctas), dim3(FWD_WARPS * 32), \
-                         smem, st, T));                                                          \
+    if (mode == M_PLAIN) MM_FWD1(HD, M_PLAIN)                                                    \
+    else if (mode == M_FIRST) MM_FWD1(HD, M_FIRST)                                               \
+    else if (mode == M_MID) MM_FWD1(HD, M_MID)                                                   \
+    else if (mode == M_LAST) MM_FWD1(HD, M_LAST)                                                 \
+    else MM_FWD1(HD, M_GEN)                                                                      \
   }
   if (hd == 16) MM_FWD(16) else if (hd == 32) MM_FWD(32) else MM_FWD(64)
 #undef MM_FWD
+#undef MM_FWD1
+  return MMEMO_OK;
+}
+}  // namespace
+
+int resattn_mma_fwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
+  if (n < 1 || n > MAXP) return MMEMO_ERR_ARG;
+  const int hd = (int)ps[0].hd;
+  for (int i = 0; i < n; ++i)
+    if (ps[i].hd != hd || !resattn_mma_supported(ps[i], false)) return MMEMO_ERR_SHAPE;
+  // one launch per instantiation present (the problems of a trunk layer share their flags: one)
+  for (int mode = M_GEN; mode <= M_LAST; ++mode) {
+    const int rc = fwd_launch(ps, n, mode, st);
+    if (rc) return rc;
+  }
   return MMEMO_OK;
 }
 
@@ -827,7 +1001,7 @@ int bwd_warps(int64_t Lq) {
   return w < 2 ? 2 : w;
 }
 
-int bwd_launch(const mmemo_attn_problem* const* ps, int n, int warps, cudaStream_t st) {
+int bwd_launch(const mmemo_attn_problem* const* ps, int n, int warps, int mode, cudaStream_t st) {
   static thread_local Table T;
   T.n = n;
   const int hd = (int)ps[0]->hd;
@@ -865,12 +1039,37 @@ int bwd_launch(const mmemo_attn_problem* const* ps, int n, int warps, cudaStream
     if (e[0] == '6' && smem64 <= SMEM_MAX) kb64 = true;
     if (e[0] == '3') kb64 = false;
   }
+  // dQ in registers: hd = 16 (8 registers per tile), 32-key blocks, <= 3 row tiles per warp
+  // (only where the fp32 tile costs a resident CTA: the register version needs ~30 more registers)
+  bool dqreg = hd == 16 && !kb64 && !blocked && smem32 > 70 * 1024 && !getenv("MMEMO_ATTN_DQSMEM");
+  for (int i = 0; i < n && dqreg; ++i) dqreg = cdiv(cdiv(ps[i]->Lq, 16), warps) <= 3;
+  if (dqreg) {
+    smem32 = 0;
+    for (int i = 0; i < n; ++i) {
+      const bool same = ps[i]->k == ps[i]->v && ps[i]->ldk == ps[i]->ldv;
+      const size_t s32 = bwd_smem(hd, 32, (int)ps[i]->Lq, (int)ps[i]->Lk, same, false, true);
+      smem32 = s32 > smem32 ? s32 : smem32;
+    }
+  }
+#define MM_BWD2(HD, KBK, PL, DQ, SM)                                                              \
+  {                                                                                               \
+    MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_bwd_kernel<HD, KBK, PL, DQ>,                      \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)));     \
+    MM_CUDA_OK(mm_launch(resattn_mma_bwd_kernel<HD, KBK, PL, DQ>, dim3((unsigned)ctas),           \
+                         dim3((unsigned)(warps * 32)), SM, st, T));                               \
+  }
+#define MM_BWD1(HD, KBK, PL, SM)                                                                  \
+  {                                                                                               \
+    if (HD == 16 && KBK == 32 && dqreg) MM_BWD2(16, 32, PL, true, SM)                             \
+    else MM_BWD2(HD, KBK, PL, false, SM)                                                          \
+  }
 #define MM_BWD(HD, KBK, SM)                                                                       \
   {                                                                                               \
-    MM_CUDA_OK(cudaFuncSetAttribute(resattn_mma_bwd_kernel<HD, KBK>,                              \
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM)));     \
-    MM_CUDA_OK(mm_launch(resattn_mma_bwd_kernel<HD, KBK>, dim3((unsigned)ctas),                   \
-                         dim3((unsigned)(warps * 32)), SM, st, T));                               \
+    if (mode == M_PLAIN) MM_BWD1(HD, KBK, M_PLAIN, SM)                                            \
+    else if (mode == M_FIRST) MM_BWD1(HD, KBK, M_FIRST, SM)                                       \
+    else if (mode == M_MID) MM_BWD1(HD, KBK, M_MID, SM)                                           \
+    else if (mode == M_LAST) MM_BWD1(HD, KBK, M_LAST, SM)                                         \
+    else MM_BWD1(HD, KBK, M_GEN, SM)                                                              \
   }
   if (kb64) {
     if (hd == 16) MM_BWD(16, 64, smem64) else if (hd == 32) MM_BWD(32, 64, smem64)
@@ -880,6 +1079,8 @@ int bwd_launch(const mmemo_attn_problem* const* ps, int n, int warps, cudaStream
     else MM_BWD(64, 32, smem32)
   }
 #undef MM_BWD
+#undef MM_BWD1
+#undef MM_BWD2
   return MMEMO_OK;
 }
 }  // namespace
@@ -891,19 +1092,20 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
     if (ps[i].hd != hd || !resattn_mma_supported(ps[i], true)) return MMEMO_ERR_SHAPE;
   int fixed = 0;
   if (const char* e = getenv("MMEMO_ATTN_WARPS")) fixed = atoi(e);      // experiments
-  // one launch per CTA size (all chains of realformer / robot_demo share one; Ren-MME's three
-  // query lengths give three)
+  // one launch per (CTA size, instantiation): all chains of realformer / robot_demo share one;
+  // Ren-MME's three query lengths give three
   const mmemo_attn_problem* sel[MAXP];
   bool done[MAXP] = {};
   for (int i = 0; i < n; ++i) {
     if (done[i]) continue;
     const int w = (fixed >= 2 && fixed <= BWD_WARPS) ? fixed : bwd_warps(ps[i].Lq);
+    const int mode = bwd_mode(ps[i]);
     int m = 0;
     for (int j = i; j < n; ++j) {
       const int wj = (fixed >= 2 && fixed <= BWD_WARPS) ? fixed : bwd_warps(ps[j].Lq);
-      if (!done[j] && wj == w) { sel[m++] = &ps[j]; done[j] = true; }
+      if (!done[j] && wj == w && bwd_mode(ps[j]) == mode) { sel[m++] = &ps[j]; done[j] = true; }
     }
-    const int rc = bwd_launch(sel, m, w, st);
+    const int rc = bwd_launch(sel, m, w, mode, st);
     if (rc) return rc;
   }
   return MMEMO_OK;
