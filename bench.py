@@ -811,11 +811,13 @@ def main():
     reducer = None
     if world > 1:   # knobs for experiments; the defaults are the product configuration
         reducer = mdp.GradReducer(
-            model, world, bucket_bytes=int(float(os.environ.get("MMEMO_BUCKET_MB", "16")) * (1 << 20)),
+            model, world, bucket_bytes=int(float(os.environ.get("MMEMO_BUCKET_MB", "8")) * (1 << 20)),
             zero_copy=os.environ.get("MMEMO_ZERO_COPY", "1") == "1",
             sm_reserve=int(os.environ.get("MMEMO_SM_RESERVE", os.environ.get("NCCL_MAX_CTAS", "16"))),
             transport=os.environ.get("MMEMO_DP_TRANSPORT", "auto"),
-            comm_blocks=int(os.environ.get("MMEMO_COMM_BLOCKS", "16")))
+            comm_blocks=int(os.environ.get("MMEMO_COMM_BLOCKS", "16")),
+            symm_sm_reserve=int(os.environ.get("MMEMO_SYMM_SM_RESERVE", "16")),
+            reserve_launches=int(os.environ.get("MMEMO_RESERVE_LAUNCHES", "5")))
 
     def step():
         model.zero_grad(set_to_none=True)
@@ -999,7 +1001,9 @@ def main():
         g2 = None
         # (b) reduced gradients of a probe (first parameter of every bucket) vs an NCCL all-reduce
         # of the ranks' local gradients
-        probes = [b.params[0] for b in reducer.buckets]
+        # (a weight matrix: its gradient is a two-slice split-K sum, bit-reproducible between the
+        # two backward passes compared here; LayerNorm / gate gradients are atomics-ordered)
+        probes = [next((p for p in b.params if p.dim() >= 2), b.params[0]) for b in reducer.buckets]
         reducer.enabled = False
         step()
         ref = [p.grad.detach().clone() for p in probes]

@@ -11,9 +11,11 @@
  * Conventions
  *   - every pointer is a DEVICE pointer unless the comment says "host"; buffers are owned by the
  *     caller; nothing here allocates or synchronises; all work is enqueued on `stream` (a
- *     cudaStream_t passed as void*).  The only process-wide state are the three settings of the
- *     "library / device info" block (split-K workspace, SM budget, programmatic dependent launch);
- *     one process drives one GPU.
+ *     cudaStream_t passed as void*).  The library keeps NO process-wide mutable state: the three
+ *     launch settings of the "library / device info" block (split-K workspace, SM budget,
+ *     programmatic dependent launch) are attributes of a STREAM, read by the entry points from the
+ *     stream they are given, so host threads driving different streams are independent
+ *     (re-entrant); the last-error string is thread-local.
  *   - return 0 on success, <0 on error (MMEMO_ERR_*).  No CPU fallback exists.
  *   - suffix _f32 / _bf16 = dtype of ACTIVATIONS and GEMM weights (T).  Small parameter vectors
  *     (bias, LayerNorm gamma/beta, gates a/b/c, position tables) and ALL parameter gradients are
@@ -40,18 +42,24 @@ typedef void* mmemo_stream_t; /* cudaStream_t */
 /* library / device info */
 int mmemo_version(void);
 const char* mmemo_last_error(void); /* host string describing the last MMEMO_ERR_CUDA */
-/* Scratch for split-K partial tiles of the tcgen05 GEMM (weight-gradient shapes).  The library
- * never allocates: the host registers one device buffer per process (one process per GPU); kernels
- * that need more than `bytes` simply do not split.  Launches that use it must be stream-ordered. */
-int mmemo_set_workspace(void* ptr, int64_t bytes);
-/* Number of SMs the persistent (one CTA per SM) kernels may occupy; 0 = all.  Data-parallel
- * training sets it below the SM count so that the NCCL all-reduce kernels overlapped with backward
- * have SMs of their own instead of delaying the last CTAs of a persistent grid. */
-int mmemo_set_sm_budget(int n_sms);
-/* Programmatic dependent launch for the hot kernels (tcgen05 GEMM / attention, vector LayerNorm,
- * column sums, weight casts): the next kernel's prologue overlaps the previous kernel's drain.
- * On by default; 0 launches every kernel fully serialised. */
-int mmemo_set_pdl(int enabled);
+/* Per-stream launch settings.  Every entry point below looks them up by the `stream` argument of
+ * the call (defaults for a stream that was never configured: no workspace, all SMs, PDL on).
+ *  - workspace: scratch for split-K partial tiles of the tcgen05 GEMM when the output is bf16 or
+ *    carries a bias (fp32 weight gradients are summed by TMA reduce-add and need none).  The
+ *    library never allocates: the host attaches one device buffer to each stream it launches on;
+ *    launches of one stream are ordered, so they can share it, and two streams never share one.
+ *    A GEMM that would need more than `bytes` simply does not split.
+ *  - sm_budget: number of SMs the persistent (one CTA per SM) kernels launched on the stream may
+ *    occupy; 0 = all.  Data-parallel training lowers it for the GEMMs that follow a bucket
+ *    all-reduce, so that the collective's CTAs have SMs of their own.
+ *  - pdl: programmatic dependent launch for the hot kernels (tcgen05 GEMM / attention, vector
+ *    LayerNorm, column sums, weight casts): the next kernel's prologue overlaps the previous
+ *    kernel's drain.  On by default; 0 launches every kernel of the stream fully serialised.
+ *  - reset: forget the stream (call before cudaStreamDestroy; handles can be reused by CUDA). */
+int mmemo_stream_set_workspace(mmemo_stream_t stream, void* ptr, int64_t bytes);
+int mmemo_stream_set_sm_budget(mmemo_stream_t stream, int n_sms);
+int mmemo_stream_set_pdl(mmemo_stream_t stream, int enabled);
+int mmemo_stream_reset(mmemo_stream_t stream);
 /* 1 if (M,N,K,mode) is served by the tcgen05/TMA tensor-core GEMM, 0 if by the SIMT GEMM */
 int mmemo_gemm_uses_tensor_cores(int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                                  int64_t ldc, int mode);

@@ -43,9 +43,10 @@ class AttnProblem(C.Structure):
 
 SIGNATURES = {
     "mmemo_version": [],
-    "mmemo_set_workspace": [_vp, _i64],
-    "mmemo_set_sm_budget": [_i32],
-    "mmemo_set_pdl": [_i32],
+    "mmemo_stream_set_workspace": [_vp, _vp, _i64],
+    "mmemo_stream_set_sm_budget": [_vp, _i32],
+    "mmemo_stream_set_pdl": [_vp, _i32],
+    "mmemo_stream_reset": [_vp],
     "mmemo_gemm_uses_tensor_cores": [_i64, _i64, _i64, _i64, _i64, _i64, _i32],
     "mmemo_resattn_uses_tensor_cores": [_i64, _i64, _i64, _i64],
     "mmemo_linear_fwd_f32": _LINEAR_FWD, "mmemo_linear_fwd_bf16": _LINEAR_FWD,
@@ -120,8 +121,6 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.mmemo_last_error.argtypes = []
     lib.mmemo_last_error.restype = C.c_char_p
-    if os.environ.get("MMEMO_PDL", "1") == "0":     # debugging knob: fully serialised launches
-        lib.mmemo_set_pdl(0)
     _lib = lib
     return lib
 

@@ -90,6 +90,12 @@ class FullAttentionBlock(nn.Module):
                 self.ffn[0].weight, self.ffn[0].bias, self.ffn[2].weight, self.ffn[2].bias,
                 self.a, self.b, self.c]
 
+    def mmemo_grad_unit(self):
+        """dp.GradReducer protocol: the parameters whose gradients the fused backward accumulates
+        into ONE zero-filled buffer, with their offsets (the reducer carves that buffer out of an
+        all-reduce bucket, so nothing is copied)."""
+        return ops.full_block_grad_layout(self._params())
+
     def multi_head_attention(self, q, k, v, mask, scores=None):
         """Projected attention + output projection; returns (drop(proj(att v)), scores)."""
         bf = is_bf16()

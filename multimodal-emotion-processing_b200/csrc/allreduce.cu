@@ -8,8 +8,12 @@
 //
 // Blocks of the same index on all ranks meet at a flag barrier in the ranks' signal pads before
 // (every rank's gradients are written) and after (every replica is complete).  The kernel needs
-// no shared memory and few registers, so its CTAs co-reside with the persistent GEMM CTAs instead
-// of taking SMs away from them.
+// no shared memory and its CTAs are 256 threads x <= 96 registers (24 576 registers), which is what
+// a persistent GEMM CTA (320 threads x 128) or a tcgen05 attention CTA leaves free on an SM: the
+// all-reduce co-resides with them instead of queueing behind one-CTA-per-SM grids whose work is
+// partitioned statically (a 512-thread version could not, and the GEMMs it delayed exposed nearly
+// the whole transfer).  The LayerNorm backward fills the register file, so it and the GEMMs shrink
+// their grids by the stream's SM budget while a bucket is in flight (dp.GradReducer).
 #include "common.cuh"
 
 namespace {
@@ -68,10 +72,11 @@ __device__ __forceinline__ void mc_st(float* mc, float4 v) {
 }
 
 constexpr int kMaxWorld = 16;
-constexpr int kUnroll = 8;
+constexpr int kUnroll = 12;
+constexpr int kThreads = 256;
 
 template <bool NVLS>
-__global__ void __launch_bounds__(512)
+__global__ void __maxnreg__(96)
 allreduce_kernel(float* mc, float* const* bufs, uint32_t* const* pads, int slot_base,
                  int64_t offset, int64_t n, int rank, int world) {
     rank_barrier(pads, slot_base, rank, world);
@@ -139,11 +144,11 @@ extern "C" int mmemo_allreduce_sum_f32(void* multicast_ptr, void* const* buffer_
     auto bufs = reinterpret_cast<float* const*>(buffer_ptrs_dev);
     auto pads = reinterpret_cast<uint32_t* const*>(signal_pad_ptrs_dev);
     if (multicast_ptr)
-        allreduce_kernel<true><<<blocks, 512, 0, s>>>(static_cast<float*>(multicast_ptr), bufs,
+        allreduce_kernel<true><<<blocks, kThreads, 0, s>>>(static_cast<float*>(multicast_ptr), bufs,
                                                       pads, (int)signal_slot_base, offset_elems,
                                                       n_elems, rank, world);
     else
-        allreduce_kernel<false><<<blocks, 512, 0, s>>>(nullptr, bufs, pads, (int)signal_slot_base,
+        allreduce_kernel<false><<<blocks, kThreads, 0, s>>>(nullptr, bufs, pads, (int)signal_slot_base,
                                                        offset_elems, n_elems, rank, world);
     MM_LAUNCH_OK();
     return MMEMO_OK;

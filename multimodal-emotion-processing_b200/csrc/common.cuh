@@ -33,7 +33,15 @@ static inline cudaStream_t mm_stream(mmemo_stream_t s) { return reinterpret_cast
 // completed and its writes are visible.  Every thread of such a kernel calls pdl_wait() before
 // its first global-memory access (reads AND writes: buffers are recycled between kernels) and
 // before any early return, so completion order stays transitive along the stream.
-extern int g_mm_pdl;   // lib.cu; mmemo_set_pdl
+// Per-stream launch settings (lib.cu; mmemo_stream_set_*): split-K scratch of the tcgen05 GEMM,
+// SMs the persistent kernels may occupy (0 = all), programmatic dependent launch on/off.
+struct MmStreamCfg {
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  int sm_budget = 0;
+  int pdl = 1;
+};
+MmStreamCfg mm_stream_cfg(cudaStream_t st);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 
@@ -49,7 +57,7 @@ static inline cudaError_t mm_launch(void (*kern)(KArgs...), dim3 grid, dim3 bloc
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = g_mm_pdl ? 1 : 0;
+  cfg.numAttrs = mm_stream_cfg(st).pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

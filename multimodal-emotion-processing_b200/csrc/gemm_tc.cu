@@ -70,6 +70,8 @@ template <int NG> struct TmapGroup { CUtensorMap a[NG], b[NG], c[NG], aux[NG]; }
 template <int NG> struct GroupArgs {
   int n;
   int any_aux;             // some problem of the launch prefetches an aux tile (owns the second 32 KB)
+  int streamk;             // 1: item_start counts K-BLOCKS (tiles x kb_total per problem) and every
+  int kb_per_unit;         //    unit owns one contiguous range of kb_per_unit of them (see below)
   int item_start[NG + 1];
   TcArgs p[NG];
 };
@@ -106,9 +108,48 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     while (g + 1 < G.n && w >= G.item_start[g + 1]) ++g;
     lw = w - G.item_start[g];
   };
-  auto decode = [&](const TcArgs& a, int lw, int& m0, int& n0, int& sp, int& tile) {
-    sp = lw % a.splits;
-    tile = lw / a.splits;
+  // The work of a unit (CTA or CTA pair) is a sequence of SEGMENTS = (problem, output tile, range
+  // of k-blocks); one accumulator pass each.
+  //   regular : items (tile, split-K slice) numbered problem by problem; unit u takes items
+  //             u, u + units, ...
+  //   stream-K: (weight gradients: few output tiles, long K, fp32 C summed by TMA reduce-add) the
+  //             k-blocks of ALL tiles of all problems form one line, cut into `units` equal
+  //             ranges; a unit's range covers the tail of one tile and the head of the next, so
+  //             every unit gets the same number of MMAs whatever the tile count (32 tiles on 74
+  //             pairs: 86 % -> 99 % of the pairs busy).
+  struct WorkIter { int pos, end, g; };
+  auto iter_init = [&](WorkIter& it) {
+    it.g = 0;
+    if (G.streamk) {
+      it.pos = unit * G.kb_per_unit;
+      it.end = min(total, it.pos + G.kb_per_unit);
+    } else {
+      it.pos = unit;
+      it.end = total;
+    }
+  };
+  auto iter_next = [&](WorkIter& it, int& g, int& tile, int& sp, int& kb_beg, int& kb_end) -> bool {
+    if (it.pos >= it.end) return false;
+    int lw;
+    locate(it.pos, it.g, lw);
+    g = it.g;
+    const TcArgs& a = G.p[g];
+    if (G.streamk) {
+      tile = lw / a.kb_total;
+      kb_beg = lw - tile * a.kb_total;
+      kb_end = min(a.kb_total, kb_beg + (it.end - it.pos));
+      sp = 0;
+      it.pos += kb_end - kb_beg;
+    } else {
+      sp = lw % a.splits;
+      tile = lw / a.splits;
+      kb_beg = sp * a.kb_per;
+      kb_end = min(a.kb_total, kb_beg + a.kb_per);
+      it.pos += units;
+    }
+    return true;
+  };
+  auto tile_origin = [&](const TcArgs& a, int tile, int& m0, int& n0) {
     const int tm = tile / a.tiles_n, tn = tile - tm * a.tiles_n;
     m0 = tm * TM + (int)rank * BM;     // rows owned by this CTA
     n0 = tn * BN;                      // first column of the (pair) tile
@@ -129,7 +170,11 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     tc::tma_prefetch_desc(&TMS.b[0]);
     tc::tma_prefetch_desc(&TMS.c[0]);
   }
-  pdl_wait();
+  // The dependents may be scheduled right away; this kernel's own setup (barriers, TMEM, the
+  // pair's first cluster barrier) touches no global memory and overlaps the previous kernel's
+  // drain.  griddepcontrol.wait comes right before the first global access of each role: the TMA
+  // producer (everything the MMA issuer and the epilogue consume derives from its loads) and the
+  // epilogue threads (bias / position-table reads, aux loads, stores).
   pdl_trigger();
   if (warp == 1) {
     if (CTA2) { tc::tmem_alloc_2sm(tmem_slot, 2 * BN); tc::tmem_relinquish_2sm(); }
@@ -143,17 +188,18 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
   if (warp == 0) {
     // ================= TMA producer (every CTA stages its own rows of A and columns of B) =========
     if (lane == 0) {
+      pdl_wait();
       uint32_t it = 0;
-      int g = 0;
-      for (int w = unit; w < total; w += units) {
-        int lw, m0, n0, sp, tile;
-        locate(w, g, lw);
+      WorkIter wi;
+      iter_init(wi);
+      int g, tile, sp, kb_beg, kb_end;
+      while (iter_next(wi, g, tile, sp, kb_beg, kb_end)) {
+        int m0, n0;
         const TcArgs& a = G.p[g];
         const CUtensorMap* tmA = &TMS.a[g];
         const CUtensorMap* tmB = &TMS.b[g];
-        decode(a, lw, m0, n0, sp, tile);
+        tile_origin(a, tile, m0, n0);
         const int nb = n0 + (int)rank * 128;           // this CTA's 128 columns of B
-        const int kb_beg = sp * a.kb_per, kb_end = min(a.kb_total, kb_beg + a.kb_per);
         for (int kb = kb_beg; kb < kb_end; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           tc::mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -184,13 +230,11 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     // ================= MMA issuer (leader CTA only) =================
     if (lane == 0 && rank == 0) {
       uint32_t it = 0, ti = 0;
-      int g = 0;
-      for (int w = unit; w < total; w += units, ++ti) {
-        int lw;
-        locate(w, g, lw);
+      WorkIter wi;
+      iter_init(wi);
+      int g, tile, sp, kb_beg, kb_end;
+      for (; iter_next(wi, g, tile, sp, kb_beg, kb_end); ++ti) {
         const TcArgs& a = G.p[g];
-        const int sp = lw % a.splits;
-        const int kb_beg = sp * a.kb_per, kb_end = min(a.kb_total, kb_beg + a.kb_per);
         const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
         tc::mbar_wait(bar_acce + 8 * buf, aph ^ 1);     // epilogues have drained this accumulator
         tc::tc_fence_after();
@@ -227,29 +271,31 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     const int te = threadIdx.x - 64;
     // step = (work item, 128-column half); aux tile of a step: old C (accumulate) or the saved
     // activation (ReLU mask), bf16, prefetched one step ahead (issue order == consumption order)
-    int g_aux = 0;                 // cursor of the aux prefetches (they run one step ahead)
-    auto issue_aux = [&](int w, int half) {
-      int lw, m0, n0, sp, tile;
-      locate(w, g_aux, lw);
-      const int g = g_aux;
+    auto issue_aux = [&](int g, int tile, int half) {
       if (!G.p[g].aux) return;
-      decode(G.p[g], lw, m0, n0, sp, tile);
+      int m0, n0;
+      tile_origin(G.p[g], tile, m0, n0);
       tc::mbar_expect_tx(bar_aux, 32 * 1024);
       tc::tma_load_2d(sAux, &TMS.aux[g], n0 + half * 128, m0, bar_aux);
       tc::tma_load_2d(sAux + 16384, &TMS.aux[g], n0 + half * 128 + 64, m0, bar_aux);
     };
-    if (te == 0 && unit < total) issue_aux(unit, 0);
+    pdl_wait();
+    WorkIter wi;
+    iter_init(wi);
+    int g, tile, sp, kb_beg, kb_end;
+    if (te == 0 && G.any_aux) {    // aux tile of the first step
+      WorkIter first = wi;
+      if (iter_next(first, g, tile, sp, kb_beg, kb_end)) issue_aux(g, tile, 0);
+    }
     uint32_t ti = 0, aux_ctr = 0, step = 0;
     bool prev_f32 = true;          // the previous step's store may span both staging buffers
-    int g = 0;
-    for (int w = unit; w < total; w += units, ++ti) {
-      int lw, m0, n0, sp, tile;
-      locate(w, g, lw);
+    for (; iter_next(wi, g, tile, sp, kb_beg, kb_end); ++ti) {
+      int m0, n0;
       const TcArgs& a = G.p[g];
       const CUtensorMap* tmC = &TMS.c[g];
-      const bool partial = a.splits > 1;
+      const bool partial = a.splits > 1 || G.streamk;
       const bool out_f32 = partial || !a.c_bf16;
-      decode(a, lw, m0, n0, sp, tile);
+      tile_origin(a, tile, m0, n0);
       const int64_t m = (int64_t)m0 + row;
       const int pos_row = a.pos ? (int)((uint32_t)(m0 + row) % (uint32_t)a.pos_period) : 0;
       const uint32_t buf = ti & 1, aph = (ti >> 1) & 1;
@@ -367,8 +413,15 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
           }
           tc::tma_store_commit();
           // prefetch the aux tile of the next step (if that step has one)
-          if (half + 1 < NHALF) issue_aux(w, half + 1);
-          else if (w + units < total) issue_aux(w + units, 0);
+          if (G.any_aux) {
+            if (half + 1 < NHALF) {
+              issue_aux(g, tile, half + 1);
+            } else {
+              WorkIter nx = wi;      // (wi already points past the current segment)
+              int g2, t2, s2, b2, e2;
+              if (iter_next(nx, g2, t2, s2, b2, e2)) issue_aux(g2, t2, 0);
+            }
+          }
         }
       }
     }
@@ -420,23 +473,16 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const ReduceArgs a) 
   }
 }
 
-float* g_ws = nullptr;
-size_t g_ws_bytes = 0;
-int g_sm_budget = 0;    // SMs the persistent kernels may occupy (0 = all); mmemo_set_sm_budget
-
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  // a communication kernel running concurrently (NCCL all-reduce overlapped with backward) holds
-  // some SMs; a persistent grid larger than what is free would serialise its last CTAs
-  return (g_sm_budget > 0 && g_sm_budget < n) ? g_sm_budget : n;
+int num_sms(int sm_budget) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = 148;
+  // a communication kernel running concurrently (all-reduce overlapped with backward) holds some
+  // SMs; a persistent grid larger than what is free would serialise its last CTAs
+  return (sm_budget > 0 && sm_budget < n) ? sm_budget : n;
 }
 
 bool make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int rank,
@@ -458,16 +504,6 @@ bool make_tmap(CUtensorMap* out, CUtensorMapDataType dt, const void* base, int r
 }
 
 }  // namespace
-
-extern "C" int mmemo_set_workspace(void* ptr, int64_t bytes) {
-  g_ws = static_cast<float*>(ptr);
-  g_ws_bytes = ptr ? (size_t)bytes : 0;
-  return MMEMO_OK;
-}
-extern "C" int mmemo_set_sm_budget(int n_sms) {
-  g_sm_budget = n_sms;
-  return MMEMO_OK;
-}
 
 PFN_encodeTiled mm_get_encode_tiled() {
   static PFN_encodeTiled fn = nullptr;
@@ -521,6 +557,9 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, NG, FAM>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  const MmStreamCfg scfg = mm_stream_cfg(st);    // this stream's workspace / SM budget / PDL
+  float* const ws = scfg.ws;
+  const size_t ws_bytes = scfg.ws_bytes;
   // CTA pairs (256 x 256 tiles) when every output is wide and tall enough to fill them
   bool cta2 = true;
   for (int i = 0; i < n; ++i) cta2 = cta2 && gs[i].N >= 256 && gs[i].M >= 256;
@@ -534,12 +573,12 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
       else if (v > 1) {
         long pt = 0;
         for (int i = 0; i < n; ++i) pt += cdiv(gs[i].M, 256) * cdiv(gs[i].N, 256);
-        if (pt * 100 < (long)v * (num_sms() / 2)) cta2 = false;   // v = percent of one pair wave
+        if (pt * 100 < (long)v * (num_sms(scfg.sm_budget) / 2)) cta2 = false;   // v = percent of one pair wave
       }
     }
   }
   const int TM = cta2 ? 256 : 128, BN = cta2 ? 256 : 128;
-  const int sms = num_sms();
+  const int sms = num_sms(scfg.sm_budget);
   const int units_max = cta2 ? sms / 2 : sms;      // schedulable work units (pairs or CTAs)
   // split-K when the outputs have too few tiles to occupy the machine and K is long (needs linear
   // epilogues: bias and accumulate are applied after / by the reduction)
@@ -554,13 +593,35 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     all_reduce_add = all_reduce_add && !c_bf16s[i] && !g.bias;   // fp32 C summed by TMA reduce-add
   }
   int splits = 1;
-  if (tiles_sum * 2 <= units_max && kb_min >= 16 && linear && (all_reduce_add || n == 1)) {
+  // Stream-K (see the kernel): fp32 outputs summed by TMA reduce-add.  Each unit gets
+  // ceil(total k-blocks / units) consecutive k-blocks, so problems of very different K share the
+  // machine evenly (Ren-MME layer, 48 weight gradients with K = 10 240 ... 70 400 rows: 127 ->
+  // 104 us).  Only for launches whose problems have at most two output tiles each: tiles of ONE
+  // problem share operand strips, and the regular item list keeps them in lockstep along K so
+  // that a strip is fetched from HBM once; stream-K ranges start at unrelated k offsets and
+  // measured 166 vs 108 us on the 32-tile weight-gradient group of the seq-256 encoder (operand
+  // traffic 1.07 GB instead of 0.44 GB) and 32.9 vs 31.7 us at seq 128.
+  int64_t kb_sum = 0;
+  int tiles_max = 0;
+  for (int i = 0; i < n; ++i) {
+    const int t = (int)(cdiv(gs[i].M, TM) * cdiv(gs[i].N, BN));
+    tiles_max = t > tiles_max ? t : tiles_max;
+    kb_sum += t * cdiv(gs[i].K, BK);
+  }
+  int kb_per_unit = (int)cdiv(kb_sum, units_max);
+  bool streamk = linear && all_reduce_add && kb_min >= 16 && tiles_max <= 2 && n > 1 &&
+                 kb_per_unit >= 8 && kb_sum < (1ll << 30);
+  {
+    const char* env = getenv("MMEMO_GEMM_STREAMK");     // A/B knob: 0 = the split-K item list
+    if (env && env[0] == '0') streamk = false;
+  }
+  if (!streamk && tiles_sum * 2 <= units_max && kb_min >= 16 && linear && (all_reduce_add || n == 1)) {
     splits = units_max / tiles_sum;                     // one balanced round of work items
     if (splits > kb_min / 4) splits = kb_min / 4;
     if (splits > 32) splits = 32;
     if (!all_reduce_add) {
       const size_t per_split = (size_t)tiles_sum * TM * BN * sizeof(float);
-      if (per_split * (size_t)splits > g_ws_bytes) splits = (int)(g_ws_bytes / per_split);
+      if (per_split * (size_t)splits > ws_bytes) splits = (int)(ws_bytes / per_split);
     }
     if (splits < 2) splits = 1;
   }
@@ -569,6 +630,8 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
   static thread_local GroupArgs<NG> G;
   G = GroupArgs<NG>{};
   G.n = n;
+  G.streamk = streamk ? 1 : 0;
+  G.kb_per_unit = kb_per_unit;
   int items = 0;
   bool ok = true;
   for (int i = 0; i < n; ++i) {
@@ -581,7 +644,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     const int kb_total = (int)cdiv(g.K, BK);
     const int kb_per = (int)cdiv(kb_total, splits);
     const int sp = (int)cdiv(kb_total, kb_per);        // every slice owns >= 1 k-block
-    const bool partial = sp > 1;
+    const bool partial = sp > 1 || streamk;
     const bool reduce_add = partial && all_reduce_add;
     const int aux = partial ? AUX_NONE : (g.relu_src ? AUX_RELU : (g.accumulate ? AUX_ACC : AUX_NONE));
     uint64_t dims[2], str[1];
@@ -595,7 +658,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     if (partial && !reduce_add) {     // n == 1 here
       dims[0] = BN; dims[1] = (uint64_t)tiles * sp * TM; str[0] = (uint64_t)BN * 4;
       box[0] = 32; box[1] = BM;
-      ok = ok && mm_make_tmap_f32(&tms.c[i], g_ws, 2, dims, str, box);
+      ok = ok && mm_make_tmap_f32(&tms.c[i], ws, 2, dims, str, box);
     } else if (!c_bf16) {
       dims[0] = g.N; dims[1] = g.M; str[0] = g.ldc * 4; box[0] = 32; box[1] = BM;
       ok = ok && mm_make_tmap_f32(&tms.c[i], g.C, 2, dims, str, box);
@@ -625,7 +688,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     a.reduce_add = reduce_add;
     a.tiles_m = tiles_m; a.tiles_n = tiles_n;
     G.item_start[i] = items;
-    items += tiles * sp;
+    items += streamk ? tiles * kb_total : tiles * sp;
     if (reduce_add && !g.accumulate && !g.c_zeroed)   // the slices accumulate into C: start from zero
       MM_CUDA_OK(cudaMemset2DAsync(g.C, g.ldc * sizeof(float), 0, g.N * sizeof(float), g.M, st));
   }
@@ -634,7 +697,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     mmemo_set_error("cuTensorMapEncodeTiled failed (gemm_tc)", __FILE__, __LINE__);
     return MMEMO_ERR_CUDA;
   }
-  const int units = items < units_max ? items : units_max;
+  const int units = streamk ? (int)cdiv(items, kb_per_unit) : (items < units_max ? items : units_max);
   if (cta2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * units));
@@ -649,7 +712,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = g_mm_pdl ? 2 : 1;
+    cfg.numAttrs = scfg.pdl ? 2 : 1;
     MM_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<true, NG, FAM>, tms, G));
   } else {
     MM_CUDA_OK(mm_launch(gemm_tc_kernel<false, NG, FAM>, dim3((unsigned)units), dim3(NTHREADS),
@@ -658,7 +721,7 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
   if (n == 1 && G.p[0].splits > 1 && !G.p[0].reduce_add) {
     const GemmArgs& g = gs[0];
     ReduceArgs r = {};
-    r.partial = g_ws; r.C = g.C; r.ldc = g.ldc; r.M = (int)g.M; r.N = (int)g.N;
+    r.partial = ws; r.C = g.C; r.ldc = g.ldc; r.M = (int)g.M; r.N = (int)g.N;
     r.splits = G.p[0].splits; r.tiles_n = G.p[0].tiles_n; r.c_bf16 = c_bf16s[0];
     r.accumulate = g.accumulate;
     r.tm_rows = TM; r.bn_cols = BN;

@@ -674,8 +674,13 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
   if (vec && !relu && (dgamma || dbeta || dxsum) && cdiv(d / V, 32) * V <= 16) {
     // single pass (<= 16 columns per lane keep the accumulators in registers): one persistent
     // 16-warp CTA per SM
+    // one full-register-file CTA per SM, rows strided: like the persistent GEMM it honours the
+    // stream's SM budget, so that a gradient all-reduce in flight keeps SMs of its own instead of
+    // making the last CTAs of this grid wait for it
+    const int sb = mm_stream_cfg(st).sm_budget;
+    const int64_t sms = (sb > 0 && sb < 148) ? sb : 148;
     int64_t g1 = cdiv(M, LNB_WARPS);
-    if (g1 > 148) g1 = 148;
+    if (g1 > sms) g1 = sms;
     const int nch = (int)cdiv(d / V, 32);
     const size_t sm_bytes = (1 + LNB_WARPS) * (size_t)d * sizeof(float);   // <= 34 KB
 #define MM_FUSED(NCH_)                                                                          \
@@ -802,7 +807,9 @@ int bwd_grouped(int n, const void* const* dy, const void* const* res, const void
   const int nchunk = (int)(d / V);
   const int rpw = nchunk <= 8 ? 4 : (nchunk <= 16 ? 2 : 1);
   int64_t gx = cdiv(mmax, LNB_WARPS * rpw);
-  const int64_t cap = cdiv(148, n) > 1 ? cdiv(148, n) : 1;
+  const int sb = mm_stream_cfg(st).sm_budget;
+  const int64_t sms = (sb > 0 && sb < 148) ? sb : 148;      // (see ln_bwd_fused_vec's launcher)
+  const int64_t cap = cdiv(sms, n) > 1 ? cdiv(sms, n) : 1;
   if (gx > cap) gx = cap;
   const dim3 grid((unsigned)gx, (unsigned)n);
   const int nch = (int)cdiv(nchunk, 32);

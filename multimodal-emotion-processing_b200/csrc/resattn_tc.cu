@@ -83,12 +83,12 @@ resattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc::mbar_init(bar_o, 1);
     tc::fence_barrier_init();
   }
-  pdl_wait();
   pdl_trigger();
-  if (warp == 1) {
+  if (warp == 1) {        // TMEM allocation overlaps the previous kernel's drain
     tc::tmem_alloc(base + OFF_BAR + 64, 256);
     tc::tmem_relinquish();
   }
+  pdl_wait();             // before the first global access (mask row, TMA loads)
   if (threadIdx.x >= 64) {  // softmax threads stage the mask row (same for every query)
     const int j = threadIdx.x - 64;
     // additive mask term 1e8*(1-m), computed once per key (same fp32 ops as the reference)
@@ -402,12 +402,12 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc::mbar_init(bar_mm2, 1);
     tc::fence_barrier_init();
   }
-  pdl_wait();
   pdl_trigger();
-  if (warp == 1) {
+  if (warp == 1) {        // TMEM allocation overlaps the previous kernel's drain
     tc::tmem_alloc(base + B_OFF_BAR + 64, 512);
     tc::tmem_relinquish();
   }
+  pdl_wait();             // before the first global access (mask row, TMA loads)
   if (threadIdx.x >= 64) {
     const int j = threadIdx.x - 64;
     // additive mask term 1e8*(1-m), computed once per key (same fp32 ops as the reference)

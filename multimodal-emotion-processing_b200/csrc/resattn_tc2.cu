@@ -102,12 +102,12 @@ resattn_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tc::mbar_init(bar_o, 1);
     tc::fence_barrier_init();
   }
-  pdl_wait();
   pdl_trigger();
-  if (warp == 1) {
+  if (warp == 1) {        // TMEM allocation overlaps the previous kernel's drain
     tc::tmem_alloc(base + F_OFF_BAR + 64, 512);
     tc::tmem_relinquish();
   }
+  pdl_wait();             // before the first global access (mask row, TMA loads)
   if (threadIdx.x >= 64) {
     const int j = threadIdx.x - 64;   // 256 softmax threads = 256 keys
     mask_s[j] = a.mask ? __fmul_rn(1.0e8f, __fsub_rn(1.0f, a.mask[(int64_t)b * a.mask_bs + j])) : 0.0f;
@@ -347,12 +347,12 @@ resattn_bwd_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     tc::mbar_init(bar_free, 1);
     tc::fence_barrier_init();
   }
-  pdl_wait();
   pdl_trigger();
-  if (warp == 1) {
+  if (warp == 1) {        // TMEM allocation overlaps the previous kernel's drain
     tc::tmem_alloc(base + B_OFF_BAR + 96, 512);
     tc::tmem_relinquish();
   }
+  pdl_wait();             // before the first global access (mask row, TMA loads)
   if (threadIdx.x >= 64) {
     for (int j = threadIdx.x - 64; j < Lk; j += NSOFT)
       mask_s[j] = a.mask ? __fmul_rn(1.0e8f, __fsub_rn(1.0f, a.mask[(int64_t)b * a.mask_bs + j])) : 0.0f;

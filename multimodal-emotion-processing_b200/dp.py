@@ -58,8 +58,23 @@ def shard_batch(batch, rank: int, world: int, align: int = 1):
     return batch
 
 
+class _Unit:
+    """The parameters of one fused module whose gradients are accumulated into ONE contiguous
+    zero-filled buffer by its backward (``module.mmemo_grad_unit()``, e.g. the full
+    Attention_Block: five weight gradients + LayerNorm / bias / gate gradients).  A unit is placed
+    in a bucket as a whole, with the module's own internal offsets, so that the module's buffer is
+    a bucket region and none of its gradients is copied."""
+    __slots__ = ("key", "members", "total")
+
+    def __init__(self, key, members, total):
+        self.key, self.members, self.total = key, list(members), int(total)
+
+    def numel(self) -> int:
+        return self.total
+
+
 class _Bucket:
-    __slots__ = ("flat", "params", "offsets", "pending", "work", "todo", "base")
+    __slots__ = ("flat", "params", "offsets", "pending", "work", "todo", "base", "units")
 
     ALIGN = 1024        # bucket length granularity (floats)
 
@@ -71,15 +86,24 @@ class _Bucket:
         import math
         align = math.lcm(cls.ALIGN, 4 * max(world, 1))
         offsets, n = [], 0
-        for p in params:
+        for p in params:          # an entry is a parameter or a _Unit (offset = start of its region)
             offsets.append(n)
             n += (p.numel() + 31) // 32 * 32          # 128-byte aligned slots
         return offsets, (n + align - 1) // align * align
 
-    def __init__(self, params: Sequence[torch.nn.Parameter], flat: Optional[torch.Tensor] = None,
+    def __init__(self, entries: Sequence, flat: Optional[torch.Tensor] = None,
                  base: int = 0, world: int = 1):
-        self.params = list(params)
-        self.offsets, n = self.layout(self.params, world)
+        starts, n = self.layout(entries, world)
+        self.params, self.offsets, self.units = [], [], []
+        for e, o in zip(entries, starts):
+            if isinstance(e, _Unit):
+                self.units.append((e, o))
+                for p, rel in e.members:
+                    self.params.append(p)
+                    self.offsets.append(o + rel)
+            else:
+                self.params.append(e)
+                self.offsets.append(o)
         p0 = self.params[0]
         self.flat = (torch.zeros(n, dtype=torch.float32, device=p0.device) if flat is None
                      else flat[base:base + n])
@@ -91,9 +115,9 @@ class _Bucket:
 
 class GradReducer:
     def __init__(self, model: torch.nn.Module, world_size: Optional[int] = None,
-                 bucket_bytes: int = 16 << 20, group=None, zero_copy: bool = True,
+                 bucket_bytes: int = 8 << 20, group=None, zero_copy: bool = True,
                  sm_reserve: int = 16, reserve_launches: int = 5, transport: str = "auto",
-                 comm_blocks: int = 16):
+                 comm_blocks: int = 16, symm_sm_reserve: int = 16):
         self.model = model
         self.group = group
         self.world = world_size if world_size is not None else dist.get_world_size(group)
@@ -114,7 +138,9 @@ class GradReducer:
         self._symm = None           # (handle, comm stream) once the buckets are built
         self._flat_all = None       # the one symmetric buffer all buckets are views of
         self._nccl_sm_reserve = sm_reserve if on_cuda else 0
-        self.sm_reserve = self._nccl_sm_reserve if self.transport == "nccl" else 0
+        # (the symmetric-memory kernel: `symm_sm_reserve` SMs, 0 = share the SMs with the GEMMs)
+        self._symm_sm_reserve = symm_sm_reserve if on_cuda else 0
+        self.sm_reserve = self._nccl_sm_reserve if self.transport == "nccl" else self._symm_sm_reserve
         self.reserve_launches = reserve_launches
         self._slot: Dict[torch.nn.Parameter, tuple] = {}
         self._order: List[torch.nn.Parameter] = []
@@ -125,10 +151,33 @@ class GradReducer:
     # -- bucket construction ---------------------------------------------------------------
     def _build(self) -> None:
         """Pack the parameters that received a gradient, in readiness order, into buckets."""
-        groups, cur, size = [], [], 0
+        # fused modules declare gradient units (see _Unit); a unit enters the order where its first
+        # gradient became ready, with the members that actually receive gradients
+        got = set(self._order)
+        unit_of: Dict[torch.nn.Parameter, _Unit] = {}
+        if self.zero_copy and self._order and self._order[0].is_cuda:
+            for m in self.model.modules():
+                fn = getattr(m, "mmemo_grad_unit", None)
+                if fn is None:
+                    continue
+                key, members, total = fn()
+                members = [(p, off) for p, off in members if p in got]
+                if key in got and members and not any(p in unit_of for p, _ in members):
+                    u = _Unit(key, members, total)
+                    for p, _ in members:
+                        unit_of[p] = u
+        entries, seen = [], set()
         for p in self._order:
-            cur.append(p)
-            size += p.numel() * 4
+            u = unit_of.get(p)
+            if u is None:
+                entries.append(p)
+            elif id(u) not in seen:
+                seen.add(id(u))
+                entries.append(u)
+        groups, cur, size = [], [], 0
+        for e in entries:
+            cur.append(e)
+            size += e.numel() * 4
             if size >= self.bucket_bytes:
                 groups.append(cur)
                 cur, size = [], 0
@@ -136,16 +185,20 @@ class GradReducer:
             groups.append(cur)
         flat, bases = None, [0] * len(groups)
         if self.transport == "symm" and groups:
+            first = groups[0][0]
             flat, bases = self._try_symmetric([_Bucket.layout(g, self.world)[1] for g in groups],
-                                              groups[0][0].device)
+                                              (first.key if isinstance(first, _Unit) else first).device)
         self._flat_all = flat
         self.buckets = [_Bucket(g, flat, base, self.world) for g, base in zip(groups, bases)]
         for bi, b in enumerate(self.buckets):
+            from . import ops
+            for u, off in b.units:
+                # the module's whole gradient buffer is this bucket region
+                ops.register_zbuf_dest(u.key, b.flat, off, u.total)
             for p, off in zip(b.params, b.offsets):
                 self._slot[p] = (bi, off)
-                if p.is_cuda and p.dim() >= 2 and self.zero_copy:
+                if p.is_cuda and p.dim() >= 2 and self.zero_copy and p not in unit_of:
                     # large weights: the fused backward writes dW straight into this slot
-                    from . import ops
                     ops.register_grad_dest(p, b.flat, off)
         self._built = True
 
@@ -259,9 +312,9 @@ class GradReducer:
             else:
                 b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group,
                                          async_op=True)
-                if self.sm_reserve:
-                    from . import ops
-                    ops.reserve_sms_for(self.reserve_launches, self.sm_reserve)
+            if self.sm_reserve:
+                from . import ops
+                ops.reserve_sms_for(self.reserve_launches, self.sm_reserve)
 
     # -- public API --------------------------------------------------------------------------
     def backward(self, loss: torch.Tensor) -> None:
@@ -317,6 +370,8 @@ class GradReducer:
                     view = b.flat[off:off + p.numel()].view_as(p)
                     view.copy_(p.grad)
                     p.grad = view
+                if self.no_comm:
+                    continue
                 if self._symm is not None:
                     self._launch_symm(b)
                 else:

@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -38,31 +39,43 @@ def _p(t: Optional[Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-_workspace = {}
-WORKSPACE_BYTES = 64 << 20
+# Launch settings live with the STREAM in libmmemo (mmemo_stream_set_*): the first launch on a
+# stream attaches a split-K scratch buffer of its own (launches of one stream are ordered and can
+# share it; two streams never do), so concurrent streams - the ensemble's side streams, a capture
+# stream next to the default stream - are independent.
+_stream_ws: dict = {}
+WORKSPACE_BYTES = 32 << 20
+_PDL_OFF = os.environ.get("MMEMO_PDL", "1") == "0"     # debugging knob: fully serialised launches
 
 
-def _ensure_workspace() -> None:
-    """Register the split-K scratch buffer of the tcgen05 GEMM once per process (one GPU each)."""
-    dev = torch.cuda.current_device()
-    if dev not in _workspace:
-        buf = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=f"cuda:{dev}")
-        _lib.check(_lib.load().mmemo_set_workspace(buf.data_ptr(), buf.numel()), "set_workspace")
-        _workspace.clear()
-        _workspace[dev] = buf
+def _ensure_stream(stream: int) -> None:
+    key = (torch.cuda.current_device(), stream)
+    if key in _stream_ws:
+        return
+    lib = _lib.load()
+    buf = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=f"cuda:{key[0]}")
+    _lib.check(lib.mmemo_stream_set_workspace(stream, buf.data_ptr(), buf.numel()), "stream_set_workspace")
+    if _PDL_OFF:
+        _lib.check(lib.mmemo_stream_set_pdl(stream, 0), "stream_set_pdl")
+    _stream_ws[key] = buf
 
 
-# Data-parallel overlap: while a bucket all-reduce is in flight its NCCL CTAs hold some SMs; a
+# Data-parallel overlap: while a bucket all-reduce is in flight its CTAs hold some SMs; a
 # persistent (one CTA per SM) GEMM launched meanwhile would have that many CTAs serialised behind
 # the others (measured: 12.9 -> 23.4 us per GEMM).  dp.GradReducer therefore lowers the SM budget of
-# the next few GEMM launches after it issues an all-reduce; the countdown restores the full budget.
+# the next few GEMM launches of the compute stream after it issues an all-reduce; the countdown
+# restores the full budget.
 _budget_countdown = 0
+_budget_stream = 0
 
 
 def reserve_sms_for(n_launches: int, n_sms_reserved: int) -> None:
-    global _budget_countdown
+    global _budget_countdown, _budget_stream
     total = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    _lib.check(_lib.load().mmemo_set_sm_budget(max(2, (total - n_sms_reserved) // 2 * 2)), "sm_budget")
+    release_sms()
+    _budget_stream = _stream()
+    _lib.check(_lib.load().mmemo_stream_set_sm_budget(
+        _budget_stream, max(2, (total - n_sms_reserved) // 2 * 2)), "sm_budget")
     _budget_countdown = n_launches
 
 
@@ -70,19 +83,18 @@ def release_sms() -> None:
     global _budget_countdown
     if _budget_countdown:
         _budget_countdown = 0
-        _lib.check(_lib.load().mmemo_set_sm_budget(0), "sm_budget")
+        _lib.check(_lib.load().mmemo_stream_set_sm_budget(_budget_stream, 0), "sm_budget")
 
 
 def _call(name: str, *args) -> None:
     global launch_count, _budget_countdown
-    if not _workspace:
-        _ensure_workspace()
+    _ensure_stream(_stream())
     launch_count += 1
     _lib.check(getattr(_lib.load(), name)(*args), name)
     if _budget_countdown and name.startswith("mmemo_linear"):
         _budget_countdown -= 1
         if _budget_countdown == 0:
-            _lib.check(_lib.load().mmemo_set_sm_budget(0), "sm_budget")
+            _lib.check(_lib.load().mmemo_stream_set_sm_budget(_budget_stream, 0), "sm_budget")
 
 
 def _try_call(name: str, *args) -> bool:
@@ -90,8 +102,7 @@ def _try_call(name: str, *args) -> bool:
     MMEMO_ERR_SHAPE (a problem of the group is outside the grouped kernel's limits; the caller then
     issues the problems one by one), raises on any other error."""
     global launch_count
-    if not _workspace:
-        _ensure_workspace()
+    _ensure_stream(_stream())
     rc = getattr(_lib.load(), name)(*args)
     if rc == -2:
         return False
@@ -240,6 +251,36 @@ def _claim(*ws: Tensor) -> bool:
 
 def clear_grad_dest() -> None:
     _grad_dest.clear()
+    _zbuf_dest.clear()
+
+
+# The fused full block accumulates ALL its parameter gradients (five weight gradients + the small
+# "+=" outputs) into one zero-filled buffer ("zbuf", layout: full_block_grad_layout).  Under data
+# parallelism the reducer gives every block a contiguous bucket region with that layout and
+# registers it here (keyed by the block's Wq): the block's zbuf IS then a bucket slice, p.grad of
+# all 15 parameters are views of the bucket, and nothing is copied or filled per block.
+_zbuf_dest: dict = {}
+
+
+def register_zbuf_dest(key: Tensor, flat: Tensor, offset: int, total: int) -> None:
+    _zbuf_dest[key.data_ptr()] = (flat, offset, total)
+
+
+def full_block_grad_layout(params: Sequence[Tensor]):
+    """(key parameter, [(parameter, offset in floats)], total floats) of a full block's zbuf; the
+    offsets are the views _block_full_backward hands to autograd."""
+    wq, wk, wv, wo, n1w, n1b, n2w, n2b, f1w, f1b, f2w, f2b, ga, gb, gc = params
+    d, dff = wq.shape[0], f1w.shape[0]
+    n_small, sizes = _zbuf_layout(d, dff)
+    p1, zo = 1 + 2 * d, 2 * (1 + 2 * d)
+    lay = [(gb, 0), (n2w, 1), (n2b, 1 + d), (ga, p1), (n1w, p1 + 1), (n1b, p1 + 1 + d),
+           (f2b, zo), (f1b, zo + d), (gc, zo + d + dff)]
+    o = n_small
+    for w, n in zip((wq, wk, wv, wo, f1w, f2w), (d * d, d * d, d * d, d * d, dff * d, d * dff)):
+        lay.append((w, o))
+        o += n
+    assert o == n_small + sum(sizes)
+    return wq, lay, o
 
 
 def _dest(w: Tensor) -> Optional[Tensor]:
@@ -754,7 +795,13 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     # ... and, unless they have a data-parallel bucket slot, for the five weight gradients
     in_z = _dest(wq) is None
     n_small, w_sizes = _zbuf_layout(d, dff)
-    zbuf = torch.zeros(n_small + (sum(w_sizes) if in_z else 0), dtype=F32, device=dev)
+    zd = _zbuf_dest.get(wq.data_ptr()) if (grad_dest_enabled and grad_dest_zeroed) else None
+    in_bucket = zd is not None and zd[2] == n_small + sum(w_sizes) and _claim(wq)
+    if in_bucket:
+        zbuf = zd[0][zd[1]:zd[1] + zd[2]]     # a bucket region, zero-filled by the reducer
+        in_z = True
+    else:
+        zbuf = torch.zeros(n_small + (sum(w_sizes) if in_z else 0), dtype=F32, device=dev)
     z_dp2, z_dp1 = zbuf[:1 + 2 * d], zbuf[1 + 2 * d:2 * (1 + 2 * d)]
     zo = 2 * (1 + 2 * d)
     # LN2: h2 = LN(h1 + b*f2)
@@ -818,8 +865,11 @@ def block_full_bwd_op(dh2: Tensor, ds_next: Optional[Tensor], q: Tensor, kv: Ten
     # (dc lives in zbuf; its output slot stays an empty placeholder — like the weight gradients
     # when they live in zbuf or in a bucket slot)
     ph = [torch.empty(0, device=dev) if r is None else r for r in (r_q, r_kv, r_o, r_f1, r_f2)]
+    # (a zbuf that is a bucket region is not returned either: custom ops must not return views of
+    # tensors they do not own; the autograd wrapper looks the region up again)
     return [dq, dkv, ds_prev if ds_prev is not None else torch.empty(0, device=dev),
-            torch.empty(0, device=dev), ph[0], ph[1], ph[2], zbuf, ph[3], ph[4]]
+            torch.empty(0, device=dev), ph[0], ph[1], ph[2],
+            torch.empty(0, device=dev) if in_bucket else zbuf, ph[3], ph[4]]
 
 
 def _block_full_setup(ctx, inputs, output):
@@ -845,6 +895,9 @@ def _block_full_backward(ctx, grads):
                                 same_qkv, need_dsprev)
     # the small "+=" outputs share one zero-initialised buffer: [dp2 | dp1 | db_f2 | db_f1 | dc]
     dff = params[8].shape[0]
+    if zbuf.numel() == 0:                 # the block's zero buffer is a data-parallel bucket region
+        zd = _zbuf_dest[params[0].data_ptr()]
+        zbuf = zd[0][zd[1]:zd[1] + zd[2]]
     dp2, dp1 = zbuf[:1 + 2 * d], zbuf[1 + 2 * d:2 * (1 + 2 * d)]
     zo = 2 * (1 + 2 * d)
     db_f2, db_f1 = zbuf[zo:zo + d], zbuf[zo + d:zo + d + dff]

@@ -31,6 +31,35 @@ def test_header_symbols_are_exported(built):
     exported = set(re.findall(r" T (mmemo_[a-z0-9_]+)", out))
     missing = declared_symbols() - exported
     assert not missing, missing
+    # ... and nothing the header does not declare (no debug hooks, no process-wide setters)
+    assert not (exported - declared_symbols()), exported - declared_symbols()
+    assert not {"mmemo_set_workspace", "mmemo_set_sm_budget", "mmemo_set_pdl"} & exported
+
+
+def test_launch_settings_are_per_stream_and_thread_safe(built):
+    """re-entrant, no global state.  The settings table is keyed by the stream
+    handle (opaque here: no CUDA call is made) and can be driven from many host threads."""
+    import threading
+    errs = []
+
+    def worker(i):
+        h = 0x1000 + 16 * i          # fake, distinct stream handles
+        try:
+            for _ in range(200):
+                assert built.mmemo_stream_set_sm_budget(h, 2 + i) == 0
+                assert built.mmemo_stream_set_pdl(h, i & 1) == 0
+                assert built.mmemo_stream_set_workspace(h, None, 0) == 0
+            assert built.mmemo_stream_reset(h) == 0
+        except Exception as e:       # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    assert built.mmemo_stream_set_sm_budget(0x1000, -1) == -1      # MMEMO_ERR_ARG
+    assert built.mmemo_stream_set_workspace(0x1000, None, -5) == -1
+    assert built.mmemo_stream_reset(0x1000) == 0
 
 
 def test_ctypes_table_matches_header(built):

@@ -129,3 +129,59 @@ def test_grad_reducer_symm_matches_nccl():
     for rank, worst in res.items():
         assert isinstance(worst, float), worst
         assert worst <= 1e-5, (rank, worst)
+
+
+def test_full_block_gradients_live_in_the_bucket_single_gpu():
+    """The reducer's bucket plumbing without any collective (no_comm, a pretended world of two, one
+    GPU): the fused full block's gradient buffer is a bucket region (``mmemo_grad_unit``), so after
+    the first step no parameter gradient is copied, the buckets hold exactly the local gradients /
+    world, and nothing in the step fills or copies per block."""
+    import mmemo_b200
+    from mmemo_b200 import dp as mdp, ops, synth
+
+    dev = torch.device("cuda")
+    mmemo_b200.set_precision("bf16")
+    try:
+        torch.manual_seed(0)
+        model = mmemo_b200.ResidualEncoder(128, 2, 3, 2)
+        sd = synth.randomize_gates({k: v.detach().clone() for k, v in model.state_dict().items()})
+        model.load_state_dict(sd)
+        model = model.to(dev).train()
+        b = synth.encoder_batch(seed=5, B=4, L=128, d=128)
+        x, m = b["x"].to(dev), b["mask"].to(dev)
+
+        def loss_fn():
+            return ops.sq_mean_op(model(x, m))
+
+        model.zero_grad(set_to_none=True)
+        loss_fn().backward()
+        ref = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+
+        red = mdp.GradReducer(model, world_size=2, transport="nccl", bucket_bytes=1 << 19)
+        red.no_comm = True
+        for step in range(3):
+            model.zero_grad(set_to_none=True)
+            red.backward(loss_fn())
+            if step == 0:
+                continue
+            assert len(red.buckets) >= 2 and sum(len(bk.units) for bk in red.buckets) == 3
+            for bk in red.buckets:
+                lo = bk.flat.data_ptr()
+                hi = lo + 4 * bk.flat.numel()
+                for p in bk.params:
+                    assert lo <= p.grad.data_ptr() < hi           # a view of the bucket: zero-copy
+            for n, p in model.named_parameters():
+                if n in ref:
+                    err = (2 * p.grad - ref[n]).abs().max() / ref[n].abs().max().clamp_min(1e-12)
+                    assert err < 2e-2, (n, float(err))            # bf16 run-to-run (atomics order)
+        n0 = ops.launch_count
+        model.zero_grad(set_to_none=True)
+        red.backward(loss_fn())
+        model.zero_grad(set_to_none=True)
+        plain = ops.launch_count
+        loss_fn().backward()
+        assert ops.launch_count - plain == plain - n0            # same libmmemo launches as plain
+        red.remove()
+        ops.clear_grad_dest()
+    finally:
+        mmemo_b200.set_precision("fp32")

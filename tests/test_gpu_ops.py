@@ -91,6 +91,37 @@ def test_linear_bf16(M, N, K):
     assert rel_err(wc.grad, dy.float().t() @ x.float()) < TOLBF
 
 
+def test_split_k_workspace_is_per_stream():
+    """The split-K scratch of the tcgen05 GEMM is an attribute of the stream (mmemo_stream_set_*):
+    the same bf16-output split-K GEMM issued back to back on two concurrent streams must not mix
+    partial tiles (it did when the workspace was one process-wide buffer)."""
+    M, N, K = 512, 512, 4096        # 4 pair tiles, K long: splits into 16 slices through the scratch
+    gen = g(11)
+    xs = [rnd(gen, M, K).bfloat16().to(DEV) for _ in range(2)]
+    ws = [rnd(gen, N, K, scale=1 / math.sqrt(K)).to(DEV) for _ in range(2)]
+    refs = [x.float() @ w.bfloat16().float().t() for x, w in zip(xs, ws)]
+    ops.clear_shadow_cache()
+    with torch.no_grad():
+        for x, w in zip(xs, ws):
+            ops.linear(x, w, bf16=True)                         # shadows + default-stream warm-up
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[], []]
+    with torch.no_grad():
+        for it in range(20):
+            for i, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    outs[i].append(ops.linear(xs[i], ws[i], bf16=True))
+    torch.cuda.synchronize()
+    keys = {k[1] for k in ops._stream_ws}
+    assert all(st.cuda_stream in keys for st in streams)        # each stream got its own scratch
+    bufs = {ops._stream_ws[k].data_ptr() for k in ops._stream_ws}
+    assert len(bufs) == len(ops._stream_ws)
+    for i in range(2):
+        for y in outs[i]:
+            assert rel_err(y.float(), refs[i]) < TOLBF
+
+
 # ------------------------------------------------------------------------------------------------
 ATTN_SHAPES = [  # B, H, Lq, Lk, hd
     (3, 6, 50, 50, 16), (2, 6, 20, 200, 16), (2, 8, 40, 275, 16), (2, 6, 25, 100, 32),

@@ -101,28 +101,33 @@ def test_loss_curve_fp32_per_step_lr1e4(ref_curves):
 # At the reference learning rate (1e-3) the 200-step trajectory is chaotic: the float32 oracle
 # differs from ITSELF by 0.19 % (smoothed, max over the curve) when only the number of CPU threads
 # (= summation order) changes, and by 0.12 % from the float64 oracle.  Our kernels reorder sums too
-# (atomics, split-K), and measured over repeated runs on B200 the smoothed deviation is 0.11-0.42 %
-# (tools/loss_curve_margins.py) with rare excursions beyond 1 % in round 1.  Round 2 measured the
-# noise floor directly (profiles/r02_loss_curve_margins.txt): two runs of OUR OWN path differ from
-# each other by 0.09-0.21 % (fp32) / 0.19-0.33 % (bf16) on this metric, the same size as their
-# distance to the oracle (0.11-0.28 % / 0.12-0.33 %) — the deviation is summation-order noise
-# amplified by the trajectory, not a systematic error.  The strict 1 % bar is therefore
-# asserted on the per-step curve at lr 1e-4 (measured 0.01-0.05 %), and the lr 1e-3 comparison —
-# SURVEY §8(d)'s "20-step-smoothed at the reference lr" — gets 2 %.
-SMOOTHED_LR1E3_TOL = 0.02
+# (atomics in the LayerNorm backward, split-K reduce-add), so two runs of OUR OWN path differ from
+# each other by 0.09-0.21 % (fp32) / 0.19-0.33 % (bf16) on this metric - the same size as their
+# distance to the oracle (0.11-0.28 % / 0.12-0.33 %; profiles/r02_loss_curve_margins.txt, eight
+# runs): summation-order noise amplified by the trajectory, not a systematic error.  The bound is
+# north_star's 1 % (round 1 had loosened it to 2 %).  Because a chaotic trajectory can make a
+# rare excursion, a run above 1 % is repeated once: one of the two must be within 1 % and both
+# within 2 % (a systematic error fails every run).
+SMOOTHED_LR1E3_TOL = 0.01
+SMOOTHED_LR1E3_HARD = 0.02
+
+
+def smoothed_lr1e3_check(precision, ref):
+    rels = []
+    for _ in range(2):
+        ours = our_curve(1e-3, precision)
+        rels.append(((smooth(ours) - smooth(ref)).abs() / smooth(ref)).max().item())
+        if rels[-1] < SMOOTHED_LR1E3_TOL:
+            break
+    assert min(rels) < SMOOTHED_LR1E3_TOL and max(rels) < SMOOTHED_LR1E3_HARD, rels
 
 
 def test_loss_curve_fp32_smoothed_lr1e3(ref_curves):
-    ours, ref = our_curve(1e-3, "fp32"), ref_curves[1e-3]
-    rel = ((smooth(ours) - smooth(ref)).abs() / smooth(ref)).max().item()
-    assert rel < SMOOTHED_LR1E3_TOL, rel
+    smoothed_lr1e3_check("fp32", ref_curves[1e-3])
 
 
 def test_loss_curve_bf16_lr1e4_and_smoothed_lr1e3(ref_curves):
     ours = our_curve(1e-4, "bf16")
     rel = ((ours - ref_curves[1e-4]).abs() / ref_curves[1e-4].abs()).max().item()
     assert rel < 0.01, rel
-    ours = our_curve(1e-3, "bf16")
-    ref = ref_curves[1e-3]
-    rel = ((smooth(ours) - smooth(ref)).abs() / smooth(ref)).max().item()
-    assert rel < SMOOTHED_LR1E3_TOL, rel
+    smoothed_lr1e3_check("bf16", ref_curves[1e-3])
