@@ -1024,7 +1024,7 @@ def main():
                    "exposed_comm_us": (ms_per_step - ms_nocomm) * 1e3,
                    "grad_check": {"probe_tensors": len(probes), "max_rel_err": err,
                                   "what": "max |reduced - allreduce(local)/N| / max |ref| over the "
-                                          "first parameter of every bucket"}}
+                                          "first weight matrix of every bucket"}}
 
     # ---- CPU baseline + eager-PyTorch-on-this-GPU baseline (rank 0, N=1 only) -----------------------
     cpu, gpu_eager = None, None

@@ -155,6 +155,10 @@ class LiteAttentionBlock(nn.Module):
         n = self._norm
         return [self.proj.weight, self.minus.weight, n.weight, n.bias, self.c]
 
+    def mmemo_grad_unit(self):
+        """dp.GradReducer protocol (see FullAttentionBlock.mmemo_grad_unit)."""
+        return ops.lite_block_grad_layout(self._params())
+
     def multi_head_attention(self, q, k, v, mask, scores=None):
         bf = is_bf16()
         q, k, v = as_act(q), as_act(k), as_act(v)

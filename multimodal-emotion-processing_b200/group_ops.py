@@ -295,8 +295,7 @@ def trunk_full_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[T
 def _full_zlayout(d: int, dff: int):
     """Per-problem zero buffer: [dp2 (1+2d) | dp1 (1+2d) | db_f2 (d) | db_f1 (dff) | dc (1) | pad]
     then dWq (d,d) dWkv (2d,d) dWo (d,d) dWf1 (dff,d) dWf2 (d,dff)."""
-    n_small = (2 * (1 + 2 * d) + d + dff + 1 + 63) // 64 * 64
-    sizes = [d * d, 2 * d * d, d * d, dff * d, d * dff]
+    n_small, sizes = ops._zbuf_layout(d, dff)       # (the per-block op and the reducer share it)
     return n_small, sizes, n_small + sum(sizes)
 
 
@@ -338,8 +337,15 @@ def trunk_full_bwd_op(dh2s: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: Se
     dsn = [_opt(t) for t in ds_nexts]
     dh2s = [t.contiguous() for t in dh2s]
     _, _, zlen = _full_zlayout(d, dff)
-    zall = torch.zeros(G * zlen, dtype=F32, device=dev)      # ONE fill for every "+=" output
-    Z = [_full_zviews(zall[g * zlen:(g + 1) * zlen], d, dff) for g in range(G)]
+    # data parallel: every block's buffer is a region of an all-reduce bucket, zero-filled by the
+    # reducer (dp.GradReducer, ops.register_zbuf_dest) - no fill here, no gradient copies later
+    zbs = ops.claim_zbufs([p[0] for p in P], zlen)
+    if zbs is None:
+        zall = torch.zeros(G * zlen, dtype=F32, device=dev)      # ONE fill for every "+=" output
+        zbs = [zall[g * zlen:(g + 1) * zlen] for g in range(G)]
+    else:
+        zall = _e(dev)
+    Z = [_full_zviews(zbs[g], d, dff) for g in range(G)]
     # LN2: h2 = LN(h1 + b*f2); colsum(df2) = the FFN-2 bias gradient comes out of the same pass
     if drop_p > 0:   # the FFN-2 bias sees the gradient BEFORE the dropout: mask first, then column sums
         dh1s, df2s = ln_bwd_group(bf16, dh2s, h1s, f2s, [p[13] for p in P], [p[6] for p in P], st2s,
@@ -445,7 +451,8 @@ def _trunk_full_backward(ctx, grads):
         dqs.append(dq if dq.numel() else None)
         dkvs.append(dkv if dkv.numel() else None)
         dsps.append(dsp if dsp.numel() else None)
-        dp2, dp1, db_f2, db_f1, dc, ws = _full_zviews(zall[g * zlen:(g + 1) * zlen], d, dff)
+        zb = zall[g * zlen:(g + 1) * zlen] if zall.numel() else ops.zbuf_region(params[N_FULL * g])
+        dp2, dp1, db_f2, db_f1, dc, ws = _full_zviews(zb, d, dff)
         pgrads += [ws[0], ws[1][:d], ws[1][d:], ws[2], dp1[1:1 + d], dp1[1 + d:], dp2[1:1 + d],
                    dp2[1 + d:], ws[3], db_f1, ws[4], db_f2, dp1[0:1], dp2[0:1],
                    dc if ctx.has_prev else None]
@@ -509,8 +516,7 @@ def trunk_lite_op(qs: Sequence[Tensor], kvs: Sequence[Tensor], masks: Sequence[T
 
 def _lite_zlayout(d: int):
     """[dpn (1+2d) | dc (1) | pad] then dWo (d,d), dWm (d,2d)."""
-    n_small = (1 + 2 * d + 1 + 63) // 64 * 64
-    return n_small, n_small + d * d + 2 * d * d
+    return ops.lite_zlayout(d)
 
 
 def _lite_zviews(z: Tensor, d: int):
@@ -546,8 +552,13 @@ def trunk_lite_bwd_op(douts: Sequence[Tensor], ds_nexts: Sequence[Tensor], qs: S
         ops._dropout_group(douts, masked, drop_p, ops.site_seeds(drop_seed, G, 1))
         douts = masked
     _, zlen = _lite_zlayout(d)
-    zall = torch.zeros(G * zlen, dtype=F32, device=dev)
-    Z = [_lite_zviews(zall[g * zlen:(g + 1) * zlen], d) for g in range(G)]
+    zbs = ops.claim_zbufs([p[0] for p in P], zlen)       # (see trunk_full_bwd_op)
+    if zbs is None:
+        zall = torch.zeros(G * zlen, dtype=F32, device=dev)
+        zbs = [zall[g * zlen:(g + 1) * zlen] for g in range(G)]
+    else:
+        zall = _e(dev)
+    Z = [_lite_zviews(zbs[g], d) for g in range(G)]
     _, dys = ln_bwd_group(bf16, douts, [None] * G, ys, [None] * G, [p[2] for p in P], sts, False,
                           [z[0] for z in Z])
     wms = [_weight(bf16, P[g][1]) for g in range(G)]
@@ -637,7 +648,8 @@ def _trunk_lite_backward(ctx, grads):
         dqs.append(dq if dq.numel() else None)
         dkvs.append(dkv if dkv.numel() else None)
         dsps.append(dsp if dsp.numel() else None)
-        dpn, dc, dwo, dwm = _lite_zviews(zall[g * zlen:(g + 1) * zlen], d)
+        zb = zall[g * zlen:(g + 1) * zlen] if zall.numel() else ops.zbuf_region(params[N_LITE * g])
+        dpn, dc, dwo, dwm = _lite_zviews(zb, d)
         pgrads += [dwo, dwm, dpn[1:1 + d], dpn[1 + d:], dc if ctx.has_prev else None]
     n_prev = G if ctx.has_prev else 0
     return (dqs, dkvs, [None] * G, dsps if need_dsprev else [None] * n_prev, pgrads, None, None,

@@ -283,6 +283,39 @@ def full_block_grad_layout(params: Sequence[Tensor]):
     return wq, lay, o
 
 
+def lite_zlayout(d: int):
+    """Zero buffer of a lite block: [dpn (1+2d) | dc (1) | pad] then dWo (d,d), dWm (d,2d)."""
+    n_small = (1 + 2 * d + 1 + 63) // 64 * 64
+    return n_small, n_small + d * d + 2 * d * d
+
+
+def lite_block_grad_layout(params: Sequence[Tensor]):
+    """Like full_block_grad_layout for the lite block (params: Wo, Wm, norm weight, norm bias, c)."""
+    wo, wm, nw, nb, c = params
+    d = wo.shape[0]
+    n_small, total = lite_zlayout(d)
+    return wo, [(nw, 1), (nb, 1 + d), (c, 1 + 2 * d), (wo, n_small), (wm, n_small + d * d)], total
+
+
+def claim_zbufs(keys: Sequence[Tensor], total: int) -> Optional[List[Tensor]]:
+    """Bucket regions for the zero buffers of a GROUP of blocks (one grouped trunk layer): all of
+    them or none (None: the caller allocates and fills its own buffer)."""
+    if not (grad_dest_enabled and grad_dest_zeroed):
+        return None
+    zs = [_zbuf_dest.get(k.data_ptr()) for k in keys]
+    if any(z is None or z[2] != total for z in zs):
+        return None
+    if any(k.data_ptr() in _dest_claimed for k in keys):
+        return None
+    _dest_claimed.update(k.data_ptr() for k in keys)
+    return [z[0][z[1]:z[1] + z[2]] for z in zs]
+
+
+def zbuf_region(key: Tensor) -> Tensor:
+    z = _zbuf_dest[key.data_ptr()]
+    return z[0][z[1]:z[1] + z[2]]
+
+
 def _dest(w: Tensor) -> Optional[Tensor]:
     e = _grad_dest.get(w.data_ptr()) if grad_dest_enabled else None
     if e is None or e[2] != w.numel():
@@ -763,7 +796,7 @@ def block_full_op(q: Tensor, kv: Tensor, mask: Optional[Tensor], s_prev: Optiona
 
 def _zbuf_layout(d: int, dff: int):
     """(floats of the small "+=" outputs rounded to 256 B, [sizes of dWq, dWkv, dWo, dWf1, dWf2])."""
-    n_small = (2 * (1 + 2 * d) + d + dff + 32 + 63) // 64 * 64
+    n_small = (2 * (1 + 2 * d) + d + dff + 1 + 63) // 64 * 64
     return n_small, [d * d, 2 * d * d, d * d, dff * d, d * dff]
 
 

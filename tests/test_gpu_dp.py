@@ -84,8 +84,12 @@ def _reducer_worker(rank, world, port, q):
             grads[transport] = {k: p.grad.detach().cpu().clone()
                                 for k, p in model.named_parameters() if p.grad is not None}
             red.remove()
-        worst = max(float((grads["nccl"][k] - grads["symm"][k]).abs().max()
-                          / grads["nccl"][k].abs().max().clamp_min(1e-20)) for k in grads["nccl"])
+        def rel(k):
+            return float((grads["nccl"][k] - grads["symm"][k]).abs().max()
+                         / grads["nccl"][k].abs().max().clamp_min(1e-20))
+        # scalar gates are one atomics-ordered sum with cancellation: two backward passes of the
+        # SAME transport differ by ~1e-5 there, so they are compared at a tenth of the weight
+        worst = max(rel(k) / (10.0 if grads["nccl"][k].numel() == 1 else 1.0) for k in grads["nccl"])
         q.put((rank, worst))
         dist.barrier()
         torch.cuda.synchronize()
@@ -181,6 +185,56 @@ def test_full_block_gradients_live_in_the_bucket_single_gpu():
         plain = ops.launch_count
         loss_fn().backward()
         assert ops.launch_count - plain == plain - n0            # same libmmemo launches as plain
+        red.remove()
+        ops.clear_grad_dest()
+    finally:
+        mmemo_b200.set_precision("fp32")
+
+
+def test_grouped_trunk_gradients_live_in_the_bucket_single_gpu():
+    """Same for the grouped fusion trunk (lite blocks of cmu-mosei / Ren-MME): every block's zero
+    buffer of a trunk layer is a bucket region; gradients equal the plain backward's / world."""
+    import mmemo_b200
+    from mmemo_b200 import dp as mdp, ops, synth
+
+    dev = torch.device("cuda")
+    mmemo_b200.set_precision("bf16")
+    try:
+        torch.manual_seed(1)
+        ct = mmemo_b200.cmu_mosei.Concat_Trans(32, 12, 20, 28, 2, 2, 1, l_dim=24, v_dim=16, a_dim=8)
+        sd = synth.randomize_gates({k: v.detach().clone() for k, v in ct.state_dict().items()})
+        ct.load_state_dict(sd)
+        ct = ct.to(dev).train()
+        mb = synth.mosei_batch(seed=5, B=4, L=(12, 20, 28), D=(24, 16, 8))
+        args = [mb[k].to(dev) for k in ("l", "v", "a", "l_mask", "v_mask", "a_mask")]
+        label = mb["label"].to(dev)
+
+        def loss_fn():
+            return ops.circle_loss_op(ct(*args), label).mean()
+
+        ct.zero_grad(set_to_none=True)
+        loss_fn().backward()
+        ref = {n: p.grad.detach().clone() for n, p in ct.named_parameters() if p.grad is not None}
+        red = mdp.GradReducer(ct, world_size=2, transport="nccl", bucket_bytes=1 << 16)
+        red.no_comm = True
+        for step in range(3):
+            ct.zero_grad(set_to_none=True)
+            red.backward(loss_fn())
+        n_units = sum(len(bk.units) for bk in red.buckets)
+        n_blocks = sum(1 for m in ct.modules() if hasattr(m, "mmemo_grad_unit"))
+        assert n_units == n_blocks and n_units >= 18
+        in_bucket = 0
+        for bk in red.buckets:
+            lo = bk.flat.data_ptr()
+            hi = lo + 4 * bk.flat.numel()
+            for p in bk.params:
+                assert lo <= p.grad.data_ptr() < hi
+                in_bucket += 1
+        assert in_bucket == len(ref)
+        for n, p in ct.named_parameters():
+            if n in ref:
+                err = (2 * p.grad - ref[n]).abs().max() / ref[n].abs().max().clamp_min(1e-12)
+                assert err < 3e-2, (n, float(err))
         red.remove()
         ops.clear_grad_dest()
     finally:
