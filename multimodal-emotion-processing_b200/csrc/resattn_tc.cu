@@ -329,7 +329,9 @@ int resattn_fwd_tc(const void* q, int64_t ldq, const void* k, int64_t ldk, const
 //   [S_acc = Q K^T                       only when S was not stored (last layer of a chain)]
 //   dP  = dO V^T                         (128 x 128 x 64)
 //   regs: p = exp(s - max)/sum, D = rowsum(p*dP), dS = p*(dP - D) + dS_next,
-//         dc += sum(dS*S_prev), dS_prev = c*dS        (thread = query row, two passes over TMEM)
+//         dc += sum(dS*S_prev), dS_prev = c*dS        (two passes over TMEM; EIGHT warps: thread =
+//         (query row, 64-key half) - two warps per TMEM lane quarter, the halves of D meet in
+//         shared memory; with four warps this register phase was ~40 % of a CTA's time)
 //   dV  = P^T dO, dK = dS^T Q            (A operands MN-major straight from the P / dS tiles)
 //   dQ  = dS K                           (B operand MN-major = K as loaded)
 // The S-sized tiles are updated in place in shared memory: S -> P, dS_next -> dS, S_prev -> dS_prev.
@@ -343,7 +345,9 @@ constexpr uint32_t B_OFF_B = B_OFF_A + TILE_S;         // dS_next -> dS
 constexpr uint32_t B_OFF_C = B_OFF_B + TILE_S;         // S_prev -> dS_prev
 constexpr uint32_t B_OFF_MASK = B_OFF_C + TILE_S;
 constexpr uint32_t B_OFF_BAR = B_OFF_MASK + 512;
-constexpr uint32_t SMEM_BWD = B_OFF_BAR + 128 + 1024;
+constexpr uint32_t B_OFF_DSUM = B_OFF_BAR + 128;        // D halves: [2][128] floats
+constexpr uint32_t SMEM_BWD = B_OFF_DSUM + 1024 + 1024;
+constexpr int NTHREADS_BWD = 64 + 256;                 // TMA warp, MMA warp, eight compute warps
 
 struct BwdArgs {
   const float* mask;
@@ -369,7 +373,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint32_t* v) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS_BWD, 1)
 resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                       const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmSprev,
@@ -398,7 +402,7 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc::mbar_init(bar_sp, 1);
     tc::mbar_init(bar_dsn, 1);
     tc::mbar_init(bar_mm1, 1);
-    tc::mbar_init(bar_p2, 128);
+    tc::mbar_init(bar_p2, 256);
     tc::mbar_init(bar_mm2, 1);
     tc::fence_barrier_init();
   }
@@ -408,7 +412,7 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     tc::tmem_relinquish();
   }
   pdl_wait();             // before the first global access (mask row, TMA loads)
-  if (threadIdx.x >= 64) {
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + L) {
     const int j = threadIdx.x - 64;
     // additive mask term 1e8*(1-m), computed once per key (same fp32 ops as the reference)
     mask_s[j] = a.mask ? __fmul_rn(1.0e8f, __fsub_rn(1.0f, a.mask[(int64_t)b * a.mask_bs + j])) : 0.0f;
@@ -503,8 +507,10 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     }
   } else {
     const int quarter = warp & 3;
-    const int row = quarter * 32 + lane;
+    const int khalf = (warp - 2) >> 2;              // which 64 keys (pass A / B), which 32 head
+    const int row = quarter * 32 + lane;            // columns (epilogue) this thread handles
     const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    float* dsum = reinterpret_cast<float*>(gbase + B_OFF_DSUM);
     const float cval = (a.has_prev && a.c) ? a.c[0] : 0.f;
     const float* st2 = a.stat + 2 * ((int64_t)srow0 + row);
     const float mx = st2[0], inv = 1.0f / st2[1];
@@ -517,7 +523,7 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     // ---- pass A: P (bf16) into tile A, D = sum_j p*dP ------------------------------------------
     float D = 0.f;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 2 * khalf; ch < 2 * khalf + 2; ++ch) {
       uint32_t dp[32], sa[32];
       tc::tmem_ld32(tm_dP + lane_off + ch * 32, dp);
       if (!a.has_s) tc::tmem_ld32(tm_S + lane_off + ch * 32, sa);
@@ -557,10 +563,14 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         sts128(base + B_OFF_A + off, out);
       }
     }
+    // the two key halves of a row exchange their partial D
+    dsum[khalf * 128 + row] = D;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    D += dsum[(khalf ^ 1) * 128 + row];
     // ---- pass B: dS into tile B, dc, dS_prev into tile C -----------------------------------------
     float dc_part = 0.f;
 #pragma unroll 1
-    for (int ch = 0; ch < 4; ++ch) {
+    for (int ch = 2 * khalf; ch < 2 * khalf + 2; ++ch) {
       uint32_t dp[32];
       tc::tmem_ld32(tm_dP + lane_off + ch * 32, dp);
       tc::tmem_ld_wait();
@@ -597,7 +607,7 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       dc_part = warp_sum(dc_part);
       if (lane == 0) atomicAdd(a.dc, dc_part);
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (a.has_prev && a.write_dsp && threadIdx.x == 64) {
       tc::tma_store_2d(&tmDSp, base + B_OFF_C, 0, srow0);
       tc::tma_store_2d(&tmDSp, base + B_OFF_C + TILE_S / 2, 64, srow0);
@@ -612,8 +622,8 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       const uint32_t src = t == 0 ? tm_dV : (t == 1 ? tm_dK : tm_dQ);
       const uint32_t dst = base + (t == 0 ? B_OFF_V : (t == 1 ? B_OFF_K : B_OFF_Q));
       const float sc = t == 0 ? 1.0f : inv_sqrt;
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
+      {
+        const int ch = khalf;                       // 32 of the 64 head columns per thread
         uint32_t r[32];
         tc::tmem_ld32(src + lane_off + ch * 32, r);
         tc::tmem_ld_wait();
@@ -629,7 +639,7 @@ resattn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       }
     }
     tc::fence_proxy_async();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x == 64) {
       tc::tma_store_2d(&tmDV, base + B_OFF_V, h * HD, row0);
       tc::tma_store_2d(&tmDK, base + B_OFF_K, h * HD, row0);
@@ -685,7 +695,7 @@ int resattn_bwd_tc(const void* d_o, int64_t lddo, const void* q, int64_t ldq, co
   a.idesc_tt64 = tc::idesc_bf16(L, HD, 1, 1);
   a.idesc_nt64 = tc::idesc_bf16(L, HD, 0, 1);
   dim3 grid((unsigned)H, (unsigned)B);
-  MM_CUDA_OK(mm_launch(resattn_bwd_tc_kernel, grid, dim3(NTHREADS), SMEM_BWD, st, tmQ, tmK, tmV,
+  MM_CUDA_OK(mm_launch(resattn_bwd_tc_kernel, grid, dim3(NTHREADS_BWD), SMEM_BWD, st, tmQ, tmK, tmV,
                        tmDO, tmS, tmSp, tmDSn, tmDSp, tmDQ, tmDK, tmDV, a));
   return MMEMO_OK;
 }
