@@ -181,17 +181,35 @@ struct LnProb {
   float *mean, *rstd, *dgate, *dgamma, *dbeta, *dxsum;
   long long M;
 };
-struct LnTable { LnProb p[LN_MAXP]; };
+// cta_start: the CTAs [cta_start[i], cta_start[i+1]) of the one-dimensional grid stride over the
+// rows of problem i.  The host hands out CTAs in proportion to the problems' row counts (Ren-MME's
+// streams have 40 / 76 / 275 positions: with the same number of CTAs per problem the long
+// streams ran 2-7x longer than the short ones) and keeps the backward grid within one wave of
+// full-register-file CTAs (n x ceil(148 / n) CTAs used to spill a few CTAs into a second wave,
+// doubling the launch: 153 CTAs for the nine chains of a trunk layer).
+struct LnTable {
+  LnProb p[LN_MAXP];
+  int n;
+  int cta_start[LN_MAXP + 1];
+};
+__device__ __forceinline__ int ln_locate(const LnTable& tb, unsigned& bid, unsigned& nblk) {
+  int g = 0;
+  while (g + 1 < tb.n && (int)blockIdx.x >= tb.cta_start[g + 1]) ++g;
+  bid = blockIdx.x - (unsigned)tb.cta_start[g];
+  nblk = (unsigned)(tb.cta_start[g + 1] - tb.cta_start[g]);
+  return g;
+}
 
 template <typename T, int NCH, int LPR>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_vec_grouped(const __grid_constant__ LnTable tb, int d, float eps, int relu) {
-  const LnProb& a = tb.p[blockIdx.y];
+  unsigned bid, nblk;
+  const LnProb& a = tb.p[ln_locate(tb, bid, nblk)];
   pdl_wait();
   pdl_trigger();
   ln_fwd_vec_body<T, NCH, LPR>(static_cast<const T*>(a.res), d, static_cast<const T*>(a.x), d,
                                a.gate, a.gamma, a.beta, static_cast<T*>(a.y), d, a.mean, a.rstd,
-                               a.M, d, eps, relu, blockIdx.x, gridDim.x);
+                               a.M, d, eps, relu, bid, nblk);
 }
 
 template <typename T, int NCH>
@@ -441,14 +459,14 @@ ln_bwd_fused_vec(const T* __restrict__ dy, int64_t lddy, const T* __restrict__ r
 template <typename T, int NCH, bool DXSUM, int LPR>
 __global__ void __launch_bounds__(LNB_WARPS * 32, 1)
 ln_bwd_fused_vec_grouped(const __grid_constant__ LnTable tb, int d) {
-  const LnProb& a = tb.p[blockIdx.y];
+  unsigned bid, nblk;
+  const LnProb& a = tb.p[ln_locate(tb, bid, nblk)];
   pdl_wait();
   pdl_trigger();
   ln_bwd_fused_body<T, NCH, DXSUM, LPR>(static_cast<const T*>(a.dy), d, static_cast<const T*>(a.res), d,
                                    static_cast<const T*>(a.x), d, a.gate, a.gamma, a.mean, a.rstd,
                                    static_cast<T*>(a.dres), d, static_cast<T*>(a.dx), d, a.dgate,
-                                   a.dgamma, a.dbeta, DXSUM ? a.dxsum : nullptr, a.M, d,
-                                   blockIdx.x, gridDim.x);
+                                   a.dgamma, a.dbeta, DXSUM ? a.dxsum : nullptr, a.M, d, bid, nblk);
 }
 
 // dgamma / dbeta: CTA = (64 columns, strip of rows); lane owns 2 adjacent columns
@@ -735,6 +753,25 @@ int bwd(const void* dy, int64_t lddy, const void* res, int64_t ldres, const void
   return MMEMO_OK;
 }
 
+// CTAs per problem: one each plus a share of the rest proportional to the rows, never more than
+// a problem has row groups; returns the grid size (<= total whenever total >= n).
+unsigned ln_share_ctas(LnTable& tb, int n, const int64_t* M, int64_t rows_per_cta, int64_t total) {
+  int64_t msum = 0;
+  for (int i = 0; i < n; ++i) msum += M[i];
+  const int64_t spare = total > n ? total - n : 0;
+  int at = 0;
+  tb.n = n;
+  for (int i = 0; i < n; ++i) {
+    int64_t c = 1 + (msum > 0 ? spare * M[i] / msum : 0);
+    const int64_t useful = cdiv(M[i], rows_per_cta) > 1 ? cdiv(M[i], rows_per_cta) : 1;
+    if (c > useful) c = useful;
+    tb.cta_start[i] = at;
+    at += (int)c;
+  }
+  tb.cta_start[n] = at;
+  return (unsigned)at;
+}
+
 template <typename T>
 int fwd_grouped(int n, const void* const* res, const void* const* x, const float* const* gate,
                 const float* const* gamma, const float* const* beta, void* const* y,
@@ -761,10 +798,7 @@ int fwd_grouped(int n, const void* const* res, const void* const* x, const float
   // ~6 CTAs (48 warps) per SM over the whole group; narrow rows share a warp (LPR lanes per row)
   const int nchunk = (int)(d / V);
   const int rpw = nchunk <= 8 ? 4 : (nchunk <= 16 ? 2 : 1);
-  int64_t gx = cdiv(mmax, LN_WARPS * rpw);
-  const int64_t cap = cdiv(148 * 6, n);
-  if (gx > cap) gx = cap;
-  const dim3 grid((unsigned)gx, (unsigned)n);
+  const dim3 grid(ln_share_ctas(tb, n, M, LN_WARPS * rpw, 148 * 6));
   const int nch = (int)cdiv(nchunk, 32);
 #define MM_G(NCH_, LPR_) MM_CUDA_OK(mm_launch(ln_fwd_vec_grouped<T, NCH_, LPR_>, grid, dim3(LN_WARPS * 32), 0, st, tb, (int)d, eps, relu))
   if (rpw == 4) MM_G(1, 8); else if (rpw == 2) MM_G(1, 16);
@@ -806,12 +840,9 @@ int bwd_grouped(int n, const void* const* dy, const void* const* res, const void
   // share a warp (LPR lanes per row)
   const int nchunk = (int)(d / V);
   const int rpw = nchunk <= 8 ? 4 : (nchunk <= 16 ? 2 : 1);
-  int64_t gx = cdiv(mmax, LNB_WARPS * rpw);
   const int sb = mm_stream_cfg(st).sm_budget;
   const int64_t sms = (sb > 0 && sb < 148) ? sb : 148;      // (see ln_bwd_fused_vec's launcher)
-  const int64_t cap = cdiv(sms, n) > 1 ? cdiv(sms, n) : 1;
-  if (gx > cap) gx = cap;
-  const dim3 grid((unsigned)gx, (unsigned)n);
+  const dim3 grid(ln_share_ctas(tb, n, M, LNB_WARPS * rpw, sms));
   const int nch = (int)cdiv(nchunk, 32);
   const size_t sm_bytes = (1 + LNB_WARPS * rpw) * (size_t)d * sizeof(float);
 #define MM_G(NCH_, LPR_)                                                                          \

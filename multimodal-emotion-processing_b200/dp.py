@@ -155,7 +155,7 @@ class GradReducer:
         # gradient became ready, with the members that actually receive gradients
         got = set(self._order)
         unit_of: Dict[torch.nn.Parameter, _Unit] = {}
-        if self.zero_copy and self._order and self._order[0].is_cuda:
+        if self.zero_copy and self._order:
             for m in self.model.modules():
                 fn = getattr(m, "mmemo_grad_unit", None)
                 if fn is None:

@@ -32,6 +32,14 @@ class Net(torch.nn.Module):
         return self.c(torch.relu(self.b(torch.relu(self.a(x)))))
 
 
+class UnitNet(Net):
+    """``b``'s gradients are declared as one contiguous unit (the protocol of the fused blocks,
+    ``mmemo_grad_unit``): [pad 7 | bias 40 | pad 17 | weight 1600 | pad 8], key = weight."""
+
+    def mmemo_grad_unit(self):
+        return self.b.weight, [(self.b.bias, 7), (self.b.weight, 64), (self.unused, 3)], 1672
+
+
 def _loss(model, x, y):
     return ((model(x) - y) ** 2).mean()
 
@@ -41,7 +49,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)
-    model = Net()
+    model = (UnitNet if os.environ.get("MMEMO_TEST_UNITS") == "1" else Net)()
     g = torch.Generator().manual_seed(1)
     x, y = torch.randn(16, 12, generator=g), torch.randn(16, 5, generator=g)
     red = dp.GradReducer(model, world, bucket_bytes=4096)
@@ -52,11 +60,22 @@ def _worker(rank, world, port, q):
         red.backward(_loss(model, shard["x"], shard["y"]))
         layouts.append(red.bucket_layout())
         grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    if isinstance(model, UnitNet):       # the unit sits in ONE bucket with the declared offsets
+        bk = [b for b in red.buckets if b.units]
+        assert len(bk) == 1 and len(bk[0].units) == 1
+        unit, start = bk[0].units[0]
+        assert unit.total == 1672 and start % 32 == 0
+        base = bk[0].flat.data_ptr()
+        assert model.b.bias.grad.data_ptr() == base + 4 * (start + 7)
+        assert model.b.weight.grad.data_ptr() == base + 4 * (start + 64)
+        assert all(p is not model.unused for p in bk[0].params)     # no gradient: left out
     q.put((rank, layouts[-1], {k: v.tolist() for k, v in grads.items()}))
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_matches_full_batch():
+@pytest.mark.parametrize("units", [False, True])
+def test_bucketed_allreduce_matches_full_batch(units, monkeypatch):
+    monkeypatch.setenv("MMEMO_TEST_UNITS", "1" if units else "0")   # inherited by the spawned ranks
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
