@@ -601,16 +601,22 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
   // that a strip is fetched from HBM once; stream-K ranges start at unrelated k offsets and
   // measured 166 vs 108 us on the 32-tile weight-gradient group of the seq-256 encoder (operand
   // traffic 1.07 GB instead of 0.44 GB) and 32.9 vs 31.7 us at seq 128.
-  int64_t kb_sum = 0;
+  int64_t kb_sum = 0, operand_bytes = 0;
   int tiles_max = 0;
   for (int i = 0; i < n; ++i) {
     const int t = (int)(cdiv(gs[i].M, TM) * cdiv(gs[i].N, BN));
     tiles_max = t > tiles_max ? t : tiles_max;
     kb_sum += t * cdiv(gs[i].K, BK);
+    operand_bytes += 2 * gs[i].K * (gs[i].M + gs[i].N);
   }
+  // (... or whose operands are small enough to stay in L2 whatever the order: the modality
+  // projections' weight gradients - three problems of 10 / 50 / 100 k-blocks on five tiles - ran
+  // 33 us on five CTAs.)  A range is at least 8 k-blocks, so tiny launches use fewer units.
   int kb_per_unit = (int)cdiv(kb_sum, units_max);
-  bool streamk = linear && all_reduce_add && kb_min >= 16 && tiles_max <= 2 && n > 1 &&
-                 kb_per_unit >= 8 && kb_sum < (1ll << 30);
+  if (kb_per_unit < 8) kb_per_unit = 8;
+  bool streamk = linear && all_reduce_add && (tiles_max <= 2 || operand_bytes <= (16ll << 20)) &&
+                 tiles_sum <= 4 * units_max && kb_sum >= 16 && kb_sum < (1ll << 30) &&
+                 (n > 1 || tiles_sum * 2 <= units_max);
   {
     const char* env = getenv("MMEMO_GEMM_STREAMK");     // A/B knob: 0 = the split-K item list
     if (env && env[0] == '0') streamk = false;

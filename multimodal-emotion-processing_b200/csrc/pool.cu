@@ -31,10 +31,25 @@ pool_fwd_kernel(SegTable tb, int64_t B, int d, float* __restrict__ out, int32_t*
   for (int g = 0; g < tb.n_groups; ++g) {
     const T* __restrict__ p = static_cast<const T*>(tb.ptr[g * tb.n_slots + slot]) +
                               b * (int64_t)tb.len[g] * d + k;
-    for (int t = 0; t < tb.len[g]; ++t, ++pos) {
+    // eight independent loads in flight per thread (the positions of one feature are d elements
+    // apart: one load at a time left the kernel waiting on memory latency 320 times in a row)
+    const int n = tb.len[g];
+    int t = 0;
+    for (; t + 8 <= n; t += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = to_f(p[(int64_t)(t + j) * d]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sum += v[j];
+        if (v[j] > mx) { mx = v[j]; arg = pos + j; }  // strict '>' keeps the FIRST maximum
+      }
+      pos += 8;
+    }
+    for (; t < n; ++t, ++pos) {
       const float v = to_f(p[(int64_t)t * d]);
       sum += v;
-      if (v > mx) { mx = v; arg = pos; }  // strict '>' keeps the FIRST maximum
+      if (v > mx) { mx = v; arg = pos; }
     }
   }
   out[b * 2 * F + f] = sum / (float)tb.total_len;
