@@ -933,13 +933,30 @@ int bwd_mode(const mmemo_attn_problem& p) {
   return M_GEN;
 }
 
+// Heaviest problems first: CTAs are dispatched in index order, so the long-sequence CTAs (Ren-MME:
+// 275 x 275 scores against 40 x 40) start while the machine is full and the short ones fill the
+// tail, instead of a last wave made of the slowest CTAs only.
+void heavy_first(const mmemo_attn_problem* ps, int n, int* idx) {
+  for (int i = 0; i < n; ++i) idx[i] = i;
+  for (int i = 1; i < n; ++i) {          // stable insertion sort (n <= 40)
+    const int v = idx[i];
+    const int64_t w = ps[v].Lq * ps[v].Lk;
+    int j = i - 1;
+    while (j >= 0 && ps[idx[j]].Lq * ps[idx[j]].Lk < w) { idx[j + 1] = idx[j]; --j; }
+    idx[j + 1] = v;
+  }
+}
+
 // the problems of `ps` that run in `mode`, as one launch of that instantiation
 int fwd_launch(const mmemo_attn_problem* ps, int n, int mode, cudaStream_t st) {
   static thread_local Table T;      // host staging (copied by value into the launch)
   const int hd = (int)ps[0].hd;
   size_t smem = 0;
   int ctas = 0, m = 0;
-  for (int i = 0; i < n; ++i) {
+  int order[MAXP];
+  heavy_first(ps, n, order);
+  for (int oi = 0; oi < n; ++oi) {
+    const int i = order[oi];
     if (fwd_mode(ps[i]) != mode) continue;
     fill(T.p[m], ps[i]);
     T.p[m].cta_start = ctas;
@@ -1096,12 +1113,16 @@ int resattn_mma_bwd(const mmemo_attn_problem* ps, int n, cudaStream_t st) {
   // Ren-MME's three query lengths give three
   const mmemo_attn_problem* sel[MAXP];
   bool done[MAXP] = {};
-  for (int i = 0; i < n; ++i) {
+  int order[MAXP];
+  heavy_first(ps, n, order);             // launches and the problems inside them, heaviest first
+  for (int oi = 0; oi < n; ++oi) {
+    const int i = order[oi];
     if (done[i]) continue;
     const int w = (fixed >= 2 && fixed <= BWD_WARPS) ? fixed : bwd_warps(ps[i].Lq);
     const int mode = bwd_mode(ps[i]);
     int m = 0;
-    for (int j = i; j < n; ++j) {
+    for (int oj = oi; oj < n; ++oj) {
+      const int j = order[oj];
       const int wj = (fixed >= 2 && fixed <= BWD_WARPS) ? fixed : bwd_warps(ps[j].Lq);
       if (!done[j] && wj == w && bwd_mode(ps[j]) == mode) { sel[m++] = &ps[j]; done[j] = true; }
     }
