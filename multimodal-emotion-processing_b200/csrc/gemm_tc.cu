@@ -425,7 +425,9 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
         }
       }
     }
-    if (te == 0) tc::tma_store_wait_all();
+    // the staging tiles must outlive the bulk stores' READS only; the writes are complete by the
+    // time the grid is (what a dependent launch waits for), like the attention kernels' exits
+    if (te == 0) tc::tma_store_wait_read();
   }
   tc::tc_fence_before();
   if (CTA2) tc::cluster_sync(); else __syncthreads();   // the peer may still signal our barriers

@@ -9,22 +9,28 @@ per-rank gradients reproduces the single-process full-batch gradient up to fp32 
 Mechanics: parameters are packed into flat float32 buckets in the order their gradients become
 ready (observed during the first backward, like DDP's bucket rebuild; parameters that never
 receive a gradient, e.g. the first-layer ``c`` of each chain, are left out identically on all
-ranks).  The fused block backward writes its weight gradients straight into their slots
-(``ops.register_grad_dest``; the buckets are zero-filled once per backward so the split-K
-reduce-add needs no fills of its own; one writer per slot and backward — a shared weight's second
-gradient goes through autograd's normal accumulation); a post-accumulate hook copies every other
-gradient into its slot and re-points ``p.grad`` at it.  When a bucket is full its all-reduce is
-issued asynchronously on a side stream, so it overlaps the rest of backward, also under CUDA-graph
-capture.  ``finish()`` joins the collectives.  The loss is pre-scaled by 1/world so a SUM reduction yields
-the average (gloo has no AVG).
+ranks).  The fused blocks accumulate ALL their parameter gradients into one zero-filled buffer;
+a block declares that buffer's layout (``module.mmemo_grad_unit()``) and the reducer places the
+whole unit in a bucket with the block's own offsets, so the block's buffer IS a bucket region
+(``ops.register_zbuf_dest``): the buckets are zero-filled once per backward, no block fills or
+copies anything, and ``p.grad`` of every block parameter is a view of its bucket (one writer per
+region and backward — a shared block's second use goes through autograd's normal accumulation).
+Other gradients are copied into their slots by a post-accumulate hook.  When a bucket is full its
+all-reduce is issued asynchronously on a side stream, so it overlaps the rest of backward, also
+under CUDA-graph capture.  ``finish()`` joins the collectives.  The loss is pre-scaled by 1/world
+so a SUM reduction yields the average (gloo has no AVG).
 
 Transport: on CUDA the buckets are carved out of ONE symmetric-memory allocation
 (``torch.distributed._symmetric_memory``: same layout on every rank, peer and NVLS multicast
 mappings) and reduced by libmmemo's own two-shot kernel (csrc/allreduce.cu) on a side stream:
 ``multimem.ld_reduce`` lets the NVSwitch sum a slice across all replicas, ``multimem.st``
-broadcasts it back.  The kernel uses no shared memory and a handful of CTAs, so it co-resides
-with the persistent GEMM CTAs of backward instead of taking SMs from them the way NCCL's
-kernels do.  ``transport="nccl"`` (and every CPU/gloo run) uses ``dist.all_reduce`` per bucket.
+broadcasts it back.  Its CTAs (256 threads, <= 96 registers, no shared memory) fit next to a
+persistent GEMM or attention CTA on the same SM; the LayerNorm backward fills the register file,
+so while a bucket is in flight the one-CTA-per-SM kernels of the compute stream shrink their
+grids by ``symm_sm_reserve`` SMs (``mmemo_stream_set_sm_budget``) instead of queueing statically
+partitioned work behind the collective.  Measured on 2 GPUs (profiles/r02_dp_sweep_2gpu.log):
+step with / without the collectives 1.62 / 1.53 ms, against 1.55 ms on one GPU.
+``transport="nccl"`` (and every CPU/gloo run) uses ``dist.all_reduce`` per bucket.
 """
 from __future__ import annotations
 
