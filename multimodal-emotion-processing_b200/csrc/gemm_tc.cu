@@ -141,8 +141,8 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
       sp = 0;
       it.pos += kb_end - kb_beg;
     } else {
-      sp = lw % a.splits;
-      tile = lw / a.splits;
+      if (a.splits == 1) { sp = 0; tile = lw; }          // (no integer division on the common path)
+      else { sp = lw % a.splits; tile = lw / a.splits; }
       kb_beg = sp * a.kb_per;
       kb_end = min(a.kb_total, kb_beg + a.kb_per);
       it.pos += units;
@@ -150,7 +150,10 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
     return true;
   };
   auto tile_origin = [&](const TcArgs& a, int tile, int& m0, int& n0) {
-    const int tm = tile / a.tiles_n, tn = tile - tm * a.tiles_n;
+    int tm, tn;
+    if (a.tiles_n == 1) { tm = tile; tn = 0; }
+    else if (a.tiles_n == 2) { tm = tile >> 1; tn = tile & 1; }
+    else { tm = tile / a.tiles_n; tn = tile - tm * a.tiles_n; }
     m0 = tm * TM + (int)rank * BM;     // rows owned by this CTA
     n0 = tn * BN;                      // first column of the (pair) tile
   };
