@@ -8,6 +8,11 @@
 //       half of the accumulator.  Bytes staged per flop are half those of a 128 x 128 tile — the
 //       128 x 128 version was L2-bandwidth-bound (profiles/).
 //   CTA2 = false: one CTA per 128 x 128 tile (small N, and the ragged shapes).
+//   LITE (CTA2 = false only): the same kernel with a 2-stage ring and one 32 KB bf16 staging tile
+//       (98 KB, 256 TMEM columns): TWO CTAs per SM.  The small-K grouped launches of the d <= 192
+//       models are bound by the epilogue's dependent chain (TMEM load -> math -> st.shared ->
+//       fence -> barrier -> TMA store, ncu: 3/4 of the stall samples) with the loads idle; a
+//       second resident CTA runs its loads / MMAs / epilogue in the gaps of the first.
 //
 //   warp 0   TMA producer : cp.async.bulk.tensor (SWIZZLE_128B) into a 5-stage shared-memory ring
 //   warp 1   MMA issuer   : one thread (of the leader CTA) issues the UMMAs into one of TWO TMEM
@@ -36,11 +41,16 @@
 namespace {
 
 constexpr int BM = 128, BK = 64, STAGES = 5;
+constexpr int STAGES_FULL = STAGES;
 constexpr uint32_t A_TILE = BM * BK * 2, B_TILE = 128 * BK * 2;   // per CTA per stage: 16 KB + 16 KB
 constexpr uint32_t RING = STAGES * (A_TILE + B_TILE);             // 160 KB
 constexpr uint32_t OUT_BYTES = 64 * 1024;    // fp32 staging (128x128), or bf16 staging + aux tile
+constexpr uint32_t OUT_FULL = OUT_BYTES;
 constexpr int NTHREADS = 320;   // TMA warp, MMA warp, two epilogue warpgroups
 constexpr uint32_t SMEM_BYTES = RING + OUT_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 512 /*bias*/;
+constexpr int LITE_STAGES = 2;
+constexpr uint32_t LITE_OUT = 32 * 1024;
+constexpr uint32_t SMEM_LITE = LITE_STAGES * (A_TILE + B_TILE) + LITE_OUT + 1024 + 256 + 512;
 constexpr int AUX_NONE = 0, AUX_ACC = 1, AUX_RELU = 2;
 
 struct TcArgs {
@@ -76,9 +86,13 @@ template <int NG> struct GroupArgs {
   TcArgs p[NG];
 };
 
-template <bool CTA2, int NG, int FAM>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <bool CTA2, int NG, int FAM, bool LITE = false>
+__global__ void __launch_bounds__(NTHREADS, LITE ? 2 : 1)
 gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant__ GroupArgs<NG> G) {
+  static_assert(!(LITE && CTA2), "the two-CTA-per-SM variant is single-CTA tiles only");
+  constexpr int STAGES = LITE ? LITE_STAGES : STAGES_FULL;
+  constexpr uint32_t RING = STAGES * (A_TILE + B_TILE);
+  constexpr uint32_t OUT_BYTES = LITE ? LITE_OUT : OUT_FULL;
   constexpr int BN = CTA2 ? 256 : 128;        // accumulator columns per tile
   constexpr int TM = CTA2 ? 256 : 128;        // output rows per work item (pair or CTA)
   constexpr int NHALF = BN / 128;             // epilogue works on 128 columns at a time
@@ -310,7 +324,7 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
         // bf16 tiles (32 KB) alternate between the two 32 KB staging buffers when no problem of
         // the launch needs the second one for aux tiles: the store of the previous step may then
         // still be reading its buffer while this step fills the other one
-        const bool alt = !out_f32 && !G.any_aux;
+        const bool alt = !LITE && !out_f32 && !G.any_aux;
         const uint32_t sO = sOut + ((alt && (step & 1)) ? 32 * 1024 : 0);
         if (te == 0) {
           if (alt && !prev_f32) tc::tma_store_wait_read1();
@@ -562,6 +576,8 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, NG, FAM>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  MM_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, NG, FAM, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_LITE));
   const MmStreamCfg scfg = mm_stream_cfg(st);    // this stream's workspace / SM budget / PDL
   float* const ws = scfg.ws;
   const size_t ws_bytes = scfg.ws_bytes;
@@ -708,8 +724,20 @@ int gemm_tc_grouped_t(const GemmArgs* gs, const int* c_bf16s, int n, cudaStream_
     mmemo_set_error("cuTensorMapEncodeTiled failed (gemm_tc)", __FILE__, __LINE__);
     return MMEMO_ERR_CUDA;
   }
-  const int units = streamk ? (int)cdiv(items, kb_per_unit) : (items < units_max ? items : units_max);
-  if (cta2) {
+  // two CTAs per SM (LITE) for launches of bf16 tiles with no auxiliary tile and more than one
+  // tile per SM: one CTA's epilogue chain overlaps the other's loads and MMAs
+  bool lite = !cta2 && !streamk && splits == 1 && !G.any_aux && items > units_max;
+  for (int i = 0; i < n && lite; ++i) lite = c_bf16s[i] != 0;
+  {
+    const char* env = getenv("MMEMO_GEMM_LITE");        // A/B knob: 0 = one CTA per SM
+    if (env && env[0] == '0') lite = false;
+  }
+  const int cap = lite ? 2 * units_max : units_max;
+  const int units = streamk ? (int)cdiv(items, kb_per_unit) : (items < cap ? items : cap);
+  if (lite) {
+    MM_CUDA_OK(mm_launch(gemm_tc_kernel<false, NG, FAM, true>, dim3((unsigned)units),
+                         dim3(NTHREADS), SMEM_LITE, st, tms, G));
+  } else if (cta2) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * units));
     cfg.blockDim = dim3(NTHREADS);
