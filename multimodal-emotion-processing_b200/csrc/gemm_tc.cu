@@ -126,11 +126,12 @@ gemm_tc_kernel(const __grid_constant__ TmapGroup<NG> TMS, const __grid_constant_
   // of k-blocks); one accumulator pass each.
   //   regular : items (tile, split-K slice) numbered problem by problem; unit u takes items
   //             u, u + units, ...
-  //   stream-K: (weight gradients: few output tiles, long K, fp32 C summed by TMA reduce-add) the
-  //             k-blocks of ALL tiles of all problems form one line, cut into `units` equal
-  //             ranges; a unit's range covers the tail of one tile and the head of the next, so
-  //             every unit gets the same number of MMAs whatever the tile count (32 tiles on 74
-  //             pairs: 86 % -> 99 % of the pairs busy).
+  //   stream-K: (grouped weight gradients: one or two output tiles per problem, K of very
+  //             different lengths, fp32 C summed by TMA reduce-add) the k-blocks of ALL tiles of
+  //             all problems form one line, cut into `units` equal ranges; a unit's range covers
+  //             the tail of one tile and the head of the next, so every unit gets the same number
+  //             of MMAs whatever the tile count and the K of each problem (the host decides when:
+  //             gemm_tc_grouped_t).
   struct WorkIter { int pos, end, g; };
   auto iter_init = [&](WorkIter& it) {
     it.g = 0;

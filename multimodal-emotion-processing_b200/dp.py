@@ -402,3 +402,6 @@ class GradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        if self.buckets:      # the fused backward must stop writing into this reducer's buckets
+            from . import ops
+            ops.unregister_grad_dests([b.flat for b in self.buckets])

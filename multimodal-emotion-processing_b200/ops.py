@@ -254,6 +254,15 @@ def clear_grad_dest() -> None:
     _zbuf_dest.clear()
 
 
+def unregister_grad_dests(flats: Sequence[Tensor]) -> None:
+    """Forget every destination that lives in one of ``flats`` (a reducer that goes away must not
+    leave entries keyed by parameter addresses a later model could reuse)."""
+    ids = {id(f) for f in flats}
+    for reg in (_grad_dest, _zbuf_dest):
+        for k in [k for k, v in reg.items() if id(v[0]) in ids]:
+            del reg[k]
+
+
 # The fused full block accumulates ALL its parameter gradients (five weight gradients + the small
 # "+=" outputs) into one zero-filled buffer ("zbuf", layout: full_block_grad_layout).  Under data
 # parallelism the reducer gives every block a contiguous bucket region with that layout and

@@ -225,6 +225,41 @@ def test_fused_adamw_host_logic(monkeypatch):
     assert mo.Adam([w1]).param_groups[0]["weight_decay"] == 0.0
 
 
+def test_block_gradient_regions_are_claimed_once_and_forgotten_with_their_reducer():
+    """ops.claim_zbufs: the bucket regions of a GROUP of blocks are handed out all-or-nothing, once
+    per backward, only while the reducer has zero-filled them; unregister_grad_dests drops every
+    destination that lives in a removed reducer's buckets."""
+    k1, k2 = torch.nn.Parameter(torch.zeros(2, 2)), torch.nn.Parameter(torch.zeros(2, 2))
+    other = torch.nn.Parameter(torch.zeros(3))
+    flat_a, flat_b = torch.zeros(256), torch.zeros(256)
+    ops.clear_grad_dest()
+    ops.register_zbuf_dest(k1, flat_a, 0, 100)
+    ops.register_zbuf_dest(k2, flat_a, 128, 100)
+    ops.register_grad_dest(other, flat_b, 32)
+    try:
+        ops.grad_dest_enabled, ops.grad_dest_zeroed = True, False
+        ops.begin_backward()
+        assert ops.claim_zbufs([k1, k2], 100) is None                  # buckets not zero-filled
+        ops.grad_dest_zeroed = True
+        assert ops.claim_zbufs([k1, other], 100) is None               # one block has no region
+        assert ops.claim_zbufs([k1, k2], 96) is None                   # layout mismatch
+        z = ops.claim_zbufs([k1, k2], 100)
+        assert [t.data_ptr() for t in z] == [flat_a.data_ptr(), flat_a[128:].data_ptr()]
+        assert all(t.numel() == 100 for t in z)
+        assert ops.claim_zbufs([k1, k2], 100) is None                  # second use in this backward
+        ops.begin_backward()
+        assert ops.claim_zbufs([k2], 100) is not None
+        ops.unregister_grad_dests([flat_a])
+        ops.begin_backward()
+        assert ops.claim_zbufs([k2], 100) is None and ops._dest(other) is not None
+        ops.unregister_grad_dests([flat_b])
+        assert ops._dest(other) is None
+    finally:
+        ops.grad_dest_zeroed = False
+        ops.clear_grad_dest()
+        ops.begin_backward()
+
+
 def test_bucket_slot_is_written_once_per_backward():
     """A weight that is used twice in one forward (shared module) must not have both gradients
     written into the same data-parallel bucket slot: the second use gets a fresh buffer and
