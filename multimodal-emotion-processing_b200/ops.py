@@ -42,7 +42,8 @@ def _p(t: Optional[Tensor]) -> Optional[int]:
 # Launch settings live with the STREAM in libmmemo (mmemo_stream_set_*): the first launch on a
 # stream attaches a split-K scratch buffer of its own (launches of one stream are ordered and can
 # share it; two streams never do), so concurrent streams - the ensemble's side streams, a capture
-# stream next to the default stream - are independent.
+# stream next to the default stream - are independent.  The buffers live as long as the process:
+# a captured CUDA graph keeps the pointer of the stream it was captured on.
 _stream_ws: dict = {}
 WORKSPACE_BYTES = 32 << 20
 _PDL_OFF = os.environ.get("MMEMO_PDL", "1") == "0"     # debugging knob: fully serialised launches
