@@ -795,12 +795,24 @@ int fwd_grouped(int n, const void* const* res, const void* const* x, const float
     mmax = M[i] > mmax ? M[i] : mmax;
   }
   if (mmax == 0) return MMEMO_OK;
-  // ~6 CTAs (48 warps) per SM over the whole group; narrow rows share a warp (LPR lanes per row)
+  // narrow rows share a warp (LPR lanes per row)
   const int nchunk = (int)(d / V);
   const int rpw = nchunk <= 8 ? 4 : (nchunk <= 16 ? 2 : 1);
-  const dim3 grid(ln_share_ctas(tb, n, M, LN_WARPS * rpw, 148 * 6));
   const int nch = (int)cdiv(nchunk, 32);
-#define MM_G(NCH_, LPR_) MM_CUDA_OK(mm_launch(ln_fwd_vec_grouped<T, NCH_, LPR_>, grid, dim3(LN_WARPS * 32), 0, st, tb, (int)d, eps, relu))
+  // the grid is ONE wave of resident CTAs (registers allow 3 ... 8 per SM, by instantiation): the
+  // rows are shared out evenly, so CTAs of a partial second wave would finish a whole CTA-time late
+#define MM_G(NCH_, LPR_)                                                                          \
+  do {                                                                                            \
+    static thread_local int occ = 0;                                                              \
+    if (!occ) {                                                                                   \
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                          \
+              &occ, ln_fwd_vec_grouped<T, NCH_, LPR_>, LN_WARPS * 32, 0) != cudaSuccess || occ < 1) \
+        occ = 4;                                                                                  \
+    }                                                                                             \
+    const dim3 grid(ln_share_ctas(tb, n, M, LN_WARPS * rpw, 148 * (int64_t)occ));                 \
+    MM_CUDA_OK(mm_launch(ln_fwd_vec_grouped<T, NCH_, LPR_>, grid, dim3(LN_WARPS * 32), 0, st, tb, \
+                         (int)d, eps, relu));                                                     \
+  } while (0)
   if (rpw == 4) MM_G(1, 8); else if (rpw == 2) MM_G(1, 16);
   else if (nch <= 1) MM_G(1, 32); else if (nch <= 2) MM_G(2, 32); else if (nch <= 4) MM_G(4, 32);
   else MM_G(8, 32);
