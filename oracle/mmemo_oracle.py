@@ -4,7 +4,8 @@ This file is a functional restatement (plain torch on CPU, weights passed as a f
 ``dict[str, Tensor]`` keyed by the reference's ``state_dict`` names) of the algorithm that the
 reference implements inside its ``nn.Module`` classes.  It exists to *check* the CUDA path; the
 product never imports it.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
-``cpu_baseline`` / ``--impl reference`` legs may import it.
+``cpu_baseline`` / ``gpu_eager_baseline`` / ``--impl reference`` legs (the baselines the product is
+measured AGAINST) may import it.
 
 Pinning: the reference ships no tests or golden vectors for this path ("parity unpinned" by the
 reference itself).  The oracle is therefore pinned against *outputs of the reference's own classes*
