@@ -619,7 +619,9 @@ int mmemo_colsum_grouped_bf16(int n, const void* const* x, float* const* out, co
   }
   if (mmax == 0) return MMEMO_OK;
   const int64_t groups = cdiv(N, 256);
-  int64_t strips = cdiv(148 * 2, groups * n);
+  // ~6 CTAs of 8 warps per SM over the whole group: with 2 the launch was latency-bound (the
+  // nine chains of a trunk layer, N = 192: 36 rows per warp in turn; cfg 1a step 1.335 -> 1.322 ms)
+  int64_t strips = cdiv(148 * 6, groups * n);
   if (strips > cdiv(mmax, 32)) strips = cdiv(mmax, 32);
   if (strips < 1) strips = 1;
   MM_CUDA_OK(mm_launch(colsum_bf16_vec_grouped_kernel,
